@@ -1,0 +1,9 @@
+"""avxwindowfmindex_b200 — B200-native (sm_100a) batched exact-match k-mer search for AwFmIndex.
+
+Only the hot path of TravisWheelerLab/AvxWindowFmIndex is here: awFmParallelSearchCount / awFmParallelSearchLocate
+over an AwFmKmerSearchList, on an unchanged `.awfmi` index.  The product is csrc/libawfm_b200.so (hand-written
+CUDA + C-ABI, include/awfm_gpu.h, include/awfm_abi.h); the Python modules are a ctypes veneer for tests and bench.
+"""
+from . import abi, capi, index, search, synth  # noqa: F401
+from .index import IndexArrays, read_awfmi, write_awfmi  # noqa: F401
+from .search import GpuIndex, KmerSearchList, parallel_search_count, parallel_search_locate  # noqa: F401

@@ -1,0 +1,89 @@
+"""Loader for csrc/libawfm_b200.so and prototypes of every symbol include/awfm_gpu.h and include/awfm_abi.h declare.
+
+The library is built in-tree by `__graft_entry__.build()` (or `make -C avxwindowfmindex_b200/csrc`).  There is no
+fallback of any kind: a missing library raises ImportError-like RuntimeError, a missing GPU makes calls fail.
+"""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libawfm_b200.so")
+
+GPU_SYMBOLS = [
+    "awfm_gpu_last_error", "awfm_gpu_device_count", "awfm_gpu_ctx_create", "awfm_gpu_ctx_create_from_device",
+    "awfm_gpu_ctx_destroy", "awfm_gpu_ctx_device_bytes", "awfm_gpu_ctx_get_stats", "awfm_gpu_ctx_set_tuning",
+    "awfm_gpu_count_host", "awfm_gpu_locate_host", "awfm_gpu_count_device", "awfm_gpu_scan_ranges_device",
+    "awfm_gpu_locate_device", "awfm_gpu_search_list_count", "awfm_gpu_search_list_locate",
+    "awfm_gpu_gather_bandwidth",
+]
+DROPIN_SYMBOLS = [
+    "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",
+    "awFmGpuReleaseIndex", "awFmGpuPrepareIndex", "awFmGpuLastCountStatus",
+]
+
+_lib = None
+
+
+class AwfmGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"awfm_gpu error {code}: {message}")
+        self.code = code
+
+
+def declare_search_list_api(lib):
+    """Prototypes of the four reference entry points (src/AwFmIndex.h:308,326-327,364-367,400-403); works for the
+    drop-in library and for the compiled reference alike."""
+    lib.awFmCreateKmerSearchList.restype = C.POINTER(abi.AwFmKmerSearchList)
+    lib.awFmCreateKmerSearchList.argtypes = [C.c_size_t]
+    lib.awFmDeallocKmerSearchList.restype = None
+    lib.awFmDeallocKmerSearchList.argtypes = [C.POINTER(abi.AwFmKmerSearchList)]
+    lib.awFmParallelSearchCount.restype = None
+    lib.awFmParallelSearchCount.argtypes = [C.c_void_p, C.POINTER(abi.AwFmKmerSearchList), C.c_uint32]
+    lib.awFmParallelSearchLocate.restype = C.c_int
+    lib.awFmParallelSearchLocate.argtypes = [C.c_void_p, C.POINTER(abi.AwFmKmerSearchList), C.c_uint32]
+    return lib
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the search path.")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+    vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
+    lib.awfm_gpu_last_error.restype = C.c_char_p
+    lib.awfm_gpu_device_count.restype = C.c_int
+    lib.awfm_gpu_ctx_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(abi.awfm_index_view)]
+    lib.awfm_gpu_ctx_create_from_device.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(abi.awfm_index_view)]
+    lib.awfm_gpu_ctx_destroy.argtypes = [vp]
+    lib.awfm_gpu_ctx_destroy.restype = None
+    lib.awfm_gpu_ctx_device_bytes.argtypes = [vp]
+    lib.awfm_gpu_ctx_device_bytes.restype = u64
+    lib.awfm_gpu_ctx_get_stats.argtypes = [vp, C.POINTER(abi.awfm_gpu_stats)]
+    lib.awfm_gpu_ctx_set_tuning.argtypes = [vp, C.c_char_p, i64]
+    lib.awfm_gpu_count_host.argtypes = [vp, vp, vp, u32, u64, vp, vp]
+    lib.awfm_gpu_locate_host.argtypes = [vp, vp, vp, u32, u64, vp, vp, u64, vp]
+    lib.awfm_gpu_count_device.argtypes = [vp, vp, vp, u32, u64, vp, vp, vp]
+    lib.awfm_gpu_scan_ranges_device.argtypes = [vp, vp, u64, vp, vp]
+    lib.awfm_gpu_locate_device.argtypes = [vp, vp, vp, u64, u64, u64, vp, vp]
+    lib.awfm_gpu_search_list_count.argtypes = [vp, vp, u64, u32]
+    lib.awfm_gpu_search_list_locate.argtypes = [vp, vp, u64, u32]
+    lib.awfm_gpu_gather_bandwidth.argtypes = [C.c_int, u64, u32, u64, C.c_int, C.POINTER(C.c_double)]
+    declare_search_list_api(lib)
+    lib.awFmGpuReleaseIndex.argtypes = [vp]
+    lib.awFmGpuReleaseIndex.restype = None
+    lib.awFmGpuPrepareIndex.argtypes = [vp]
+    lib.awFmGpuPrepareIndex.restype = C.c_int
+    lib.awFmGpuLastCountStatus.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise AwfmGpuError(code, load().awfm_gpu_last_error().decode("utf-8", "replace"))

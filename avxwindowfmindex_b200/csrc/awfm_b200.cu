@@ -1,0 +1,813 @@
+// awfm_b200.cu — C-ABI (include/awfm_gpu.h) over the sm_100a kernels: index residency, launch dispatch,
+// packed-batch host/device entry points, and the pipelined search-list engine used by the drop-in shim.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Xcompiler -fPIC,-fopenmp -shared
+// There is NO CPU fallback anywhere in this file: every entry point fails when CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <omp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/awfm_gpu.h"
+#include "awfm_kernels.cuh"
+
+using namespace awfm;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string gLastError;
+static int fail(int code, const char *what, const char *detail = nullptr) {
+  gLastError = what;
+  if (detail) {
+    gLastError += ": ";
+    gLastError += detail;
+  }
+  return code;
+}
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      cudaGetLastError();                                                                            \
+      return fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC                               \
+                  : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? AWFM_GPU_ERR_NO_DEVICE \
+                                                                                   : AWFM_GPU_ERR_CUDA, \
+                  #call, cudaGetErrorString(e_));                                                    \
+    }                                                                                                \
+  } while (0)
+
+extern "C" const char *awfm_gpu_last_error(void) { return gLastError.c_str(); }
+extern "C" int awfm_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+struct PipeSlot {  // one in-flight chunk of the search-list engine
+  uint8_t *hLetters = nullptr, *dLetters = nullptr;
+  uint64_t lettersCap = 0;
+  uint64_t *hOffsets = nullptr, *dOffsets = nullptr;
+  uint32_t *hCounts = nullptr, *dCounts = nullptr;
+  uint4 *dRanges = nullptr;
+  uint64_t queryCap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint64_t first = 0, n = 0;
+  bool busy = false;
+};
+
+struct awfm_gpu_ctx {
+  int device = 0, numSMs = 0;
+  DevIndex ix{};
+  void *dLines = nullptr, *dXBase = nullptr, *dSeed = nullptr, *dSa = nullptr;
+  uint64_t deviceBytes = 0;
+  bool hasSa = false;
+  // tuning
+  int countLpq = 8, locateLpq = 8, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
+  int64_t chunkQueries = 1 << 21;
+  // scratch
+  void *scanTemp = nullptr;
+  size_t scanTempBytes = 0;
+  uint64_t *dLengths = nullptr;
+  uint64_t lengthsCap = 0;
+  std::vector<EventPair> kernelEvents;  // of the most recent call
+  size_t eventsUsed = 0;
+  awfm_gpu_stats stats{};
+  PipeSlot slots[3];
+  std::mutex mu;
+};
+
+static int setDevice(const awfm_gpu_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  return AWFM_GPU_OK;
+}
+
+static uint64_t numSeedsOf(uint8_t alphabet, uint8_t k) {
+  uint64_t n = 1;
+  for (int i = 0; i < k; i++) n *= (alphabet == 1 ? 20u : 4u);
+  return n;
+}
+
+static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view *v, bool fromDevice) {
+  if (!out || !v || !v->blocks || !v->prefixSums || !v->seedTable) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (v->alphabet < 1 || v->alphabet > 3) return fail(AWFM_GPU_ERR_ARG, "alphabetType must be 1 (amino), 2 (DNA) or 3 (RNA)");
+  if (v->bwtLength < 2 || v->numBlocks != 1 + (v->bwtLength - 1) / 256) return fail(AWFM_GPU_ERR_ARG, "numBlocks does not match bwtLength");
+  if (v->saBytes && (v->saRatio == 0 || v->saBitWidth == 0 || v->saBitWidth > 64)) return fail(AWFM_GPU_ERR_ARG, "bad SA ratio / bit width");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(AWFM_GPU_ERR_NO_DEVICE, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  awfm_gpu_ctx *c = new awfm_gpu_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->numSMs = prop.multiProcessorCount;
+  const bool amino = v->alphabet == 1;
+  const uint32_t rawBlockBytes = amino ? 352u : 160u;
+  const uint32_t numPrefix = amino ? 22u : 6u;
+  const cudaMemcpyKind kind = fromDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  auto bail = [&](int code) {
+    awfm_gpu_ctx_destroy(c);
+    return code;
+  };
+#define CUB_(call)                                                     \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) {                                           \
+      cudaGetLastError();                                              \
+      return bail(fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, #call, cudaGetErrorString(e_))); \
+    }                                                                  \
+  } while (0)
+
+  // blocks -> lines.  The raw copy is staged in slabs so peak extra memory stays small next to a 180 GB HBM.
+  const uint64_t lineBytes = amino ? 384u : 128u;
+  CUB_(cudaMalloc(&c->dLines, v->numBlocks * lineBytes));
+  c->deviceBytes += v->numBlocks * lineBytes;
+  if (!amino) {
+    CUB_(cudaMalloc(&c->dXBase, v->numBlocks * 8));
+    c->deviceBytes += v->numBlocks * 8;
+  }
+  {
+    const uint64_t slabBlocks = std::min<uint64_t>(v->numBlocks, 1u << 20);  // <= 352 MB staging
+    uint8_t *dRaw = nullptr;
+    CUB_(cudaMalloc(&dRaw, slabBlocks * rawBlockBytes));
+    for (uint64_t b0 = 0; b0 < v->numBlocks; b0 += slabBlocks) {
+      const uint64_t nb = std::min(slabBlocks, v->numBlocks - b0);
+      cudaError_t e = cudaMemcpy(dRaw, (const uint8_t *)v->blocks + b0 * rawBlockBytes, nb * rawBlockBytes, kind);
+      if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)((nb + 255) / 256);
+        if (amino) relayoutAmino<<<grid, 256>>>(dRaw, nb, (uint4 *)c->dLines + b0 * kAminoLineU4);
+        else relayoutNucleotide<<<grid, 256>>>(dRaw, nb, (uint4 *)c->dLines + b0 * kNucLineU4, (uint64_t *)c->dXBase + b0);
+        e = cudaDeviceSynchronize();
+      }
+      if (e != cudaSuccess) {
+        cudaFree(dRaw);
+        CUB_(e);
+      }
+    }
+    cudaFree(dRaw);
+  }
+  // seed table
+  const uint64_t numSeeds = numSeedsOf(v->alphabet, v->seedK);
+  CUB_(cudaMalloc(&c->dSeed, numSeeds * 16));
+  CUB_(cudaMemcpy(c->dSeed, v->seedTable, numSeeds * 16, kind));
+  c->deviceBytes += numSeeds * 16;
+  // sampled SA (+ zero padding so the two-word read never leaves the allocation)
+  if (v->saBytes) {
+    const uint64_t padded = ((v->saByteLength + 15) & ~15ull) + 16;
+    CUB_(cudaMalloc(&c->dSa, padded));
+    CUB_(cudaMemset(c->dSa, 0, padded));
+    CUB_(cudaMemcpy(c->dSa, v->saBytes, v->saByteLength, kind));
+    c->deviceBytes += padded;
+    c->hasSa = true;
+  }
+  DevIndex &ix = c->ix;
+  ix.lines = (const uint4 *)c->dLines;
+  ix.xBase = (const uint64_t *)c->dXBase;
+  ix.seedTable = (const uint4 *)c->dSeed;
+  ix.sa = (const uint64_t *)c->dSa;
+  ix.numBlocks = v->numBlocks;
+  ix.bwtLength = v->bwtLength;
+  ix.numSeeds = numSeeds;
+  memset(ix.prefixSums, 0, sizeof ix.prefixSums);
+  if (fromDevice) CUB_(cudaMemcpy(ix.prefixSums, v->prefixSums, numPrefix * 8, cudaMemcpyDeviceToHost));
+  else memcpy(ix.prefixSums, v->prefixSums, numPrefix * 8);
+  ix.saBitWidth = v->saBitWidth;
+  ix.saRatio = v->saRatio ? v->saRatio : 1;
+  ix.saRatioShift = 0xFFFFFFFFu;
+  if ((ix.saRatio & (ix.saRatio - 1)) == 0) {
+    ix.saRatioShift = 0;
+    while ((1u << ix.saRatioShift) < ix.saRatio) ix.saRatioShift++;
+  }
+  ix.seedK = v->seedK;
+  ix.amino = amino;
+  for (auto &s : c->slots) {
+    CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+#undef CUB_
+  *out = c;
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_ctx_create(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view) {
+  return ctxCreateCommon(ctx, device, view, false);
+}
+extern "C" int awfm_gpu_ctx_create_from_device(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view) {
+  return ctxCreateCommon(ctx, device, view, true);
+}
+
+static void freeSlot(PipeSlot &s) {
+  if (s.hLetters) cudaFreeHost(s.hLetters);
+  if (s.hOffsets) cudaFreeHost(s.hOffsets);
+  if (s.hCounts) cudaFreeHost(s.hCounts);
+  cudaFree(s.dLetters);
+  cudaFree(s.dOffsets);
+  cudaFree(s.dCounts);
+  cudaFree(s.dRanges);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  if (s.done) cudaEventDestroy(s.done);
+  s = PipeSlot();
+}
+
+extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto &s : c->slots) freeSlot(s);
+  for (auto &e : c->kernelEvents) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  cudaFree(c->dLines);
+  cudaFree(c->dXBase);
+  cudaFree(c->dSeed);
+  cudaFree(c->dSa);
+  cudaFree(c->scanTemp);
+  cudaFree(c->dLengths);
+  cudaGetLastError();
+  delete c;
+}
+
+extern "C" uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *c) { return c ? c->deviceBytes : 0; }
+
+extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t value) {
+  if (!c || !key) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  const std::string k(key);
+  auto lpqOk = [](int64_t v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+  if (k == "count_lpq" && lpqOk(value)) c->countLpq = (int)value;
+  else if (k == "locate_lpq" && lpqOk(value)) c->locateLpq = (int)value;
+  else if (k == "count_variant" && (value == 0 || value == 1)) c->countVariant = (int)value;
+  else if (k == "chunk_queries" && value >= 1024) c->chunkQueries = value;
+  else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
+  else return fail(AWFM_GPU_ERR_ARG, "unknown tuning key or bad value", key);
+  return AWFM_GPU_OK;
+}
+
+// ---- kernel event bookkeeping (device time of OUR kernels on the launching stream) ----
+static void beginCall(awfm_gpu_ctx *c) {
+  c->eventsUsed = 0;
+  c->stats = awfm_gpu_stats{};
+}
+static EventPair *nextEvents(awfm_gpu_ctx *c) {
+  if (c->eventsUsed == c->kernelEvents.size()) {
+    EventPair p;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return nullptr;
+    c->kernelEvents.push_back(p);
+  }
+  return &c->kernelEvents[c->eventsUsed++];
+}
+
+extern "C" int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *cc, awfm_gpu_stats *out) {
+  awfm_gpu_ctx *c = const_cast<awfm_gpu_ctx *>(cc);
+  if (!c || !out) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (setDevice(c)) return AWFM_GPU_ERR_CUDA;
+  double ms = 0;
+  for (size_t i = 0; i < c->eventsUsed; i++) {
+    CU(cudaEventSynchronize(c->kernelEvents[i].b));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->kernelEvents[i].a, c->kernelEvents[i].b));
+    ms += f;
+  }
+  c->stats.kernelMs = ms;
+  *out = c->stats;
+  return AWFM_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+template <typename K>
+static int gridFor(awfm_gpu_ctx *c, K kernel, int threads, int *grid) {
+  int perSm = c->blocksPerSm;
+  if (perSm == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0));
+  if (perSm < 1) perSm = 1;
+  *grid = c->numSMs * perSm;  // whole multiples of the SM count: persistent grid-stride CTAs
+  return AWFM_GPU_OK;
+}
+
+constexpr int kTile = 256, kTileLetterBytes = 8192;
+
+template <int LPQ, bool AMINO>
+static int launchCount(awfm_gpu_ctx *c, const QueryBatch &qb, uint32_t *dCounts, uint4 *dRanges, cudaStream_t st) {
+  int grid = 0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(qb.letters) & 15u) == 0;
+  if (c->countVariant == 1 && aligned) {
+    auto k = countKernelV1<LPQ, AMINO, kTile, kTileLetterBytes>;
+    if (int r = gridFor(c, k, 256, &grid)) return r;
+    const uint64_t tiles = (qb.numQueries + kTile - 1) / kTile;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, tiles);
+    k<<<grid, 256, 0, st>>>(c->ix, qb, dCounts, dRanges);
+  } else {
+    auto k = countKernelV0<LPQ, AMINO>;
+    if (int r = gridFor(c, k, 256, &grid)) return r;
+    const uint64_t need = (qb.numQueries * LPQ + 255) / 256;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, need);
+    k<<<grid, 256, 0, st>>>(c->ix, qb, dCounts, dRanges);
+  }
+  CU(cudaGetLastError());
+  return AWFM_GPU_OK;
+}
+
+template <int LPQ, bool AMINO>
+static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *dHitOffsets, uint64_t n,
+                        uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
+  int grid = 0;
+  auto k = locateKernel<LPQ, AMINO>;
+  if (int r = gridFor(c, k, 256, &grid)) return r;
+  const uint64_t need = ((he - hb) * LPQ + 255) / 256;
+  grid = (int)std::min<uint64_t>((uint64_t)grid, need);
+  k<<<grid, 256, 0, st>>>(c->ix, dRanges, dHitOffsets, n, hb, he, dPos);
+  CU(cudaGetLastError());
+  return AWFM_GPU_OK;
+}
+
+#define DISPATCH_LPQ(fn, lpq, amino, ...)                                  \
+  ((amino) ? ((lpq) == 1   ? fn<1, true>(__VA_ARGS__)                      \
+              : (lpq) == 2 ? fn<2, true>(__VA_ARGS__)                      \
+              : (lpq) == 4 ? fn<4, true>(__VA_ARGS__)                      \
+                           : fn<8, true>(__VA_ARGS__))                     \
+           : ((lpq) == 1   ? fn<1, false>(__VA_ARGS__)                     \
+              : (lpq) == 2 ? fn<2, false>(__VA_ARGS__)                     \
+              : (lpq) == 4 ? fn<4, false>(__VA_ARGS__)                     \
+                           : fn<8, false>(__VA_ARGS__)))
+
+static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
+                           uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
+  if (n == 0) return AWFM_GPU_OK;
+  QueryBatch qb{dLetters, dOffsets, n, fixedLen};
+  EventPair *ev = nextEvents(c);
+  if (ev) CU(cudaEventRecord(ev->a, st));
+  int r = DISPATCH_LPQ(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
+  if (ev) CU(cudaEventRecord(ev->b, st));
+  c->stats.launches += 1;
+  c->stats.queries += n;
+  return r;
+}
+
+extern "C" int awfm_gpu_count_device(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets,
+                                     uint32_t fixedLen, uint64_t n, uint32_t *dCounts, awfm_range *dRanges,
+                                     void *stream) {
+  if (!c || !dCounts || (n && !dLetters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = setDevice(c)) return r;
+  beginCall(c);
+  return countDeviceImpl(c, dLetters, dOffsets, fixedLen, n, dCounts, dRanges, (cudaStream_t)stream);
+}
+
+static int scanImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, uint64_t n, uint64_t *dHitOffsets, cudaStream_t st) {
+  if (c->lengthsCap < n + 1) {
+    cudaFree(c->dLengths);
+    c->dLengths = nullptr;
+    c->lengthsCap = 0;
+    CU(cudaMalloc(&c->dLengths, (n + 1) * 8));
+    c->lengthsCap = n + 1;
+  }
+  size_t need = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, need, c->dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
+  if (need > c->scanTempBytes) {
+    cudaFree(c->scanTemp);
+    c->scanTemp = nullptr;
+    c->scanTempBytes = 0;
+    CU(cudaMalloc(&c->scanTemp, need));
+    c->scanTempBytes = need;
+  }
+  CU(cudaMemsetAsync(c->dLengths + n, 0, 8, st));
+  if (n) rangeLengths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)dRanges, n, c->dLengths);
+  CU(cudaGetLastError());
+  CU(cub::DeviceScan::ExclusiveSum(c->scanTemp, need, c->dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
+  c->stats.launches += 3;
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *c, const awfm_range *dRanges, uint64_t n,
+                                           uint64_t *dHitOffsets, void *stream) {
+  if (!c || !dHitOffsets || (n && !dRanges)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = setDevice(c)) return r;
+  return scanImpl(c, dRanges, n, dHitOffsets, (cudaStream_t)stream);
+}
+
+static int locateDeviceImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, const uint64_t *dHitOffsets, uint64_t n,
+                            uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
+  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  if (he <= hb) return AWFM_GPU_OK;
+  EventPair *ev = nextEvents(c);
+  if (ev) CU(cudaEventRecord(ev->a, st));
+  int r = DISPATCH_LPQ(launchLocate, c->locateLpq, c->ix.amino != 0, c, (const uint4 *)dRanges, dHitOffsets, n, hb,
+                       he, dPos, st);
+  if (ev) CU(cudaEventRecord(ev->b, st));
+  c->stats.launches += 1;
+  c->stats.hits += he - hb;
+  return r;
+}
+
+extern "C" int awfm_gpu_locate_device(awfm_gpu_ctx *c, const awfm_range *dRanges, const uint64_t *dHitOffsets,
+                                      uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, void *stream) {
+  if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = setDevice(c)) return r;
+  return locateDeviceImpl(c, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer calls
+struct DevBuf {  // RAII device scratch
+  void *p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+};
+
+static uint64_t totalLetters(const uint64_t *offsets, uint32_t fixedLen, uint64_t n) {
+  return offsets ? offsets[n] : n * (uint64_t)fixedLen;
+}
+
+extern "C" int awfm_gpu_count_host(awfm_gpu_ctx *c, const uint8_t *letters, const uint64_t *offsets,
+                                   uint32_t fixedLen, uint64_t n, uint32_t *counts, awfm_range *ranges) {
+  if (!c || !counts || (n && !letters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  beginCall(c);
+  if (n == 0) return AWFM_GPU_OK;
+  const uint64_t nLetters = totalLetters(offsets, fixedLen, n);
+  DevBuf dL, dO, dC, dR;
+  CU(dL.alloc(nLetters + 16));
+  CU(dC.alloc(n * 4));
+  if (offsets) CU(dO.alloc((n + 1) * 8));
+  if (ranges) CU(dR.alloc(n * 16));
+  cudaStream_t st = c->slots[0].stream;
+  CU(cudaMemcpyAsync(dL.p, letters, nLetters, cudaMemcpyHostToDevice, st));
+  if (offsets) CU(cudaMemcpyAsync(dO.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (int r = countDeviceImpl(c, (const uint8_t *)dL.p, offsets ? (const uint64_t *)dO.p : nullptr, fixedLen, n,
+                              (uint32_t *)dC.p, ranges ? (awfm_range *)dR.p : nullptr, st))
+    return r;
+  CU(cudaMemcpyAsync(counts, dC.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (ranges) CU(cudaMemcpyAsync(ranges, dR.p, n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  c->stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
+  c->stats.d2hBytes = n * 4 + (ranges ? n * 16 : 0);
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_locate_host(awfm_gpu_ctx *c, const uint8_t *letters, const uint64_t *offsets,
+                                    uint32_t fixedLen, uint64_t n, uint64_t *hitOffsets, uint64_t *positions,
+                                    uint64_t positionsCapacity, awfm_range *ranges) {
+  if (!c || !hitOffsets || (n && !letters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  if (!c->hasSa && positions) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  beginCall(c);
+  hitOffsets[0] = 0;
+  if (n == 0) return AWFM_GPU_OK;
+  const uint64_t nLetters = totalLetters(offsets, fixedLen, n);
+  DevBuf dL, dO, dC, dR, dH, dP;
+  CU(dL.alloc(nLetters + 16));
+  CU(dC.alloc(n * 4));
+  CU(dR.alloc(n * 16));
+  CU(dH.alloc((n + 1) * 8));
+  if (offsets) CU(dO.alloc((n + 1) * 8));
+  cudaStream_t st = c->slots[0].stream;
+  CU(cudaMemcpyAsync(dL.p, letters, nLetters, cudaMemcpyHostToDevice, st));
+  if (offsets) CU(cudaMemcpyAsync(dO.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (int r = countDeviceImpl(c, (const uint8_t *)dL.p, offsets ? (const uint64_t *)dO.p : nullptr, fixedLen, n,
+                              (uint32_t *)dC.p, (awfm_range *)dR.p, st))
+    return r;
+  if (int r = scanImpl(c, (const awfm_range *)dR.p, n, (uint64_t *)dH.p, st)) return r;
+  CU(cudaMemcpyAsync(hitOffsets, dH.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (ranges) CU(cudaMemcpyAsync(ranges, dR.p, n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const uint64_t total = hitOffsets[n];
+  c->stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
+  c->stats.d2hBytes = (n + 1) * 8 + (ranges ? n * 16 : 0);
+  if (!positions || total == 0) return AWFM_GPU_OK;
+  if (positionsCapacity < total) return fail(AWFM_GPU_ERR_ARG, "positions buffer smaller than hitOffsets[numQueries]");
+  // bounded device staging: at most 1 Gi hits (8 GB) per launch
+  const uint64_t batch = std::min<uint64_t>(total, 1ull << 30);
+  CU(dP.alloc(batch * 8));
+  for (uint64_t hb = 0; hb < total; hb += batch) {
+    const uint64_t he = std::min(total, hb + batch);
+    if (int r = locateDeviceImpl(c, (const awfm_range *)dR.p, (const uint64_t *)dH.p, n, hb, he, (uint64_t *)dP.p, st))
+      return r;
+    CU(cudaMemcpyAsync(positions + hb, dP.p, (he - hb) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  c->stats.d2hBytes += total * 8;
+  return AWFM_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ search-list engine
+// The reference API hands over an array of 32-B structs with pointers to arbitrary host strings
+// (src/AwFmIndex.h:111-123).  Chunks of the list are packed into pinned staging by `numThreads` host threads,
+// shipped and searched on a per-slot stream, and their counts scattered back while the next chunks are in flight.
+
+static int ensureSlot(PipeSlot &s, uint64_t queries, uint64_t letterBytes, bool wantRanges) {
+  if (s.queryCap < queries) {
+    if (s.hOffsets) cudaFreeHost(s.hOffsets);
+    if (s.hCounts) cudaFreeHost(s.hCounts);
+    cudaFree(s.dOffsets);
+    cudaFree(s.dCounts);
+    cudaFree(s.dRanges);
+    s.hOffsets = nullptr, s.hCounts = nullptr, s.dOffsets = nullptr, s.dCounts = nullptr, s.dRanges = nullptr;
+    s.queryCap = 0;
+    CU(cudaHostAlloc(&s.hOffsets, (queries + 1) * 8, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&s.hCounts, queries * 4, cudaHostAllocDefault));
+    CU(cudaMalloc(&s.dOffsets, (queries + 1) * 8));
+    CU(cudaMalloc(&s.dCounts, queries * 4));
+    s.queryCap = queries;
+  }
+  if (wantRanges && !s.dRanges) CU(cudaMalloc(&s.dRanges, s.queryCap * 16));
+  if (s.lettersCap < letterBytes) {
+    if (s.hLetters) cudaFreeHost(s.hLetters);
+    cudaFree(s.dLetters);
+    s.hLetters = nullptr, s.dLetters = nullptr;
+    s.lettersCap = 0;
+    const uint64_t cap = letterBytes + letterBytes / 4 + 64;
+    CU(cudaHostAlloc(&s.hLetters, cap, cudaHostAllocDefault));
+    CU(cudaMalloc(&s.dLetters, cap));
+    s.lettersCap = cap;
+  }
+  return AWFM_GPU_OK;
+}
+
+// Packs queries [first, first+n) into the slot's pinned staging.  Returns the uniform length, or 0 if lengths differ
+// (then hOffsets is authoritative).  Two passes so each thread knows where its letters go.
+static int packChunk(PipeSlot &s, const awfm_kmer_search_data *data, uint64_t first, uint64_t n, int threads,
+                     bool wantRanges, uint32_t *uniformLen, uint64_t *letterBytes) {
+  threads = std::max(1, std::min<int>(threads, (int)std::max<uint64_t>(1, n / 4096)));
+  std::vector<uint64_t> partSum(threads + 1, 0);
+  std::vector<uint8_t> partUniform(threads, 1);
+  const uint64_t len0 = data[first].kmerLength;
+#pragma omp parallel num_threads(threads)
+  {
+    const int t = omp_get_thread_num();
+    const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
+    uint64_t sum = 0;
+    bool uni = true;
+    for (uint64_t i = a; i < b; i++) {
+      const uint64_t l = data[first + i].kmerLength;
+      sum += l;
+      uni &= (l == len0);
+    }
+    partSum[t + 1] = sum;
+    partUniform[t] = uni;
+  }
+  for (int t = 0; t < threads; t++) partSum[t + 1] += partSum[t];
+  const uint64_t total = partSum[threads];
+  if (int r = ensureSlot(s, n, total + 16, wantRanges)) return r;
+  bool uniform = len0 <= 0xFFFFFFFFull;
+  for (int t = 0; t < threads; t++) uniform &= partUniform[t] != 0;
+  uint8_t *dst = s.hLetters;
+  uint64_t *offs = s.hOffsets;
+#pragma omp parallel num_threads(threads)
+  {
+    const int t = omp_get_thread_num();
+    const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
+    uint64_t o = partSum[t];
+    for (uint64_t i = a; i < b; i++) {
+      const awfm_kmer_search_data &d = data[first + i];
+      offs[i] = o;
+      memcpy(dst + o, d.kmerString, d.kmerLength);
+      o += d.kmerLength;
+    }
+  }
+  offs[n] = total;
+  *uniformLen = uniform ? (uint32_t)len0 : 0;
+  *letterBytes = total;
+  return AWFM_GPU_OK;
+}
+
+static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, uint32_t uniformLen, uint64_t letterBytes, bool wantRanges) {
+  const bool fixed = uniformLen != 0;
+  CU(cudaMemcpyAsync(s.dLetters, s.hLetters, letterBytes, cudaMemcpyHostToDevice, s.stream));
+  if (!fixed) CU(cudaMemcpyAsync(s.dOffsets, s.hOffsets, (s.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+  if (int r = countDeviceImpl(c, s.dLetters, fixed ? nullptr : s.dOffsets, uniformLen, s.n, s.dCounts,
+                              wantRanges ? (awfm_range *)s.dRanges : nullptr, s.stream))
+    return r;
+  c->stats.h2dBytes += letterBytes + (fixed ? 0 : (s.n + 1) * 8);
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
+                                          uint32_t numThreads) {
+  if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  beginCall(c);
+  const int threads = (int)std::max<uint32_t>(1, numThreads);
+  const uint64_t chunk = (uint64_t)c->chunkQueries;
+  constexpr int NS = 3;
+  auto retire = [&](PipeSlot &s) -> int {
+    if (!s.busy) return AWFM_GPU_OK;
+    CU(cudaEventSynchronize(s.done));
+    const uint32_t *src = s.hCounts;
+    awfm_kmer_search_data *dst = data + s.first;
+    const int64_t cnt = (int64_t)s.n;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t i = 0; i < cnt; i++) dst[i].count = src[i];  // src/AwFmParallelSearch.c:187-190
+    s.busy = false;
+    return AWFM_GPU_OK;
+  };
+  int rc = AWFM_GPU_OK;
+  uint64_t chunkIndex = 0;
+  for (uint64_t first = 0; first < n && rc == AWFM_GPU_OK; first += chunk, chunkIndex++) {
+    PipeSlot &s = c->slots[chunkIndex % NS];
+    if ((rc = retire(s))) break;
+    s.first = first;
+    s.n = std::min(chunk, n - first);
+    uint32_t uniformLen = 0;
+    uint64_t letterBytes = 0;
+    if ((rc = packChunk(s, data, first, s.n, threads, false, &uniformLen, &letterBytes))) break;
+    if ((rc = submitCount(c, s, uniformLen, letterBytes, false))) break;
+    cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+    if (e != cudaSuccess) {
+      rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
+      break;
+    }
+    c->stats.d2hBytes += s.n * 4;
+    s.busy = true;
+  }
+  // drain in submission order
+  for (int k = 0; k < NS; k++) {
+    PipeSlot &s = c->slots[(chunkIndex + k) % NS];
+    if (rc == AWFM_GPU_OK) rc = retire(s);
+    else if (s.busy) {
+      cudaEventSynchronize(s.done);
+      s.busy = false;
+    }
+  }
+  return rc;
+}
+
+extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
+                                           uint32_t numThreads) {
+  if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  beginCall(c);
+  const int threads = (int)std::max<uint32_t>(1, numThreads);
+  const uint64_t chunk = (uint64_t)c->chunkQueries;
+  PipeSlot &s = c->slots[0];
+  uint64_t *hHit = nullptr, *hPos = nullptr, *dHit = nullptr, *dPos = nullptr;
+  uint64_t hitCap = 0, posCap = 0;
+  int rc = AWFM_GPU_OK;
+  bool allocFailed = false;
+  auto cleanup = [&]() {
+    if (hHit) cudaFreeHost(hHit);
+    if (hPos) cudaFreeHost(hPos);
+    cudaFree(dHit);
+    cudaFree(dPos);
+  };
+#define CUL(call)                                                         \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess) {                                              \
+      cudaGetLastError();                                                 \
+      cleanup();                                                          \
+      return fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, #call, cudaGetErrorString(e_)); \
+    }                                                                     \
+  } while (0)
+  for (uint64_t first = 0; first < n; first += chunk) {
+    s.first = first;
+    s.n = std::min(chunk, n - first);
+    uint32_t uniformLen = 0;
+    uint64_t letterBytes = 0;
+    if ((rc = packChunk(s, data, first, s.n, threads, true, &uniformLen, &letterBytes))) break;
+    if ((rc = submitCount(c, s, uniformLen, letterBytes, true))) break;
+    if (hitCap < s.n + 1) {
+      if (hHit) cudaFreeHost(hHit);
+      cudaFree(dHit);
+      hHit = nullptr, dHit = nullptr;
+      CUL(cudaHostAlloc(&hHit, (s.n + 1) * 8, cudaHostAllocDefault));
+      CUL(cudaMalloc(&dHit, (s.n + 1) * 8));
+      hitCap = s.n + 1;
+    }
+    if ((rc = scanImpl(c, (const awfm_range *)s.dRanges, s.n, dHit, s.stream))) break;
+    CUL(cudaMemcpyAsync(hHit, dHit, (s.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUL(cudaStreamSynchronize(s.stream));
+    c->stats.d2hBytes += (s.n + 1) * 8;
+    const uint64_t total = hHit[s.n];
+    // positions are produced in bounded batches of flat hit indices
+    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(total, 1ull << 28));
+    if (posCap < batch) {
+      if (hPos) cudaFreeHost(hPos);
+      cudaFree(dPos);
+      hPos = nullptr, dPos = nullptr;
+      CUL(cudaHostAlloc(&hPos, batch * 8, cudaHostAllocDefault));
+      CUL(cudaMalloc(&dPos, batch * 8));
+      posCap = batch;
+    }
+    // counts + capacity semantics first (src/AwFmParallelSearch.c:367-387): grow to exactly `count` when too small
+    {
+      awfm_kmer_search_data *dst = data + first;
+      const int64_t cnt = (int64_t)s.n;
+      bool failed = false;
+#pragma omp parallel for num_threads(threads) schedule(static) reduction(|| : failed)
+      for (int64_t i = 0; i < cnt; i++) {
+        const uint32_t count = (uint32_t)(hHit[i + 1] - hHit[i]);
+        if (dst[i].capacity >= count) {
+          dst[i].count = count;
+        } else {
+          void *p = realloc(dst[i].positionList, (size_t)count * sizeof(uint64_t));
+          if (!p) {
+            fprintf(stderr, "Critical memory failure: could not allocate memory for position list.\n");
+            dst[i].count = 0;  // never write past the old allocation
+            failed = true;
+          } else {
+            dst[i].positionList = (uint64_t *)p;
+            dst[i].capacity = count;
+            dst[i].count = count;
+          }
+        }
+      }
+      allocFailed |= failed;
+    }
+    uint64_t qCursor = 0;  // first query whose hits may intersect the current batch
+    for (uint64_t hb = 0; hb < total; hb += batch) {
+      const uint64_t he = std::min(total, hb + batch);
+      if ((rc = locateDeviceImpl(c, (const awfm_range *)s.dRanges, dHit, s.n, hb, he, dPos, s.stream))) break;
+      CUL(cudaMemcpyAsync(hPos, dPos, (he - hb) * 8, cudaMemcpyDeviceToHost, s.stream));
+      CUL(cudaStreamSynchronize(s.stream));
+      c->stats.d2hBytes += (he - hb) * 8;
+      while (qCursor < s.n && hHit[qCursor + 1] <= hb) qCursor++;
+      uint64_t qEnd = qCursor;
+      while (qEnd < s.n && hHit[qEnd] < he) qEnd++;
+      awfm_kmer_search_data *dst = data + first;
+      const int64_t q0 = (int64_t)qCursor, q1 = (int64_t)qEnd;
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (int64_t i = q0; i < q1; i++) {
+        if (dst[i].count == 0) continue;
+        const uint64_t a = std::max(hHit[i], hb), b = std::min(hHit[i + 1], he);
+        if (a < b) memcpy(dst[i].positionList + (a - hHit[i]), hPos + (a - hb), (b - a) * 8);
+      }
+    }
+    if (rc) break;
+  }
+#undef CUL
+  cleanup();
+  if (rc == AWFM_GPU_OK && allocFailed) return fail(AWFM_GPU_ERR_ALLOC, "realloc of a position list failed");
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ gather probe
+template <int BYTES>
+static int runGather(int lanes, const uint4 *d, uint64_t numRecords, uint64_t numReads, uint64_t *sink, int grid) {
+  switch (lanes) {
+    case 1: gatherProbe<BYTES, 1><<<grid, 256>>>(d, numRecords, numReads, sink); break;
+    case 2: gatherProbe<BYTES, 2><<<grid, 256>>>(d, numRecords, numReads, sink); break;
+    case 4: gatherProbe<BYTES, 4><<<grid, 256>>>(d, numRecords, numReads, sink); break;
+    case 8: gatherProbe<BYTES, 8><<<grid, 256>>>(d, numRecords, numReads, sink); break;
+    default: return fail(AWFM_GPU_ERR_ARG, "lanesPerRead must be 1, 2, 4 or 8");
+  }
+  CU(cudaGetLastError());
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32_t bytesPerRead, uint64_t numReads,
+                                         int lanesPerRead, double *gbps) {
+  if (!gbps || arrayBytes < 4096) return fail(AWFM_GPU_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  DevBuf data, sink;
+  CU(data.alloc(arrayBytes));
+  CU(sink.alloc(64));
+  CU(cudaMemset(data.p, 1, arrayBytes));
+  const uint64_t numRecords = arrayBytes / bytesPerRead;
+  const int grid = prop.multiProcessorCount * 8;
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(a));
+    int r;
+    switch (bytesPerRead) {
+      case 16: r = runGather<16>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
+      case 32: r = runGather<32>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
+      case 64: r = runGather<64>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
+      case 128: r = runGather<128>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
+      default: r = fail(AWFM_GPU_ERR_ARG, "bytesPerRead must be 16, 32, 64 or 128");
+    }
+    if (r) return r;
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *gbps = (double)numReads * bytesPerRead / (best * 1e-3) / 1e9;
+  return AWFM_GPU_OK;
+}

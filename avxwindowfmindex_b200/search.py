@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference's batched search interface over the B200 C-ABI.
+
+Two levels, both thin:
+  * `GpuIndex`       — an index resident in HBM (awfm_gpu_ctx) with the packed-batch calls of include/awfm_gpu.h.
+  * `KmerSearchList` + `parallel_search_count` / `parallel_search_locate` — the reference's own calling
+    convention (src/AwFmIndex.h:308-403): a list of {kmerString, kmerLength, positionList, count, capacity}
+    entries handed to awFmParallelSearchCount / awFmParallelSearchLocate.  `lib` may be the drop-in
+    (capi.load()) or the compiled reference, so parity tests run the same code against both.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi, capi
+from .index import IndexArrays
+
+
+def pack_queries(queries):
+    """list of bytes -> (letters uint8, offsets uint64[n+1])"""
+    lengths = np.fromiter((len(q) for q in queries), dtype=np.uint64, count=len(queries))
+    offsets = np.zeros(len(queries) + 1, dtype=np.uint64)
+    np.cumsum(lengths, out=offsets[1:])
+    letters = np.frombuffer(b"".join(queries), dtype=np.uint8).copy() if len(queries) else np.zeros(0, np.uint8)
+    return letters, offsets
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class GpuIndex:
+    """Device-resident index.  Construction uploads and re-lays-out the arrays (see csrc/awfm_device.cuh)."""
+
+    def __init__(self, arrays: IndexArrays, device=0):
+        self.lib = capi.load()
+        self.arrays = arrays
+        self.device = device
+        self._ctx = C.c_void_p()
+        view = arrays.view()
+        capi.check(self.lib.awfm_gpu_ctx_create(C.byref(self._ctx), device, C.byref(view)))
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    def close(self):
+        if self._ctx:
+            self.lib.awfm_gpu_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tuning(self, **kv):
+        for k, v in kv.items():
+            capi.check(self.lib.awfm_gpu_ctx_set_tuning(self._ctx, k.encode(), int(v)))
+
+    def device_bytes(self):
+        return int(self.lib.awfm_gpu_ctx_device_bytes(self._ctx))
+
+    def stats(self):
+        s = abi.awfm_gpu_stats()
+        capi.check(self.lib.awfm_gpu_ctx_get_stats(self._ctx, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    # ---- packed batch, host buffers ----
+    def count(self, letters, offsets=None, fixed_len=0, want_ranges=False):
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        n = (len(offsets) - 1) if offsets is not None else (len(letters) // fixed_len if fixed_len else 0)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        ranges = np.zeros((n, 2), dtype=np.uint64) if want_ranges else None
+        capi.check(self.lib.awfm_gpu_count_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
+                                                _ptr(counts), _ptr(ranges)))
+        return (counts, ranges) if want_ranges else counts
+
+    def locate(self, letters, offsets=None, fixed_len=0, want_ranges=False):
+        """CSR result: (hit_offsets uint64[n+1], positions uint64[total]) in SA order within each query."""
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        n = (len(offsets) - 1) if offsets is not None else (len(letters) // fixed_len if fixed_len else 0)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        hit_offsets = np.zeros(n + 1, dtype=np.uint64)
+        ranges = np.zeros((n, 2), dtype=np.uint64) if want_ranges else None
+        capi.check(self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
+                                                 _ptr(hit_offsets), None, 0, _ptr(ranges)))
+        total = int(hit_offsets[n]) if n else 0
+        positions = np.zeros(total, dtype=np.uint64)
+        if total:
+            capi.check(self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
+                                                     _ptr(hit_offsets), _ptr(positions), total, _ptr(ranges)))
+        return (hit_offsets, positions, ranges) if want_ranges else (hit_offsets, positions)
+
+    # ---- packed batch, device buffers (raw device pointers, e.g. torch tensors' data_ptr()) ----
+    def count_device(self, d_letters, d_offsets, fixed_len, n, d_counts, d_ranges=None, stream=0):
+        capi.check(self.lib.awfm_gpu_count_device(self._ctx, d_letters, d_offsets or None, fixed_len, n, d_counts,
+                                                  d_ranges or None, stream or None))
+
+    def scan_ranges_device(self, d_ranges, n, d_hit_offsets, stream=0):
+        capi.check(self.lib.awfm_gpu_scan_ranges_device(self._ctx, d_ranges, n, d_hit_offsets, stream or None))
+
+    def locate_device(self, d_ranges, d_hit_offsets, n, hit_begin, hit_end, d_positions, stream=0):
+        capi.check(self.lib.awfm_gpu_locate_device(self._ctx, d_ranges, d_hit_offsets, n, hit_begin, hit_end,
+                                                   d_positions, stream or None))
+
+
+class KmerSearchList:
+    """The reference's AwFmKmerSearchList, allocated and freed by `lib` itself (awFmCreateKmerSearchList /
+    awFmDeallocKmerSearchList), filled the way README.md's example does: set kmerString/kmerLength per entry and
+    `count` on the list.  Query bytes live in one numpy buffer owned by this object (the library never frees them,
+    src/AwFmIndex.h:316-321)."""
+
+    _DTYPE = np.dtype([("kmerString", "<u8"), ("kmerLength", "<u8"), ("positionList", "<u8"), ("count", "<u4"),
+                       ("capacity", "<u4")])
+
+    def __init__(self, lib, capacity):
+        self.lib = lib
+        self.capacity = capacity
+        self.ptr = lib.awFmCreateKmerSearchList(capacity)
+        if not self.ptr:
+            raise MemoryError("awFmCreateKmerSearchList returned NULL")
+        self._letters = None
+
+    def entries(self):
+        """numpy structured view (no copy) of the 32-B AwFmKmerSearchData array."""
+        n = self.capacity
+        if n == 0:
+            return np.zeros(0, dtype=self._DTYPE)
+        addr = C.addressof(self.ptr.contents.kmerSearchData.contents)
+        buf = (C.c_uint8 * (32 * n)).from_address(addr)
+        return np.frombuffer(buf, dtype=self._DTYPE)
+
+    def fill(self, letters, offsets=None, fixed_len=0):
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        if offsets is None:
+            n = len(letters) // fixed_len if fixed_len else 0
+            starts = np.arange(n, dtype=np.uint64) * np.uint64(fixed_len)
+            lengths = np.full(n, fixed_len, dtype=np.uint64)
+        else:
+            offsets = np.asarray(offsets, dtype=np.uint64)
+            n = len(offsets) - 1
+            starts, lengths = offsets[:-1], offsets[1:] - offsets[:-1]
+        assert n <= self.capacity
+        self._letters = letters
+        e = self.entries()
+        e["kmerString"][:n] = np.uint64(letters.ctypes.data) + starts
+        e["kmerLength"][:n] = lengths
+        self.ptr.contents.count = n
+        return self
+
+    @property
+    def count(self):
+        return int(self.ptr.contents.count)
+
+    def counts(self):
+        return self.entries()["count"][: self.count].copy()
+
+    def positions(self):
+        """list of uint64 arrays, one per query, copied out of the malloc'd position lists."""
+        e = self.entries()
+        out = []
+        for i in range(self.count):
+            c = int(e["count"][i])
+            if c == 0:
+                out.append(np.zeros(0, np.uint64))
+            else:
+                buf = (C.c_uint64 * c).from_address(int(e["positionList"][i]))
+                out.append(np.frombuffer(buf, dtype=np.uint64).copy())
+        return out
+
+    def close(self):
+        if self.ptr:
+            self.lib.awFmDeallocKmerSearchList(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def parallel_search_count(lib, index_ptr, search_list: KmerSearchList, num_threads=4):
+    """awFmParallelSearchCount(index, searchList, numThreads) — src/AwFmIndex.h:400-403"""
+    lib.awFmParallelSearchCount(index_ptr, search_list.ptr, num_threads)
+
+
+def parallel_search_locate(lib, index_ptr, search_list: KmerSearchList, num_threads=4):
+    """awFmParallelSearchLocate(index, searchList, numThreads) -> enum AwFmReturnCode — src/AwFmIndex.h:364-367"""
+    return int(lib.awFmParallelSearchLocate(index_ptr, search_list.ptr, num_threads))

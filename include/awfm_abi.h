@@ -1,0 +1,171 @@
+/*
+ * awfm_abi.h — layout-compatible restatement of the PUBLIC data structures of the reference library
+ * (TravisWheelerLab/AvxWindowFmIndex, src/AwFmIndex.h) that the batched k-mer search path reads and writes.
+ *
+ * The reference's header cannot be included from CUDA or from SIMD-free C (it pulls in <immintrin.h> and embeds
+ * __m256i in public structs, src/AwFmIndex.h:40-65), so the drop-in shim and the tests use these plain-C mirrors.
+ * Every struct below has the same size, alignment and member offsets as the reference's; `tests/test_abi_layout.py`
+ * proves it by compiling a probe against the real header when /root/reference is present, and the static
+ * assertions at the bottom pin the numbers that probe produced.
+ *
+ * Names keep the reference's spelling so that code written against AwFmIndex.h reads the same; a translation unit
+ * must include EITHER this file OR the reference's AwFmIndex.h, never both.
+ */
+#ifndef AWFM_ABI_H
+#define AWFM_ABI_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/AwFmIndex.h:20-28 */
+#define AW_FM_POSITIONS_PER_FM_BLOCK 256
+#define AW_FM_NUCLEOTIDE_VECTORS_PER_WINDOW 3
+#define AW_FM_NUCLEOTIDE_CARDINALITY 4
+#define AW_FM_AMINO_VECTORS_PER_WINDOW 5
+#define AW_FM_AMINO_CARDINALITY 20
+
+/* src/AwFmIndex.h:30-34 */
+enum AwFmAlphabetType { AwFmAlphabetAmino = 1, AwFmAlphabetDna = 2, AwFmAlphabetRna = 3 };
+
+/* A 256-bit letter bit-vector: bit (p % 8) of byte (p / 8) belongs to block position p (src/AwFmCreate.c:296-335).
+ * The reference types it __m256i / 2x uint8x16_t (src/AwFmIndex.h:40-52); only size (32) and alignment (32) matter. */
+typedef struct AwFmBitVector256 {
+  uint8_t bytes[32];
+} __attribute__((aligned(32))) AwFmBitVector256;
+
+/* src/AwFmIndex.h:55-65.  160 B and 352 B; baseOccurrences[c] = occurrences of letter c in BWT[0, 256*blockIndex). */
+struct AwFmAminoBlock {
+  AwFmBitVector256 letterBitVectors[AW_FM_AMINO_VECTORS_PER_WINDOW];
+  uint64_t baseOccurrences[AW_FM_AMINO_CARDINALITY + 4];
+};
+struct AwFmNucleotideBlock {
+  AwFmBitVector256 letterBitVectors[AW_FM_NUCLEOTIDE_VECTORS_PER_WINDOW];
+  uint64_t baseOccurrences[AW_FM_NUCLEOTIDE_CARDINALITY + 4];
+};
+
+union AwFmBwtBlockList { /* src/AwFmIndex.h:67-70 */
+  struct AwFmNucleotideBlock *asNucleotide;
+  struct AwFmAminoBlock *asAmino;
+};
+
+struct AwFmIndexConfiguration { /* src/AwFmIndex.h:74-80 */
+  uint8_t suffixArrayCompressionRatio;
+  uint8_t kmerLengthInSeedTable;
+  enum AwFmAlphabetType alphabetType;
+  bool keepSuffixArrayInMemory;
+  bool storeOriginalSequence;
+};
+
+struct AwFmCompressedSuffixArray { /* src/AwFmIndex.h:82-86 */
+  uint8_t valueBitWidth;
+  uint8_t *values;
+  uint64_t compressedByteLength;
+};
+
+struct AwFmSearchRange { /* src/AwFmIndex.h:88-91; inclusive [startPtr, endPtr], valid iff startPtr <= endPtr */
+  uint64_t startPtr;
+  uint64_t endPtr;
+};
+
+struct FastaVector; /* lib/FastaVector/src/FastaVector.h — opaque on this path */
+
+struct AwFmIndex { /* src/AwFmIndex.h:94-109 */
+  uint32_t versionNumber;
+  uint32_t featureFlags;
+  uint64_t bwtLength;
+  union AwFmBwtBlockList bwtBlockList;
+  uint64_t *prefixSums;
+  struct AwFmSearchRange *kmerSeedTable;
+  FILE *fileHandle;
+  struct AwFmIndexConfiguration config;
+  int fileDescriptor;
+  size_t suffixArrayFileOffset;
+  size_t sequenceFileOffset;
+  struct FastaVector *fastaVector;
+  struct AwFmCompressedSuffixArray suffixArray;
+};
+
+struct AwFmKmerSearchData { /* src/AwFmIndex.h:111-117 */
+  char *kmerString;
+  uint64_t kmerLength;
+  uint64_t *positionList;
+  uint32_t count;
+  uint32_t capacity;
+};
+
+struct AwFmKmerSearchList { /* src/AwFmIndex.h:119-123 */
+  size_t capacity;
+  size_t count;
+  struct AwFmKmerSearchData *kmerSearchData;
+};
+
+/* src/AwFmIndex.h:132-138 */
+enum AwFmReturnCode {
+  AwFmSuccess = 1,
+  AwFmFileReadOkay = 2,
+  AwFmFileWriteOkay = 3,
+  AwFmGeneralFailure = -1,
+  AwFmUnsupportedVersionError = -2,
+  AwFmAllocationFailure = -3,
+  AwFmNullPtrError = -4,
+  AwFmSuffixArrayCreationFailure = -5,
+  AwFmIllegalPositionError = -6,
+  AwFmNoFileSrcGiven = -7,
+  AwFmNoDatabaseSequenceGiven = -8,
+  AwFmFileFormatError = -9,
+  AwFmFileOpenFail = -10,
+  AwFmFileReadFail = -11,
+  AwFmFileWriteFail = -12,
+  AwFmErrorDbSequenceNull = -13,
+  AwFmErrorSuffixArrayNull = -14,
+  AwFmFileAlreadyExists = -15
+};
+
+/* ---- the four entry points of the hot path (the translation unit src/AwFmParallelSearch.c), unchanged ---- */
+
+/* src/AwFmIndex.h:308, src/AwFmParallelSearch.c:36-84 */
+struct AwFmKmerSearchList *awFmCreateKmerSearchList(const size_t capacity);
+/* src/AwFmIndex.h:326-327, src/AwFmParallelSearch.c:86-93 */
+void awFmDeallocKmerSearchList(struct AwFmKmerSearchList *restrict const searchList);
+/* src/AwFmIndex.h:364-367, src/AwFmParallelSearch.c:95-157 */
+enum AwFmReturnCode awFmParallelSearchLocate(const struct AwFmIndex *restrict const index,
+                                             struct AwFmKmerSearchList *restrict const searchList,
+                                             uint32_t numThreads);
+/* src/AwFmIndex.h:400-403, src/AwFmParallelSearch.c:159-220 */
+void awFmParallelSearchCount(const struct AwFmIndex *restrict const index,
+                             struct AwFmKmerSearchList *restrict const searchList, uint32_t numThreads);
+
+/* ---- additive entry points of the B200 drop-in (not in the reference) ---- */
+
+/* Drops the device-resident copy of `index` (call before awFmDeallocIndex; the reference API has no hook). */
+void awFmGpuReleaseIndex(const struct AwFmIndex *index);
+/* Uploads `index` to the device now instead of lazily on the first batched call. AwFmSuccess or a failure code. */
+enum AwFmReturnCode awFmGpuPrepareIndex(const struct AwFmIndex *index);
+/* Return code of the most recent awFmParallelSearchCount on this thread (the reference's is void). */
+enum AwFmReturnCode awFmGpuLastCountStatus(void);
+
+#ifndef __cplusplus
+_Static_assert(sizeof(struct AwFmNucleotideBlock) == 160, "nucleotide block is 160 B");
+_Static_assert(sizeof(struct AwFmAminoBlock) == 352, "amino block is 352 B");
+_Static_assert(offsetof(struct AwFmNucleotideBlock, baseOccurrences) == 96, "nuc base occurrences at 96");
+_Static_assert(offsetof(struct AwFmAminoBlock, baseOccurrences) == 160, "amino base occurrences at 160");
+_Static_assert(sizeof(struct AwFmSearchRange) == 16, "range is 16 B");
+_Static_assert(sizeof(struct AwFmKmerSearchData) == 32, "search data is 32 B");
+_Static_assert(offsetof(struct AwFmKmerSearchData, count) == 24, "count at 24");
+_Static_assert(offsetof(struct AwFmKmerSearchData, capacity) == 28, "capacity at 28");
+_Static_assert(sizeof(struct AwFmKmerSearchList) == 24, "search list is 24 B");
+_Static_assert(sizeof(struct AwFmIndex) == 112, "index struct is 112 B");
+_Static_assert(offsetof(struct AwFmIndex, config) == 48, "config at 48");
+_Static_assert(offsetof(struct AwFmIndex, suffixArray) == 88, "suffixArray at 88");
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWFM_ABI_H */

@@ -1,0 +1,144 @@
+/*
+ * awfm_gpu.h — thin C-ABI between host code (C, Python/ctypes, anything with an FFI) and the hand-written sm_100a
+ * CUDA implementation of AwFmIndex's batched exact-match k-mer search.  Plain pointers and sizes only; no CUDA,
+ * torch or reference types appear in any signature.  Library: avxwindowfmindex_b200/csrc/libawfm_b200.so.
+ *
+ * What each entry point replaces in the reference (TravisWheelerLab/AvxWindowFmIndex @92b849f):
+ *
+ *   awfm_gpu_ctx_create / _destroy   the read-only arrays of struct AwFmIndex (src/AwFmIndex.h:94-109) made resident
+ *                                    in HBM: bwtBlockList, prefixSums, kmerSeedTable, suffixArray.values.
+ *   awfm_gpu_count_*                 awFmParallelSearchCount (src/AwFmParallelSearch.c:159-220) =
+ *                                    parallelSearchFindKmerSeedsForBlock (:222-271, seed table src/AwFmKmerTable.c:4-51,
+ *                                    non-seeded start src/AwFmSearch.c:485-520) + parallelSearchExtendKmersInBlock
+ *                                    (:273-313; LF step src/AwFmSearch.c:42-159; rank src/AwFmOccurrence.c:8-135 and
+ *                                    src/AwFmSimdConfig.c:89-114) + awFmSearchRangeLength (src/AwFmIndexStruct.c:126-130).
+ *   awfm_gpu_locate_*                awFmParallelSearchLocate (src/AwFmParallelSearch.c:95-157): the above, then
+ *                                    parallelSearchTracebackPositionLists (:315-365; backtrace step src/AwFmSearch.c:369-427,
+ *                                    letter-at-position src/AwFmOccurrence.c:170-217, sampled-SA read
+ *                                    src/AwFmSuffixArray.c:114-142,179-203).
+ *   awfm_gpu_search_list_*           the same two calls over the reference's own AwFmKmerSearchList memory layout
+ *                                    (src/AwFmIndex.h:111-123): pipelined host marshalling + kernels + scatter.
+ *
+ * Query batch format ("packed batch"): the ASCII letters of all queries concatenated in `letters`; query i is
+ * letters[offsets[i] .. offsets[i+1]).  If `offsets` is NULL every query has exactly `fixedLen` letters and
+ * query i starts at i*fixedLen.  Letters are the raw bytes the reference API would be given (any case, ambiguity
+ * codes allowed); translation to letter indices follows src/AwFmLetter.c:4-22,55-67 on the device.
+ *
+ * All functions return AWFM_GPU_OK (0) or a negative awfm_gpu_status; awfm_gpu_last_error() returns a
+ * thread-local human-readable message.  There is NO CPU fallback: without a usable CUDA device every call fails.
+ */
+#ifndef AWFM_GPU_H
+#define AWFM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum awfm_gpu_status {
+  AWFM_GPU_OK = 0,
+  AWFM_GPU_ERR_ARG = -1,     /* bad argument (NULL, unsupported alphabet/width, ...)        */
+  AWFM_GPU_ERR_NO_DEVICE = -2, /* no CUDA device / driver                                   */
+  AWFM_GPU_ERR_ALLOC = -3,   /* device or pinned-host allocation failed                     */
+  AWFM_GPU_ERR_CUDA = -4,    /* any other CUDA runtime / launch error                       */
+  AWFM_GPU_ERR_NO_SA = -5    /* locate requested but the context holds no sampled SA        */
+} awfm_gpu_status;
+
+/* Plain view of the index arrays (all HOST pointers; copied, never retained).  Field meaning = the reference's. */
+typedef struct awfm_index_view {
+  const void *blocks;         /* struct AwFm{Nucleotide,Amino}Block[numBlocks] (160 / 352 B each)               */
+  uint64_t numBlocks;         /* 1 + (bwtLength-1)/256                    (src/AwFmIndexStruct.c:104-106)       */
+  const uint64_t *prefixSums; /* |alphabet|+2 entries                     (src/AwFmCreate.c:338-343)            */
+  const void *seedTable;      /* struct AwFmSearchRange[|alphabet|^seedK] (src/AwFmCreate.c:407-450)            */
+  const uint8_t *saBytes;     /* bit-packed sampled SA, or NULL (count-only context)  (src/AwFmSuffixArray.c)   */
+  uint64_t saByteLength;      /* suffixArray.compressedByteLength                                                */
+  uint64_t bwtLength;
+  uint8_t saBitWidth;         /* suffixArray.valueBitWidth, 1..64                                                */
+  uint8_t saRatio;            /* config.suffixArrayCompressionRatio, 1..255                                      */
+  uint8_t seedK;              /* config.kmerLengthInSeedTable                                                    */
+  uint8_t alphabet;           /* enum AwFmAlphabetType: 1 amino, 2 DNA, 3 RNA                                    */
+} awfm_index_view;
+
+typedef struct awfm_range { /* == struct AwFmSearchRange */
+  uint64_t startPtr;
+  uint64_t endPtr;
+} awfm_range;
+
+typedef struct awfm_kmer_search_data { /* == struct AwFmKmerSearchData, 32 B (src/AwFmIndex.h:111-117) */
+  char *kmerString;
+  uint64_t kmerLength;
+  uint64_t *positionList;
+  uint32_t count;
+  uint32_t capacity;
+} awfm_kmer_search_data;
+
+typedef struct awfm_gpu_ctx awfm_gpu_ctx;
+
+/* Kernel-only timing and work counters of the most recent call on a context (device time from CUDA events). */
+typedef struct awfm_gpu_stats {
+  double kernelMs;        /* sum over launches of the search / backtrace kernels          */
+  double h2dMs, d2hMs;    /* only filled by the *_host and search_list calls              */
+  uint64_t launches;      /* kernels launched by the call (all of ours, incl. scans)      */
+  uint64_t queries, hits;
+  uint64_t h2dBytes, d2hBytes;
+} awfm_gpu_stats;
+
+const char *awfm_gpu_last_error(void);
+int awfm_gpu_device_count(void);
+
+/* ---- index residency ---- */
+int awfm_gpu_ctx_create(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view);
+/* Same, but every array pointer in `view` is a DEVICE pointer on `device` (index built or loaded on the GPU). */
+int awfm_gpu_ctx_create_from_device(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view);
+void awfm_gpu_ctx_destroy(awfm_gpu_ctx *ctx);
+uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *ctx);
+int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
+/* Tuning knobs (kernel variant selection for measurement; defaults are the shipped configuration).
+ * keys: "count_lpq" (lanes per query: 1,2,4,8), "locate_lpq", "count_variant", "chunk_queries", "cta_threads". */
+int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
+
+/* ---- packed batch, HOST buffers (H2D, kernels, D2H inside the call) ---- */
+int awfm_gpu_count_host(awfm_gpu_ctx *ctx, const uint8_t *letters, const uint64_t *offsets, uint32_t fixedLen,
+                        uint64_t numQueries, uint32_t *counts /* out, numQueries */,
+                        awfm_range *ranges /* out, numQueries, may be NULL */);
+/* Locate, CSR output: hitOffsets[numQueries+1] (exclusive prefix sum of range lengths) and positions
+ * [hitOffsets[numQueries]] in SA order within each query.  Two-step so the caller can size `positions`:
+ * pass positions == NULL to get only hitOffsets; then call again with a buffer of positionsCapacity entries. */
+int awfm_gpu_locate_host(awfm_gpu_ctx *ctx, const uint8_t *letters, const uint64_t *offsets, uint32_t fixedLen,
+                         uint64_t numQueries, uint64_t *hitOffsets /* out, numQueries+1 */,
+                         uint64_t *positions /* out or NULL */, uint64_t positionsCapacity,
+                         awfm_range *ranges /* out, may be NULL */);
+
+/* ---- packed batch, DEVICE buffers on the context's device, asynchronous on `stream` (a cudaStream_t) ---- */
+int awfm_gpu_count_device(awfm_gpu_ctx *ctx, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
+                          uint64_t numQueries, uint32_t *dCounts, awfm_range *dRanges /* may be NULL */,
+                          void *stream);
+/* dRanges (in) come from awfm_gpu_count_device; dHitOffsets (out, numQueries+1) is their exclusive scan. */
+int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, uint64_t numQueries,
+                                uint64_t *dHitOffsets, void *stream);
+/* Backtrace + sampled-SA read for flat hit indices [hitBegin, hitEnd) into dPositions[h - hitBegin]. */
+int awfm_gpu_locate_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, const uint64_t *dHitOffsets,
+                           uint64_t numQueries, uint64_t hitBegin, uint64_t hitEnd, uint64_t *dPositions,
+                           void *stream);
+
+/* ---- the reference's own search-list layout (used by the drop-in shim) ---- */
+/* Fills data[i].count for i < numQueries (uint32 truncation as in src/AwFmParallelSearch.c:187-190). */
+int awfm_gpu_search_list_count(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
+                               uint32_t numThreads);
+/* Fills count + positionList with the reference's capacity semantics (realloc to exactly count when
+ * count > capacity, src/AwFmParallelSearch.c:367-387).  Returns AWFM_GPU_ERR_ALLOC if a realloc failed. */
+int awfm_gpu_search_list_locate(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
+                                uint32_t numThreads);
+
+/* ---- measurement helper: random-gather bandwidth with this path's access shape ---- */
+/* Reads `numReads` independent pseudo-random `bytesPerRead`-byte records (16, 32, 64 or 128, aligned to their
+ * size) from a `arrayBytes` device buffer; returns achieved GB/s (bytes consumed / device time) in *gbps. */
+int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32_t bytesPerRead, uint64_t numReads,
+                              int lanesPerRead, double *gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWFM_GPU_H */

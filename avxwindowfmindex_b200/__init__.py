@@ -4,6 +4,7 @@ Only the hot path of TravisWheelerLab/AvxWindowFmIndex is here: awFmParallelSear
 over an AwFmKmerSearchList, on an unchanged `.awfmi` index.  The product is csrc/libawfm_b200.so (hand-written
 CUDA + C-ABI, include/awfm_gpu.h, include/awfm_abi.h); the Python modules are a ctypes veneer for tests and bench.
 """
-from . import abi, capi, index, search, synth  # noqa: F401
+from . import abi, build_index, capi, index, search, synth  # noqa: F401
+from .build_index import DeviceBuiltIndex  # noqa: F401
 from .index import IndexArrays, read_awfmi, write_awfmi  # noqa: F401
 from .search import GpuIndex, KmerSearchList, parallel_search_count, parallel_search_locate  # noqa: F401

@@ -16,7 +16,8 @@ GPU_SYMBOLS = [
     "awfm_gpu_ctx_destroy", "awfm_gpu_ctx_device_bytes", "awfm_gpu_ctx_get_stats", "awfm_gpu_ctx_set_tuning",
     "awfm_gpu_count_host", "awfm_gpu_locate_host", "awfm_gpu_count_device", "awfm_gpu_scan_ranges_device",
     "awfm_gpu_locate_device", "awfm_gpu_search_list_count", "awfm_gpu_search_list_locate",
-    "awfm_gpu_gather_bandwidth",
+    "awfm_gpu_gather_bandwidth", "awfm_gpu_build_index", "awfm_gpu_build_index_host", "awfm_gpu_built_view",
+    "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters",
 ]
 DROPIN_SYMBOLS = [
     "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",
@@ -74,6 +75,14 @@ def load():
     lib.awfm_gpu_search_list_count.argtypes = [vp, vp, u64, u32]
     lib.awfm_gpu_search_list_locate.argtypes = [vp, vp, u64, u32]
     lib.awfm_gpu_gather_bandwidth.argtypes = [C.c_int, u64, u32, u64, C.c_int, C.POINTER(C.c_double)]
+    u8 = C.c_uint8
+    lib.awfm_gpu_build_index.argtypes = [C.POINTER(vp), C.c_int, vp, u64, u8, u8, u8]
+    lib.awfm_gpu_build_index_host.argtypes = [C.POINTER(vp), C.c_int, vp, u64, u8, u8, u8]
+    lib.awfm_gpu_built_view.argtypes = [vp, C.POINTER(abi.awfm_index_view), C.POINTER(u64), C.POINTER(C.c_double)]
+    lib.awfm_gpu_built_download.argtypes = [vp, vp, vp, vp, vp]
+    lib.awfm_gpu_built_destroy.argtypes = [vp]
+    lib.awfm_gpu_built_destroy.restype = None
+    lib.awfm_gpu_synth_letters.argtypes = [C.c_int, vp, u64, u64, u64, C.c_int]
     declare_search_list_api(lib)
     lib.awFmGpuReleaseIndex.argtypes = [vp]
     lib.awFmGpuReleaseIndex.restype = None

@@ -43,6 +43,8 @@ static int fail(int code, const char *what, const char *detail = nullptr) {
     }                                                                                                \
   } while (0)
 
+int awfm_set_error(int code, const char *what, const char *detail) { return fail(code, what, detail); }
+
 extern "C" const char *awfm_gpu_last_error(void) { return gLastError.c_str(); }
 extern "C" int awfm_gpu_device_count(void) {
   int n = 0;

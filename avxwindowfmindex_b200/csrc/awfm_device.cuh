@@ -73,13 +73,13 @@ __device__ __forceinline__ uint32_t nucCodeCare(uint32_t letter) {
   // nibble pairs, low nibble = code, high nibble = care: A(6,6) C(5,5) G(3,3) T(1,7) X(2,7)
   return (0x7271335566ull >> (letter * 8u)) & 0xFFu;
 }
-__constant__ uint16_t kAminoCodeCare[21] = {
+static __constant__ uint16_t kAminoCodeCare[21] = {
     // (care << 8) | code
     0x1C0C, 0x0F17, 0x1303, 0x1606, 0x0F1E, 0x151A, 0x0F1B, 0x1619, 0x1A15, 0x131C, 0x0F1D,
     0x0F08, 0x1909, 0x0F04, 0x1C13, 0x1A0A, 0x1505, 0x1916, 0x0F01, 0x0F02, 0x0F1F};
 // code -> letter index (src/AwFmLetter.c:49-53, :89-96)
 __device__ __forceinline__ uint32_t nucCodeToLetter(uint32_t code) { return (0x00152435u >> (code * 4u)) & 0xFu; }
-__constant__ uint8_t kAminoCodeToLetter[32] = {21, 18, 19, 2,  13, 16, 3,  20, 11, 12, 15, 20, 0, 20, 20, 20,
+static __constant__ uint8_t kAminoCodeToLetter[32] = {21, 18, 19, 2,  13, 16, 3,  20, 11, 12, 15, 20, 0, 20, 20, 20,
                                                20, 20, 20, 14, 20, 8,  17, 1,  20, 7,  5,  6,  9, 10, 4,  20};
 
 // mask of bits 0..rel inclusive of a 32-bit word whose first bit is block position 32*chunk, for an inclusive

@@ -39,6 +39,17 @@ class GpuIndex:
         view = arrays.view()
         capi.check(self.lib.awfm_gpu_ctx_create(C.byref(self._ctx), device, C.byref(view)))
 
+    @classmethod
+    def from_device_view(cls, view, device=0):
+        """Index whose arrays already live on `device` (awfm_index_view of DEVICE pointers, e.g. from build_index)."""
+        self = cls.__new__(cls)
+        self.lib = capi.load()
+        self.arrays = None
+        self.device = device
+        self._ctx = C.c_void_p()
+        capi.check(self.lib.awfm_gpu_ctx_create_from_device(C.byref(self._ctx), device, C.byref(view)))
+        return self
+
     @property
     def ctx(self):
         return self._ctx

@@ -132,6 +132,23 @@ int awfm_gpu_search_list_count(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, u
 int awfm_gpu_search_list_locate(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
                                 uint32_t numThreads);
 
+/* ---- index construction on the device (replaces awFmCreateIndex, src/AwFmCreate.c:31-137,
+ *      for texts with bwtLength < 2^32).  Output arrays are in the reference's own formats (raw 160/352-B blocks,
+ *      prefix sums, seed table, bit-packed sampled SA) and stay on the device inside the handle. ---- */
+typedef struct awfm_built_index awfm_built_index;
+int awfm_gpu_build_index(awfm_built_index **built, int device, const uint8_t *dText /* DEVICE, ASCII */,
+                         uint64_t textLength, uint8_t alphabet, uint8_t seedK, uint8_t saRatio);
+int awfm_gpu_build_index_host(awfm_built_index **built, int device, const uint8_t *text /* HOST, ASCII */,
+                              uint64_t textLength, uint8_t alphabet, uint8_t seedK, uint8_t saRatio);
+/* `view` receives DEVICE pointers (feed it to awfm_gpu_ctx_create_from_device); valid until _destroy. */
+int awfm_gpu_built_view(awfm_built_index *built, awfm_index_view *view, uint64_t *tieSuffixes, double *buildMs);
+/* copies into caller-sized HOST buffers (sizes follow from the view); NULL pointers are skipped */
+int awfm_gpu_built_download(awfm_built_index *built, void *blocks, uint64_t *prefixSums, void *seedTable,
+                            uint8_t *saBytes);
+void awfm_gpu_built_destroy(awfm_built_index *built);
+/* splitmix64 letter stream (same as avxwindowfmindex_b200/synth.py): element i uses counter start + i */
+int awfm_gpu_synth_letters(int device, uint8_t *dOut, uint64_t count, uint64_t seed, uint64_t start, int amino);
+
 /* ---- measurement helper: random-gather bandwidth with this path's access shape ---- */
 /* Reads `numReads` independent pseudo-random `bytesPerRead`-byte records (16, 32, 64 or 128, aligned to their
  * size) from a `arrayBytes` device buffer; returns achieved GB/s (bytes consumed / device time) in *gbps. */

@@ -1,0 +1,97 @@
+"""Device index construction (row f4) must be byte-identical to the reference's awFmCreateIndex on the same text:
+blocks, prefix sums, seed table and the bit-packed sampled SA including its 8 trailing bytes."""
+import numpy as np
+import pytest
+
+from avxwindowfmindex_b200 import DeviceBuiltIndex, abi, synth, write_awfmi
+from conftest import make_text
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same(built, ref_arrays, tag):
+    mine = built.to_host()
+    assert mine.bwt_length == ref_arrays.bwt_length
+    assert np.array_equal(mine.prefix_sums, ref_arrays.prefix_sums), tag
+    assert np.array_equal(mine.blocks, ref_arrays.blocks), tag
+    assert np.array_equal(mine.seed_table, ref_arrays.seed_table), tag
+    assert np.array_equal(mine.sa_bytes, ref_arrays.sa_bytes), tag
+    return mine
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r1", "nuc_r3", "nuc_r16", "nuc_r200", "nuc_r255", "amino_r8",
+                                  "amino_r2", "amino_r1"])
+def test_matches_reference_built_indexes(small_indexes, name):
+    b = small_indexes[name]
+    built = DeviceBuiltIndex.from_host_text(b.text, b.arrays.alphabet, b.arrays.seed_k, b.arrays.sa_ratio)
+    assert_same(built, b.arrays, name)
+    built.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 255, 256, 257, 511, 513, 1000])
+def test_tiny_texts(reference, tmp_path, n):
+    text = make_text(n, False, seed=n)
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "t.awfmi"), abi.AwFmAlphabetDna, 2, 3)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetDna, 2, 3)
+    assert_same(built, reference.arrays(ptr), n)
+    built.close()
+    reference.dealloc_index(ptr)
+
+
+def test_repetitive_text_goes_through_tie_resolution(reference, tmp_path):
+    """Long repeats defeat the 22-symbol radix pass; tied groups are finished by suffix comparison on the host."""
+    rng = np.random.default_rng(0)
+    unit = make_text(300, False, seed=1)
+    text = np.concatenate([unit] * 20 + [make_text(500, False, seed=2)] + [np.frombuffer(b"ACGT" * 200, np.uint8)])
+    text = text.copy()
+    text[rng.integers(0, len(text), 5)] = ord("N")
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "rep.awfmi"), abi.AwFmAlphabetDna, 4, 5)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetDna, 4, 5)
+    assert built.tie_suffixes > 1000
+    assert_same(built, reference.arrays(ptr), "repetitive")
+    built.close()
+    reference.dealloc_index(ptr)
+
+
+def test_device_generated_text_and_file_round_trip(reference, tmp_path):
+    """Text generated on the device (same splitmix64 stream as synth.py), built on the device, written as .awfmi,
+    read back by the reference's awFmReadIndexFromFile, and compared with the reference's own build."""
+    import torch
+    from avxwindowfmindex_b200 import capi
+    n = 1_000_003
+    d_text = torch.empty(n, dtype=torch.uint8, device="cuda")
+    capi.check(capi.load().awfm_gpu_synth_letters(0, d_text.data_ptr(), n, synth.TEXT_SEED, 0, 0))
+    text = synth.random_text(n)
+    assert np.array_equal(d_text.cpu().numpy(), text)
+    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), n, abi.AwFmAlphabetDna, 8, 8)
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "ref.awfmi"), abi.AwFmAlphabetDna, 8, 8)
+    mine = assert_same(built, reference.arrays(ptr), "1Mbp")
+    path = str(tmp_path / "mine.awfmi")
+    write_awfmi(mine, path)
+    assert open(path, "rb").read() == open(str(tmp_path / "ref.awfmi"), "rb").read()
+    ptr2 = reference.read_index(path)
+    q = synth.random_queries(20000, 12)
+    assert np.array_equal(reference.count(ptr2, q, fixed_len=12, threads=4), reference.count(ptr, q, fixed_len=12, threads=4))
+    # searchable straight from device memory, no host round trip
+    gpu = built.gpu_index()
+    counts = np.zeros(20000, np.uint32)
+    d_q = torch.from_numpy(q).cuda()
+    d_c = torch.zeros(20000, dtype=torch.int32, device="cuda")
+    gpu.count_device(d_q.data_ptr(), None, 12, 20000, d_c.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_c.cpu().numpy().astype(np.uint32), reference.count(ptr, q, fixed_len=12, threads=4))
+    gpu.close()
+    built.close()
+    reference.dealloc_index(ptr)
+    reference.dealloc_index(ptr2)
+
+
+def test_amino_device_text(reference, tmp_path):
+    n = 300_007
+    text = synth.random_text(n, amino=True)
+    text[::5003] = ord("X")
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "a.awfmi"), abi.AwFmAlphabetAmino, 3, 7)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetAmino, 3, 7)
+    assert_same(built, reference.arrays(ptr), "amino")
+    built.close()
+    reference.dealloc_index(ptr)

@@ -80,7 +80,7 @@ struct awfm_gpu_ctx {
   uint64_t deviceBytes = 0;
   bool hasSa = false;
   // tuning
-  int countLpq = 8, locateLpq = 8, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
+  int countLpq = 4, locateLpq = 1, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
   int64_t chunkQueries = 1 << 21;
   // scratch
   void *scanTemp = nullptr;

@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — batched exact-match k-mer COUNT throughput (BASELINE.json configs[1]):
+3.1 Gbp synthetic nucleotide index (seed k=12, SA ratio 8), 100 M random 20-mers per GPU, query-sharded.
+
+    python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N ...             the reference's own OpenMP/AVX2 path on the host cores
+
+One "step" = one pass of awFmParallelSearchCount's work over this rank's whole query batch.
+  value : queries/s, whole job, inputs (packed queries + index) already resident in HBM, CUDA-event timed;
+          for N>1 every step also gathers the per-rank count arrays onto rank 0 over NCCL/NVLink, overlapped
+          with the search kernels chunk by chunk (the only collective on this path).
+  e2e   : queries/s through the reference-facing drop-in call awFmParallelSearchCount(index, searchList, threads)
+          on HOST memory: the 32-B AwFmKmerSearchData entries point at host strings; packing, H2D, kernels, D2H
+          and the scatter of `count` back into the structs are all inside the timed region.
+The index is built on the device by avxwindowfmindex_b200.build_index (byte-identical to awFmCreateIndex, see
+tests/test_gpu_build_index.py) because the reference's CPU build of 3.1 Gbp takes ~20 min; the reference arm and
+the cpu_baseline leg search that same index with the UNMODIFIED reference library (oracle/_ref/libawfm_ref.so).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kmer_count_queries_per_sec"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bp", type=int, default=3_100_000_000, help="text length (config: 3.1 Gbp)")
+    ap.add_argument("--queries", type=int, default=100_000_000, help="queries per GPU (config: 100 M)")
+    ap.add_argument("--kmer", type=int, default=20)
+    ap.add_argument("--seed-k", type=int, default=12)
+    ap.add_argument("--sa-ratio", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="queries per CPU-baseline pass")
+    ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        cmd = ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per launch of the count kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_count_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def host_index_struct(arrays):
+    """struct AwFmIndex over host arrays, as a C caller of the reference API holds it."""
+    return arrays.as_awfm_index()
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_pass(ref, index_ptr, letters, n, length, threads, reps):
+    """Times the unmodified reference's awFmParallelSearchCount on `n` host queries; returns best queries/s."""
+    from avxwindowfmindex_b200 import KmerSearchList
+    sl = KmerSearchList(ref.lib, n).fill(letters[: n * length], fixed_len=length)
+    best = 0.0
+    ref.lib.awFmParallelSearchCount(index_ptr, sl.ptr, threads)  # warm-up (page in index, spin up OpenMP)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ref.lib.awFmParallelSearchCount(index_ptr, sl.ptr, threads)
+        times.append(time.perf_counter() - t0)
+        best = max(best, n / times[-1])
+    counts = sl.counts()
+    sl.close()
+    return best, times, counts
+
+
+def build_on_device(args, device, lib):
+    import torch
+    from avxwindowfmindex_b200 import DeviceBuiltIndex, abi, capi, synth
+    d_text = torch.empty(args.bp, dtype=torch.uint8, device=f"cuda:{device}")
+    capi.check(lib.awfm_gpu_synth_letters(device, d_text.data_ptr(), args.bp, synth.TEXT_SEED + 2, 0, 0))
+    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), args.bp, abi.AwFmAlphabetDna, args.seed_k,
+                                              args.sa_ratio, device=device)
+    del d_text
+    torch.cuda.synchronize()
+    return built
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the reference arm
+    import torch
+    from avxwindowfmindex_b200 import capi, synth
+    from oracle import harness
+    lib = capi.load()
+    threads = os.cpu_count()
+    config = workload_config(args, 1)
+    if not harness.have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libawfm_ref.so was not built"}))
+        return
+    ref = harness.Reference()
+    built = build_on_device(args, 0, lib)  # setup only: byte-identical to awFmCreateIndex, never timed
+    arrays = built.to_host()
+    built.close()
+    torch.cuda.empty_cache()
+    ix = host_index_struct(arrays)
+    n = min(args.cpu_sample, args.queries)
+    letters = synth.random_queries(n, args.kmer, seed=synth.QUERY_SEED + 2)
+    sl_times = []
+    from avxwindowfmindex_b200 import KmerSearchList
+    sl = KmerSearchList(ref.lib, n).fill(letters, fixed_len=args.kmer)
+    for _ in range(args.warmup):
+        ref.lib.awFmParallelSearchCount(C.addressof(ix), sl.ptr, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        ref.lib.awFmParallelSearchCount(C.addressof(ix), sl.ptr, threads)
+        sl_times.append(time.perf_counter() - t1)
+    total = time.perf_counter() - t0
+    sl.close()
+    value = n * args.steps / total
+    sample = f"{n} of the {args.queries} random {args.kmer}-mers per step, reference awFmParallelSearchCount, numThreads={threads}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"count: {args.bp} bp synthetic nucleotide index (seed k={args.seed_k}, SA ratio {args.sa_ratio}), "
+                    f"{args.queries} random {args.kmer}-mers per GPU (BASELINE.json configs[1])",
+        "text_bp": args.bp, "seed_k": args.seed_k, "sa_ratio": args.sa_ratio, "kmer": args.kmer,
+        "queries_per_gpu": args.queries, "parallelism": f"query-sharded x{world}, index replicated per GPU",
+        "l2_policy": "inputs larger than L2 (index 3.5 GB + packed queries 2 GB per step vs 126 MB L2)",
+        "index_built_by": "device builder, byte-identical to the reference's awFmCreateIndex (tests/test_gpu_build_index.py)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from avxwindowfmindex_b200 import KmerSearchList, abi, capi, synth
+    from oracle import harness  # checker + cpu_baseline only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    lib = capi.load()  # raises if the CUDA library is missing: there is no fallback
+    dev = torch.device(f"cuda:{local}")
+
+    # ---- index: built on this GPU, stays resident ----
+    t0 = time.time()
+    built = build_on_device(args, local, lib)
+    gpu = built.gpu_index()
+    build_s = time.time() - t0
+    need_host = (not args.no_e2e) or (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    arrays = built.to_host() if need_host else None
+    tie_suffixes, build_ms = built.tie_suffixes, built.build_ms
+    built.close()
+    torch.cuda.empty_cache()
+
+    # ---- queries: this rank's shard of the random k-mer stream, resident in HBM ----
+    n, L = args.queries, args.kmer
+    d_letters = torch.empty(n * L + 64, dtype=torch.uint8, device=dev)
+    capi.check(lib.awfm_gpu_synth_letters(local, d_letters.data_ptr(), n * L, synth.QUERY_SEED + 2, rank * n * L, 0))
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    chunks = args.gather_chunks if world > 1 else 1
+    bounds = [n * i // chunks for i in range(chunks + 1)]
+    gathered = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def step():
+        works = []
+        for c in range(chunks):
+            a, b = bounds[c], bounds[c + 1]
+            gpu.count_device(d_letters.data_ptr() + a * L, None, L, b - a, d_counts.data_ptr() + 4 * a, None,
+                             stream.cuda_stream)
+            if world > 1:  # gather this chunk's counts onto rank 0 while the next chunk is searched
+                works.append(dist.gather(d_counts[a:b], [g[a:b] for g in gathered] if rank == 0 else None, dst=0,
+                                         async_op=True))
+        for w in works:
+            w.wait()
+        return chunks
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches = 0
+    with ClockSampler(local) as clocks:
+        ev[0].record(stream)
+        for s in range(args.steps):
+            launches += step()
+            ev[s + 1].record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # kernel-only duration (one launch over the whole batch) for the roofline, CUDA events on the launching stream
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    for _ in range(5):
+        ka.record(stream)
+        gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
+        kb.record(stream)
+        torch.cuda.synchronize()
+        kernel_ms.append(ka.elapsed_time(kb))
+    kernel_avg = sum(kernel_ms) / len(kernel_ms)
+
+    # ---- parity on a sample + exact algorithmic bytes from the oracle (checker, not the product) ----
+    result = {}
+    sample = min(n, 1_000_000)
+    h_counts_sample = d_counts[:sample].cpu().numpy().astype(np.uint32)
+    h_letters_sample = d_letters[: sample * L].cpu().numpy()
+    if arrays is not None or rank == 0:
+        if arrays is None:
+            # rebuilt only when the host copy was skipped
+            b2 = build_on_device(args, local, lib)
+            arrays = b2.to_host()
+            b2.close()
+        o_counts, _, work = harness.Oracle(arrays).count(h_letters_sample, fixed_len=L, threads=os.cpu_count())
+        parity = bool(np.array_equal(o_counts, h_counts_sample))
+        bytes_per_query = work["countBytes"] / sample
+        result["parity_sample"] = {"queries": sample, "bit_exact_vs_oracle": parity,
+                                   "lf_steps_per_query": work["lfSteps"] / sample,
+                                   "block_reads_per_query": work["lfBlockReads"] / sample,
+                                   "algorithmic_bytes_per_query": bytes_per_query}
+        if not parity:
+            raise SystemExit("PARITY FAILURE: CUDA counts differ from the oracle on the bench workload")
+    else:
+        bytes_per_query = None
+
+    # ---- e2e: the reference-facing drop-in call on host memory ----
+    e2e = None
+    threads = max(1, (os.cpu_count() or 1) // world)
+    if not args.no_e2e:
+        h_letters = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+        h_letters.copy_(d_letters[: n * L])
+        hl = h_letters.numpy()
+        ix = host_index_struct(arrays)
+        ip = C.addressof(ix)
+        t0 = time.time()
+        sl = KmerSearchList(lib, n).fill(hl, fixed_len=L)  # awFmCreateKmerSearchList: n position lists, as the reference
+        list_s = time.time() - t0
+        assert lib.awFmGpuPrepareIndex(ip) == abi.AwFmSuccess  # one-time upload, reported separately
+        lib.awFmParallelSearchCount(ip, sl.ptr, threads)
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(args.e2e_steps):
+            t1 = time.perf_counter()
+            lib.awFmParallelSearchCount(ip, sl.ptr, threads)
+            times.append(time.perf_counter() - t1)
+        assert lib.awFmGpuLastCountStatus() == abi.AwFmSuccess
+        e2e_counts = sl.entries()["count"][:sample]
+        if not np.array_equal(e2e_counts, h_counts_sample):
+            raise SystemExit("PARITY FAILURE: drop-in counts differ from the device-resident path")
+        t_step = sum(times) / len(times)
+        if world > 1:
+            t = torch.tensor([t_step], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_step = float(t.item())
+        e2e = {"value": world * n / t_step, "unit": UNIT, "h2d_bytes_per_step": n * L, "d2h_bytes_per_step": n * 4,
+               "call": "awFmParallelSearchCount(index, searchList, numThreads) drop-in, host AwFmKmerSearchList",
+               "host_threads": threads, "ms_per_step": 1e3 * t_step, "search_list_setup_s": round(list_s, 2)}
+        sl.close()
+        lib.awFmGpuReleaseIndex(ip)
+        del h_letters
+
+    # ---- cpu baseline (rank 0, N=1): the unmodified reference on the host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        ns = min(args.cpu_sample, n)
+        hs = d_letters[: ns * L].cpu().numpy()
+        if harness.have_reference():
+            ref = harness.Reference()
+            ix = host_index_struct(arrays)
+            best, times, r_counts = cpu_reference_pass(ref, C.addressof(ix), hs, ns, L, cores, reps=3)
+            ok = bool(np.array_equal(r_counts[:sample], h_counts_sample[: len(r_counts[:sample])]))
+            cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"first {ns} of the {n} queries, 1 warm-up + best of 3 passes of the reference's "
+                             f"awFmParallelSearchCount (oracle/_ref), numThreads={cores}",
+                   "bit_exact_vs_cuda": ok}
+        else:
+            t1 = time.perf_counter()
+            harness.Oracle(arrays).count(hs[: 1_000_000 * L], fixed_len=L, threads=cores)
+            dt = time.perf_counter() - t1
+            cpu = {"value": 1_000_000 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first 1000000 queries, scalar C oracle with OpenMP over queries"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    achieved = (bytes_per_query * n / (kernel_avg * 1e-3) / 1e9) if bytes_per_query else None
+    traffic = ncu_traffic_per_launch()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "countKernel (one launch over the rank's whole batch)", "kernel_ms": kernel_avg,
+                     "algorithmic_bytes_per_launch": bytes_per_query * n if bytes_per_query else None},
+        "cpu_baseline": cpu,
+        "index": {"device_bytes": gpu.device_bytes(), "build_s": round(build_s, 2), "build_gpu_ms": round(build_ms, 1),
+                  "tie_suffixes_resolved_on_host": tie_suffixes},
+    }
+    line.update(result)
+    print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,14 +43,22 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     if not args.skip_gather:
         gather_table(lib, out)
-    ref = harness.Reference()
+    from avxwindowfmindex_b200 import DeviceBuiltIndex
     t0 = time.time()
-    text = synth.random_text(args.bp)
-    ptr = ref.create_index(text.tobytes(), "/tmp/probe.awfmi", abi.AwFmAlphabetDna, args.seed_k, 8)
-    arrays = ref.arrays(ptr, copy=False)
+    d_text = torch.empty(args.bp, dtype=torch.uint8, device="cuda")
+    capi.check(lib.awfm_gpu_synth_letters(0, d_text.data_ptr(), args.bp, synth.TEXT_SEED, 0, 0))
+    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), args.bp, abi.AwFmAlphabetDna, args.seed_k, 8)
+    del d_text
+    torch.cuda.synchronize()
     out["build_s"] = round(time.time() - t0, 1)
-    print("index built", out["build_s"], "s", flush=True)
-    gpu = GpuIndex(arrays)
+    out["build_gpu_ms"] = built.build_ms
+    out["tie_suffixes"] = built.tie_suffixes
+    print("index built", out["build_s"], "s; gpu ms", built.build_ms, "ties", built.tie_suffixes, flush=True)
+    t0 = time.time()
+    arrays = built.to_host()
+    print("download", round(time.time() - t0, 1), "s", flush=True)
+    gpu = built.gpu_index()
+    built.close()
     out["device_bytes"] = gpu.device_bytes()
     n, L = args.queries, 20
     q = torch.from_numpy(synth.random_queries(n, L)).cuda()

@@ -17,7 +17,7 @@ GPU_SYMBOLS = [
     "awfm_gpu_count_host", "awfm_gpu_locate_host", "awfm_gpu_count_device", "awfm_gpu_scan_ranges_device",
     "awfm_gpu_locate_device", "awfm_gpu_search_list_count", "awfm_gpu_search_list_locate",
     "awfm_gpu_gather_bandwidth", "awfm_gpu_build_index", "awfm_gpu_build_index_host", "awfm_gpu_built_view",
-    "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters",
+    "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
 ]
 DROPIN_SYMBOLS = [
     "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",
@@ -83,6 +83,7 @@ def load():
     lib.awfm_gpu_built_destroy.argtypes = [vp]
     lib.awfm_gpu_built_destroy.restype = None
     lib.awfm_gpu_synth_letters.argtypes = [C.c_int, vp, u64, u64, u64, C.c_int]
+    lib.awfm_gpu_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     declare_search_list_api(lib)
     lib.awFmGpuReleaseIndex.argtypes = [vp]
     lib.awFmGpuReleaseIndex.restype = None

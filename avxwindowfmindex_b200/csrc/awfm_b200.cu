@@ -76,11 +76,11 @@ struct PipeSlot {  // one in-flight chunk of the search-list engine
 struct awfm_gpu_ctx {
   int device = 0, numSMs = 0;
   DevIndex ix{};
-  void *dLines = nullptr, *dXBase = nullptr, *dSeed = nullptr, *dSa = nullptr;
+  void *dLines = nullptr, *dXBase = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
   uint64_t deviceBytes = 0;
   bool hasSa = false;
   // tuning
-  int countLpq = 4, locateLpq = 1, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
+  int countLpq = 2, locateLpq = 1, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
   int64_t chunkQueries = 1 << 21;
   // scratch
   void *scanTemp = nullptr;
@@ -136,13 +136,32 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
     }                                                                  \
   } while (0)
 
+  // prefix sums first: the nucleotide superblock table folds C[c] in
+  uint64_t prefix[24] = {0};
+  if (fromDevice) CUB_(cudaMemcpy(prefix, v->prefixSums, numPrefix * 8, cudaMemcpyDeviceToHost));
+  else memcpy(prefix, v->prefixSums, numPrefix * 8);
+
   // blocks -> lines.  The raw copy is staged in slabs so peak extra memory stays small next to a 180 GB HBM.
-  const uint64_t lineBytes = amino ? 384u : 128u;
+  const uint64_t lineBytes = amino ? 384u : 128u;  // per 256 positions (nucleotide: two 64-B half-lines)
   CUB_(cudaMalloc(&c->dLines, v->numBlocks * lineBytes));
   c->deviceBytes += v->numBlocks * lineBytes;
+  uint64_t *dSuperCounts = nullptr;
   if (!amino) {
-    CUB_(cudaMalloc(&c->dXBase, v->numBlocks * 8));
+    CUB_(cudaMalloc(&c->dXBase, v->numBlocks * 2 * 4));
     c->deviceBytes += v->numBlocks * 8;
+    // superblock tables: counts at the first block of every 2^31-position superblock (5 letters, padded to 8)
+    const uint64_t numSuper = ((v->bwtLength - 1) >> kSuperShift) + 1;
+    std::vector<uint64_t> superCounts(numSuper * 8, 0), superC(numSuper * 8, 0);
+    for (uint64_t s = 0; s < numSuper; s++) {
+      const uint8_t *src = (const uint8_t *)v->blocks + ((s << kSuperShift) >> 8) * rawBlockBytes + 96;
+      if (fromDevice) CUB_(cudaMemcpy(&superCounts[s * 8], src, 5 * 8, cudaMemcpyDeviceToHost));
+      else memcpy(&superCounts[s * 8], src, 5 * 8);
+      for (int l = 0; l < 5; l++) superC[s * 8 + l] = prefix[l] + superCounts[s * 8 + l];
+    }
+    CUB_(cudaMalloc(&dSuperCounts, numSuper * 64));
+    CUB_(cudaMemcpy(dSuperCounts, superCounts.data(), numSuper * 64, cudaMemcpyHostToDevice));
+    CUB_(cudaMalloc(&c->dSuperC, numSuper * 64));
+    CUB_(cudaMemcpy(c->dSuperC, superC.data(), numSuper * 64, cudaMemcpyHostToDevice));
   }
   {
     const uint64_t slabBlocks = std::min<uint64_t>(v->numBlocks, 1u << 20);  // <= 352 MB staging
@@ -154,15 +173,17 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
       if (e == cudaSuccess) {
         const unsigned grid = (unsigned)((nb + 255) / 256);
         if (amino) relayoutAmino<<<grid, 256>>>(dRaw, nb, (uint4 *)c->dLines + b0 * kAminoLineU4);
-        else relayoutNucleotide<<<grid, 256>>>(dRaw, nb, (uint4 *)c->dLines + b0 * kNucLineU4, (uint64_t *)c->dXBase + b0);
+        else relayoutNucleotide<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines, (uint32_t *)c->dXBase);
         e = cudaDeviceSynchronize();
       }
       if (e != cudaSuccess) {
         cudaFree(dRaw);
+        cudaFree(dSuperCounts);
         CUB_(e);
       }
     }
     cudaFree(dRaw);
+    cudaFree(dSuperCounts);
   }
   // seed table
   const uint64_t numSeeds = numSeedsOf(v->alphabet, v->seedK);
@@ -180,15 +201,14 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   }
   DevIndex &ix = c->ix;
   ix.lines = (const uint4 *)c->dLines;
-  ix.xBase = (const uint64_t *)c->dXBase;
+  ix.xRel = (const uint32_t *)c->dXBase;
+  ix.superC = (const uint64_t *)c->dSuperC;
   ix.seedTable = (const uint4 *)c->dSeed;
   ix.sa = (const uint64_t *)c->dSa;
   ix.numBlocks = v->numBlocks;
   ix.bwtLength = v->bwtLength;
   ix.numSeeds = numSeeds;
-  memset(ix.prefixSums, 0, sizeof ix.prefixSums);
-  if (fromDevice) CUB_(cudaMemcpy(ix.prefixSums, v->prefixSums, numPrefix * 8, cudaMemcpyDeviceToHost));
-  else memcpy(ix.prefixSums, v->prefixSums, numPrefix * 8);
+  memcpy(ix.prefixSums, prefix, sizeof ix.prefixSums);
   ix.saBitWidth = v->saBitWidth;
   ix.saRatio = v->saRatio ? v->saRatio : 1;
   ix.saRatioShift = 0xFFFFFFFFu;
@@ -238,6 +258,7 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   }
   cudaFree(c->dLines);
   cudaFree(c->dXBase);
+  cudaFree(c->dSuperC);
   cudaFree(c->dSeed);
   cudaFree(c->dSa);
   cudaFree(c->scanTemp);
@@ -328,15 +349,22 @@ template <int LPQ, bool AMINO>
 static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *dHitOffsets, uint64_t n,
                         uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
   int grid = 0;
+  {  // BWT start position of every hit of the window, written into the output buffer itself
+    const uint64_t warps = (n + 31) / 32;
+    const int g = (int)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->numSMs * 8);
+    expandHits<<<std::max(g, 1), 256, 0, st>>>(dRanges, dHitOffsets, n, hb, he, dPos);
+    CU(cudaGetLastError());
+  }
   auto k = locateKernel<LPQ, AMINO>;
   if (int r = gridFor(c, k, 256, &grid)) return r;
   const uint64_t need = ((he - hb) * LPQ + 255) / 256;
   grid = (int)std::min<uint64_t>((uint64_t)grid, need);
-  k<<<grid, 256, 0, st>>>(c->ix, dRanges, dHitOffsets, n, hb, he, dPos);
+  k<<<grid, 256, 0, st>>>(c->ix, he - hb, dPos);
   CU(cudaGetLastError());
   return AWFM_GPU_OK;
 }
 
+// nucleotide half-lines have 4 chunks (groups of 1, 2 or 4 lanes); amino blocks 8 chunks (1, 2, 4 or 8 lanes)
 #define DISPATCH_LPQ(fn, lpq, amino, ...)                                  \
   ((amino) ? ((lpq) == 1   ? fn<1, true>(__VA_ARGS__)                      \
               : (lpq) == 2 ? fn<2, true>(__VA_ARGS__)                      \
@@ -344,8 +372,7 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
                            : fn<8, true>(__VA_ARGS__))                     \
            : ((lpq) == 1   ? fn<1, false>(__VA_ARGS__)                     \
               : (lpq) == 2 ? fn<2, false>(__VA_ARGS__)                     \
-              : (lpq) == 4 ? fn<4, false>(__VA_ARGS__)                     \
-                           : fn<8, false>(__VA_ARGS__)))
+                           : fn<4, false>(__VA_ARGS__)))
 
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
                            uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
@@ -410,7 +437,7 @@ static int locateDeviceImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, const ui
   int r = DISPATCH_LPQ(launchLocate, c->locateLpq, c->ix.amino != 0, c, (const uint4 *)dRanges, dHitOffsets, n, hb,
                        he, dPos, st);
   if (ev) CU(cudaEventRecord(ev->b, st));
-  c->stats.launches += 1;
+  c->stats.launches += 2;
   c->stats.hits += he - hb;
   return r;
 }
@@ -775,6 +802,16 @@ static int runGather(int lanes, const uint4 *d, uint64_t numRecords, uint64_t nu
   return AWFM_GPU_OK;
 }
 
+// L2 -> DRAM fetch granularity hint of the current device (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes).
+extern "C" int awfm_gpu_set_l2_fetch_granularity(int device, int bytes, int *actual) {
+  CU(cudaSetDevice(device));
+  if (bytes > 0) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  size_t v = 0;
+  CU(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+  if (actual) *actual = (int)v;
+  return AWFM_GPU_OK;
+}
+
 extern "C" int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32_t bytesPerRead, uint64_t numReads,
                                          int lanesPerRead, double *gbps) {
   if (!gbps || arrayBytes < 4096) return fail(AWFM_GPU_ERR_ARG, "bad argument");
@@ -799,7 +836,8 @@ extern "C" int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32
       case 32: r = runGather<32>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
       case 64: r = runGather<64>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
       case 128: r = runGather<128>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
-      default: r = fail(AWFM_GPU_ERR_ARG, "bytesPerRead must be 16, 32, 64 or 128");
+      case 256: r = runGather<256>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
+      default: r = fail(AWFM_GPU_ERR_ARG, "bytesPerRead must be 16, 32, 64, 128 or 256");
     }
     if (r) return r;
     CU(cudaEventRecord(b));

@@ -1,17 +1,21 @@
 // awfm_device.cuh — device-side data layout and rank/LF/backtrace primitives (sm_100a).
 //
-// HBM layout (built once at upload by relayout kernels in awfm_b200.cu from the unchanged reference blocks):
+// HBM layout (built once at upload by relayout kernels in awfm_kernels.cuh from the unchanged reference blocks):
 //
-//  nucleotide "line"  = 128 B, 128-B aligned, one per 256 BWT positions:
-//      8 chunks of 16 B; chunk j = { b0[j], b1[j], b2[j], cnt[j] }   (32-bit words)
-//      b_i[j]  = word j of letter bit-vector i  -> bit t of word j is block position 32*j + t
-//      cnt[2c], cnt[2c+1] = low / high 32 bits of baseOccurrences[c], c = A,C,G,T
-//      baseOccurrences[X] lives in a side array (xBase), the sentinel count is never needed by search.
-//    One rank = exactly one 128-B line = 4 sectors; lane j of an 8-lane group issues ONE 128-bit load and
-//    owns all three code bits of positions 32j..32j+31 (no bit-gather shuffles).
-//    Reference layout being replaced: struct AwFmNucleotideBlock, 160 B, 32-B aligned (src/AwFmIndex.h:61-65).
+//  nucleotide "half-line" = 64 B, 64-B aligned, one per 128 BWT positions:
+//      4 chunks of 16 B; chunk j = { b0[j], b1[j], b2[j], rel[j] }   (32-bit words)
+//      b_i[j] = bits of letter bit-vector i for positions 128*h + 32*j .. +31 (bit t <-> position 32*j + t)
+//      rel[c] = occurrences of letter c (A,C,G,T) in BWT[0, 128*h) minus the count at the start of the enclosing
+//               2^31-position superblock (fits 32 bits); absolute 64-bit superblock counts, already summed with the
+//               prefix sum C[c], sit in a tiny table (superC) that stays in L1/L2.
+//      The ambiguity letter's relative count lives in a side array (xRel); the sentinel count is never needed.
+//    One rank = exactly ONE 64-B DRAM request: lane j of a 4-lane group issues one 128-bit load and owns all three
+//    code bits of 32 positions (no bit-gather shuffles).  Measured on B200 (profiles/r01_probe_*.json): random
+//    64-B reads sustain ~39 G requests/s, random 128-B lines only ~24 G/s, which is why the first layout of this
+//    path (128-B lines holding 256 positions + 64-bit counts) was replaced.
+//    Reference layout: struct AwFmNucleotideBlock, 160 B per 256 positions, 32-B aligned (src/AwFmIndex.h:61-65).
 //
-//  amino "line triple" = 384 B, 128-B aligned:
+//  amino "line triple" = 384 B, 128-B aligned, one per 256 positions:
 //      [  0,128)  8 chunks { b0[j], b1[j], b2[j], b3[j] }
 //      [128,160)  b4[0..7]
 //      [160,328)  baseOccurrences[0..20] as u64 (A..Y, Z)
@@ -23,13 +27,15 @@
 
 namespace awfm {
 
-constexpr int kNucLineU4 = 8;     // uint4 per nucleotide line
-constexpr int kAminoLineU4 = 24;  // uint4 per amino line triple
+constexpr int kNucHalfU4 = 4;     // uint4 per nucleotide half-line (128 positions)
+constexpr int kAminoLineU4 = 24;  // uint4 per amino line triple (256 positions)
+constexpr int kSuperShift = 31;   // nucleotide superblock = 2^31 positions
 constexpr uint32_t kNucSentinel = 5, kAminoSentinel = 21;
 
 struct DevIndex {
-  const uint4 *lines;
-  const uint64_t *xBase;     // nucleotide only
+  const uint4 *lines;        // nucleotide: half-lines; amino: line triples
+  const uint32_t *xRel;      // nucleotide only: relative count of the ambiguity letter per half-line
+  const uint64_t *superC;    // nucleotide only: [superblock][8] = C[c] + count of c before the superblock, c = 0..4
   const uint4 *seedTable;    // {startLo, startHi, endLo, endHi}
   const uint64_t *sa;        // bit-packed sampled SA viewed as little-endian u64 words (+16 B zero padding)
   uint64_t numBlocks, bwtLength, numSeeds;
@@ -71,7 +77,7 @@ __device__ __forceinline__ uint32_t letterIndex(uint32_t ascii) {
 // Derived from the boolean forms of src/AwFmOccurrence.c:18-35 (nucleotide) and :65-134 (amino). ----
 __device__ __forceinline__ uint32_t nucCodeCare(uint32_t letter) {
   // nibble pairs, low nibble = code, high nibble = care: A(6,6) C(5,5) G(3,3) T(1,7) X(2,7)
-  return (0x7271335566ull >> (letter * 8u)) & 0xFFu;
+  return (uint32_t)(0x7271335566ull >> (letter * 8u)) & 0xFFu;
 }
 static __constant__ uint16_t kAminoCodeCare[21] = {
     // (care << 8) | code
@@ -80,22 +86,30 @@ static __constant__ uint16_t kAminoCodeCare[21] = {
 // code -> letter index (src/AwFmLetter.c:49-53, :89-96)
 __device__ __forceinline__ uint32_t nucCodeToLetter(uint32_t code) { return (0x00152435u >> (code * 4u)) & 0xFu; }
 static __constant__ uint8_t kAminoCodeToLetter[32] = {21, 18, 19, 2,  13, 16, 3,  20, 11, 12, 15, 20, 0, 20, 20, 20,
-                                               20, 20, 20, 14, 20, 8,  17, 1,  20, 7,  5,  6,  9, 10, 4,  20};
+                                                      20, 20, 20, 14, 20, 8,  17, 1,  20, 7,  5,  6,  9, 10, 4,  20};
 
-// mask of bits 0..rel inclusive of a 32-bit word whose first bit is block position 32*chunk, for an inclusive
-// block-local query position `local` (AwFmMaskedVectorPopcount semantics, src/AwFmSimdConfig.c:89-114)
-__device__ __forceinline__ uint32_t inclusiveMask(uint32_t local, uint32_t chunk) {
-  const int rel = (int)local - (int)(chunk * 32u);
-  return rel >= 31 ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
+// mask of the low `n` bits with n clamped to [0, 32] (one BMSK after a max with zero)
+__device__ __forceinline__ uint32_t lowBits(int n) {
+  uint32_t m;
+  const uint32_t width = (uint32_t)max(n, 0);
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(width));
+  return m;
 }
-
-__device__ __forceinline__ uint4 ldLine(const uint4 *p) { return __ldg(p); }
+// mask of the bits of a 32-bit word (first bit = block position 32*chunk) at block positions <= local, INCLUSIVE
+// (AwFmMaskedVectorPopcount semantics, src/AwFmSimdConfig.c:89-114)
+__device__ __forceinline__ uint32_t inclusiveMask(uint32_t local, uint32_t chunk) {
+  return lowBits((int)local + 1 - (int)(chunk * 32u));
+}
 
 template <int LPQ>
 __device__ __forceinline__ unsigned groupMaskOf() {
   if (LPQ == 32) return 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
   return ((1u << LPQ) - 1u) << (lane / LPQ * LPQ);
+}
+template <int LPQ>
+__device__ __forceinline__ unsigned groupBaseLane() {
+  return (threadIdx.x & 31u) / LPQ * LPQ;
 }
 
 template <int LPQ>
@@ -104,8 +118,14 @@ __device__ __forceinline__ uint64_t groupSum(uint64_t v, unsigned mask) {
   for (int d = LPQ / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d, LPQ);
   return v;
 }
+template <int LPQ>
+__device__ __forceinline__ uint32_t groupSum32(uint32_t v, unsigned mask) {
+#pragma unroll
+  for (int d = LPQ / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d, LPQ);
+  return v;
+}
 
-// Selector masks for one LF/backtrace step, expanded to 32-bit lanes: x_i = b_i ^ flip_i, y_i = x_i | dontcare_i
+// Selector masks for one LF/backtrace step, expanded to 32-bit lanes: y_i = (b_i ^ flip_i) | dontcare_i (one LOP3)
 struct Selector {
   uint32_t flip[5], dontcare[5];
 };
@@ -113,7 +133,7 @@ template <bool AMINO>
 __device__ __forceinline__ Selector makeSelector(uint32_t letter) {
   Selector s;
   uint32_t code, care;
-  if (AMINO) {
+  if constexpr (AMINO) {
     const uint32_t cc = kAminoCodeCare[letter];
     code = cc & 0xFFu;
     care = cc >> 8;
@@ -130,37 +150,44 @@ __device__ __forceinline__ Selector makeSelector(uint32_t letter) {
   return s;
 }
 
-// ---- rank of `letter` at inclusive position `pos`, cooperative over an LPQ-lane group ----
-// Every lane returns baseOccurrences[letter] + popcount(select(letter) & bits 0..pos%256).
+// ================================================================================================ nucleotide
+// LPQ lanes (1, 2 or 4) cooperate on one half-line; lane `sub` holds chunks sub, sub+LPQ, ...
 template <int LPQ>
 struct NucLoad {
-  uint4 v[8 / LPQ];
+  uint4 v[4 / LPQ];
 };
 template <int LPQ>
-__device__ __forceinline__ NucLoad<LPQ> nucIssue(const DevIndex &ix, uint64_t block, unsigned sub) {
+__device__ __forceinline__ NucLoad<LPQ> nucIssue(const DevIndex &ix, uint64_t half, unsigned sub) {
   NucLoad<LPQ> l;
-  const uint4 *line = ix.lines + block * kNucLineU4;
+  const uint4 *line = ix.lines + half * kNucHalfU4;
 #pragma unroll
-  for (int i = 0; i < 8 / LPQ; i++) l.v[i] = ldLine(line + sub + LPQ * i);
+  for (int i = 0; i < 4 / LPQ; i++) l.v[i] = __ldg(line + sub + LPQ * i);
   return l;
 }
+// this lane's share of popcount(select(letter) & positions 0..local)
 template <int LPQ>
-__device__ __forceinline__ uint64_t nucPartial(const NucLoad<LPQ> &l, const Selector &s, uint32_t letter,
-                                               uint32_t local, unsigned sub) {
-  uint64_t acc = 0;
+__device__ __forceinline__ uint32_t nucPop(const NucLoad<LPQ> &l, const Selector &s, uint32_t local, unsigned sub) {
+  uint32_t acc = 0;
 #pragma unroll
-  for (int i = 0; i < 8 / LPQ; i++) {
-    const uint32_t chunk = sub + LPQ * i;
+  for (int i = 0; i < 4 / LPQ; i++) {
     const uint4 v = l.v[i];
     const uint32_t sel = ((v.x ^ s.flip[0]) | s.dontcare[0]) & ((v.y ^ s.flip[1]) | s.dontcare[1]) &
                          ((v.z ^ s.flip[2]) | s.dontcare[2]);
-    acc += __popc(sel & inclusiveMask(local, chunk));
-    acc += (chunk == 2u * letter) ? (uint64_t)v.w : 0ull;
-    acc += (chunk == 2u * letter + 1u) ? ((uint64_t)v.w << 32) : 0ull;
+    acc += __popc(sel & inclusiveMask(local, sub + LPQ * i));
   }
   return acc;
 }
+// relative count word of `letter` (0..3): chunk `letter` of the half-line, fetched from the lane that loaded it
+template <int LPQ>
+__device__ __forceinline__ uint32_t nucRel(const NucLoad<LPQ> &l, uint32_t letter, unsigned sub, unsigned mask) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 4 / LPQ; i++) w = (sub + LPQ * i == letter) ? l.v[i].w : w;
+  if (LPQ > 1) w = __shfl_sync(mask, w, groupBaseLane<LPQ>() + (letter % LPQ));
+  return w;
+}
 
+// ================================================================================================ amino
 template <int LPQ>
 struct AminoLoad {
   uint4 v[8 / LPQ];
@@ -174,72 +201,82 @@ __device__ __forceinline__ AminoLoad<LPQ> aminoIssue(const DevIndex &ix, uint64_
   const uint4 *line = ix.lines + block * kAminoLineU4;
 #pragma unroll
   for (int i = 0; i < 8 / LPQ; i++) {
-    l.v[i] = ldLine(line + sub + LPQ * i);
+    l.v[i] = __ldg(line + sub + LPQ * i);
     l.b4[i] = __ldg(reinterpret_cast<const uint32_t *>(line + 8) + sub + LPQ * i);
   }
   l.base = __ldg(reinterpret_cast<const uint64_t *>(line + 10) + letter);
   return l;
 }
 template <int LPQ>
-__device__ __forceinline__ uint64_t aminoPartial(const AminoLoad<LPQ> &l, const Selector &s, uint32_t local,
-                                                 unsigned sub) {
-  uint64_t acc = 0;
+__device__ __forceinline__ uint32_t aminoPop(const AminoLoad<LPQ> &l, const Selector &s, uint32_t local,
+                                             unsigned sub) {
+  uint32_t acc = 0;
 #pragma unroll
   for (int i = 0; i < 8 / LPQ; i++) {
-    const uint32_t chunk = sub + LPQ * i;
     const uint4 v = l.v[i];
     const uint32_t sel = ((v.x ^ s.flip[0]) | s.dontcare[0]) & ((v.y ^ s.flip[1]) | s.dontcare[1]) &
                          ((v.z ^ s.flip[2]) | s.dontcare[2]) & ((v.w ^ s.flip[3]) | s.dontcare[3]) &
                          ((l.b4[i] ^ s.flip[4]) | s.dontcare[4]);
-    acc += __popc(sel & inclusiveMask(local, chunk));
+    acc += __popc(sel & inclusiveMask(local, sub + LPQ * i));
   }
   return acc;
 }
 
+// ================================================================================================ LF step
 // One LF-mapping step (src/AwFmSearch.c:42-159): sp' = C[c] + Occ(c, sp-1), ep' = C[c] + Occ(c, ep) - 1.
-// Both block lines are requested before either is consumed (two independent misses in flight per group).
+// Both blocks are requested before either is consumed (two independent misses in flight per group); the two
+// partial popcounts travel through the group reduction packed in one 32-bit register.
+// Nucleotide groups are 1, 2 or 4 lanes (half-line = 4 chunks); amino groups 1, 2, 4 or 8 lanes (8 chunks).
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_t &ep, uint32_t letter,
                                        unsigned sub, unsigned mask) {
   const uint64_t pa = sp - 1, pb = ep;
-  const uint64_t ba = pa >> 8, bb = pb >> 8;
   const Selector s = makeSelector<AMINO>(letter);
-  uint64_t ra, rb;
-  if (AMINO) {
-    const AminoLoad<LPQ> la = aminoIssue<LPQ>(ix, ba, letter, sub);
-    const AminoLoad<LPQ> lb = aminoIssue<LPQ>(ix, bb, letter, sub);
-    ra = groupSum<LPQ>(aminoPartial<LPQ>(la, s, (uint32_t)pa & 255u, sub), mask) + la.base;
-    rb = groupSum<LPQ>(aminoPartial<LPQ>(lb, s, (uint32_t)pb & 255u, sub), mask) + lb.base;
+  if constexpr (AMINO) {
+    const AminoLoad<LPQ> la = aminoIssue<LPQ>(ix, pa >> 8, letter, sub);
+    const AminoLoad<LPQ> lb = aminoIssue<LPQ>(ix, pb >> 8, letter, sub);
+    const uint32_t packed = groupSum32<LPQ>(aminoPop<LPQ>(la, s, (uint32_t)pa & 255u, sub) |
+                                                (aminoPop<LPQ>(lb, s, (uint32_t)pb & 255u, sub) << 16),
+                                            mask);
+    const uint64_t c = ix.prefixSums[letter];
+    sp = c + la.base + (packed & 0xFFFFu);
+    ep = c + lb.base + (packed >> 16) - 1;
   } else {
-    const NucLoad<LPQ> la = nucIssue<LPQ>(ix, ba, sub);
-    const NucLoad<LPQ> lb = nucIssue<LPQ>(ix, bb, sub);
-    uint64_t xa = 0, xb = 0;
-    if (letter == 4u) {  // ambiguity letter: base count from the side array
-      xa = __ldg(ix.xBase + ba);
-      xb = __ldg(ix.xBase + bb);
+    static_assert(AMINO || LPQ <= 4, "nucleotide half-lines have 4 chunks");
+    const uint64_t ha = pa >> 7, hb = pb >> 7;
+    const NucLoad<LPQ> la = nucIssue<LPQ>(ix, ha, sub);
+    const NucLoad<LPQ> lb = nucIssue<LPQ>(ix, hb, sub);
+    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * 8 + letter);
+    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * 8 + letter);
+    uint32_t ra, rb;
+    if (letter == 4u) {  // ambiguity letter: relative count from the side array
+      ra = __ldg(ix.xRel + ha);
+      rb = __ldg(ix.xRel + hb);
+    } else {
+      ra = nucRel<LPQ>(la, letter, sub, mask);
+      rb = nucRel<LPQ>(lb, letter, sub, mask);
     }
-    ra = groupSum<LPQ>(nucPartial<LPQ>(la, s, letter, (uint32_t)pa & 255u, sub), mask) + xa;
-    rb = groupSum<LPQ>(nucPartial<LPQ>(lb, s, letter, (uint32_t)pb & 255u, sub), mask) + xb;
+    const uint32_t packed = groupSum32<LPQ>(nucPop<LPQ>(la, s, (uint32_t)pa & 127u, sub) |
+                                                (nucPop<LPQ>(lb, s, (uint32_t)pb & 127u, sub) << 16),
+                                            mask);
+    sp = ca + ra + (packed & 0xFFFFu);
+    ep = cb + rb + (packed >> 16) - 1;
   }
-  const uint64_t c = ix.prefixSums[letter];
-  sp = c + ra;
-  ep = c + rb - 1;
 }
 
 // One backtrace step (src/AwFmSearch.c:369-427): c = BWT[p]; sentinel -> 0; else C[c] + Occ(c, p) - 1.
-// The letter and the rank come from the SAME line load.
+// The letter and the rank come from the SAME block load.
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p, unsigned sub, unsigned mask) {
-  const uint64_t block = p >> 8;
-  const uint32_t local = (uint32_t)p & 255u, ownerChunk = local >> 5, bit = local & 31u;
-  const unsigned groupBase = (threadIdx.x & 31u) / LPQ * LPQ;
-  if (AMINO) {
+  if constexpr (AMINO) {
+    const uint64_t block = p >> 8;
+    const uint32_t local = (uint32_t)p & 255u, ownerChunk = local >> 5, bit = local & 31u;
     const uint4 *line = ix.lines + block * kAminoLineU4;
     AminoLoad<LPQ> l;
     uint32_t code = 0;
 #pragma unroll
     for (int i = 0; i < 8 / LPQ; i++) {
-      l.v[i] = ldLine(line + sub + LPQ * i);
+      l.v[i] = __ldg(line + sub + LPQ * i);
       l.b4[i] = __ldg(reinterpret_cast<const uint32_t *>(line + 8) + sub + LPQ * i);
     }
 #pragma unroll
@@ -249,29 +286,31 @@ __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p
                          (((v.w >> bit) & 1u) << 3) | (((l.b4[i] >> bit) & 1u) << 4);
       code = (sub + LPQ * i == ownerChunk) ? c : code;
     }
-    code = __shfl_sync(mask, code, groupBase + (ownerChunk % LPQ));
+    if (LPQ > 1) code = __shfl_sync(mask, code, groupBaseLane<LPQ>() + (ownerChunk % LPQ));
     const uint32_t letter = kAminoCodeToLetter[code];
     if (letter == kAminoSentinel) return 0;
     const uint64_t base = __ldg(reinterpret_cast<const uint64_t *>(line + 10) + letter);
     const Selector s = makeSelector<true>(letter);
-    const uint64_t r = groupSum<LPQ>(aminoPartial<LPQ>(l, s, local, sub), mask) + base;
-    return ix.prefixSums[letter] + r - 1;
+    const uint32_t pop = groupSum32<LPQ>(aminoPop<LPQ>(l, s, local, sub), mask);
+    return ix.prefixSums[letter] + base + pop - 1;
   } else {
-    const NucLoad<LPQ> l = nucIssue<LPQ>(ix, block, sub);
+    const uint64_t half = p >> 7;
+    const uint32_t local = (uint32_t)p & 127u, ownerChunk = local >> 5, bit = local & 31u;
+    const NucLoad<LPQ> l = nucIssue<LPQ>(ix, half, sub);
     uint32_t code = 0;
 #pragma unroll
-    for (int i = 0; i < 8 / LPQ; i++) {
+    for (int i = 0; i < 4 / LPQ; i++) {
       const uint4 v = l.v[i];
       const uint32_t c = ((v.x >> bit) & 1u) | (((v.y >> bit) & 1u) << 1) | (((v.z >> bit) & 1u) << 2);
       code = (sub + LPQ * i == ownerChunk) ? c : code;
     }
-    code = __shfl_sync(mask, code, groupBase + (ownerChunk % LPQ));
+    if (LPQ > 1) code = __shfl_sync(mask, code, groupBaseLane<LPQ>() + (ownerChunk % LPQ));
     const uint32_t letter = nucCodeToLetter(code);
     if (letter == kNucSentinel) return 0;
     const Selector s = makeSelector<false>(letter);
-    uint64_t r = groupSum<LPQ>(nucPartial<LPQ>(l, s, letter, local, sub), mask);
-    if (letter == 4u) r += __ldg(ix.xBase + block);
-    return ix.prefixSums[letter] + r - 1;
+    const uint32_t rel = (letter == 4u) ? __ldg(ix.xRel + half) : nucRel<LPQ>(l, letter, sub, mask);
+    const uint32_t pop = groupSum32<LPQ>(nucPop<LPQ>(l, s, local, sub), mask);
+    return __ldg(ix.superC + (p >> kSuperShift) * 8 + letter) + rel + pop - 1;
   }
 }
 

@@ -261,49 +261,100 @@ __global__ void __launch_bounds__(256)
 // position = (SA[p / ratio] + offset) mod bwtLength (src/AwFmSuffixArray.c:179-203).
 // Hit h of the flat CSR list belongs to the query q with hitOffsets[q] <= h < hitOffsets[q+1].
 // ---------------------------------------------------------------------------------------------------------------
+// Step 1, expandHits: positions[h - hitBegin] = sp(q) + (h - hitOffsets[q]) for every flat hit index h of the
+// window, written by one warp per 32 queries (lanes stride over a query's hits, so a query with millions of hits
+// is as cheap per hit as one with a single hit).
+__global__ void __launch_bounds__(256)
+    expandHits(const uint4 *__restrict__ ranges, const uint64_t *__restrict__ hitOffsets, uint64_t numQueries,
+               uint64_t hitBegin, uint64_t hitEnd, uint64_t *__restrict__ positions) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t numWarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t q0 = warp * 32; q0 < numQueries; q0 += numWarps * 32) {
+    const uint64_t q = q0 + lane;
+    uint64_t a = 0, b = 0, sp = 0;
+    if (q < numQueries) {
+      a = __ldg(hitOffsets + q);
+      b = __ldg(hitOffsets + q + 1);
+      const uint4 r = __ldg(ranges + q);
+      sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
+    }
+    const bool live = b > a && b > hitBegin && a < hitEnd;
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t qa = __shfl_sync(0xFFFFFFFFu, a, src), qb = __shfl_sync(0xFFFFFFFFu, b, src);
+      const uint64_t qsp = __shfl_sync(0xFFFFFFFFu, sp, src);
+      const uint64_t lo = max(qa, hitBegin), hi = min(qb, hitEnd);
+      for (uint64_t h = lo + lane; h < hi; h += 32) positions[h - hitBegin] = qsp + (h - qa);
+    }
+  }
+}
+
+// Step 2, locateKernel: in place, positions[i] holds a BWT position on entry and the text position on exit.
 template <int LPQ, bool AMINO>
 __global__ void __launch_bounds__(256)
-    locateKernel(const __grid_constant__ DevIndex ix, const uint4 *__restrict__ ranges,
-                 const uint64_t *__restrict__ hitOffsets, uint64_t numQueries, uint64_t hitBegin, uint64_t hitEnd,
-                 uint64_t *__restrict__ positions) {
+    locateKernel(const __grid_constant__ DevIndex ix, uint64_t numHits, uint64_t *__restrict__ positions) {
   const unsigned sub = threadIdx.x % LPQ;
   const unsigned mask = groupMaskOf<LPQ>();
   const uint64_t numGroups = (uint64_t)gridDim.x * blockDim.x / LPQ;
-  for (uint64_t h = hitBegin + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPQ; h < hitEnd;
-       h += numGroups) {
-    // upper_bound(hitOffsets, h) - 1
-    uint64_t lo = 0, hi = numQueries;  // invariant: hitOffsets[lo] <= h < hitOffsets[hi]
-    while (hi - lo > 1) {
-      const uint64_t mid = lo + (hi - lo) / 2;
-      if (__ldg(hitOffsets + mid) <= h) lo = mid;
-      else hi = mid;
-    }
-    const uint4 r = __ldg(ranges + lo);
-    uint64_t p = ((uint64_t)r.x | ((uint64_t)r.y << 32)) + (h - __ldg(hitOffsets + lo));
+  for (uint64_t h = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPQ; h < numHits; h += numGroups) {
+    uint64_t p = positions[h];
+    if (LPQ > 1) __syncwarp(mask);  // every lane of the group has read the slot before lane 0 overwrites it
     uint64_t offset = 0;
     while (!isSampled(ix, p)) {
       p = backtraceStep<LPQ, AMINO>(ix, p, sub, mask);
       offset++;
     }
-    if (sub == 0) positions[h - hitBegin] = (saValue(ix, sampleIndexOf(ix, p)) + offset) % ix.bwtLength;
+    if (sub == 0) positions[h] = (saValue(ix, sampleIndexOf(ix, p)) + offset) % ix.bwtLength;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // upload-time relayout: reference blocks -> lines (one thread per block)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void relayoutNucleotide(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint4 *__restrict__ lines,
-                                   uint64_t *__restrict__ xBase) {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= numBlocks) return;
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + b * 160);  // 160 B blocks are 32-B aligned
-  const uint64_t *base = reinterpret_cast<const uint64_t *>(raw + b * 160 + 96);
+// One thread per reference block (256 positions) -> two half-lines.  `superCounts[s][c]` = baseOccurrences[c] of the
+// block that starts superblock s (read from the raw blocks by the host before this kernel runs); `firstBlock` is the
+// global index of raw[0] (blocks are relaid in slabs).  Counts at the middle of the block = base + popcount of the
+// letter's selector over its first 128 positions.
+__global__ void relayoutNucleotide(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+                                   const uint64_t *__restrict__ superCounts /* [numSuper][8] */,
+                                   uint4 *__restrict__ halves, uint32_t *__restrict__ xRel) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numBlocks) return;
+  const uint64_t b = firstBlock + i;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + i * 160);  // 160 B blocks are 32-B aligned
+  const uint64_t *base = reinterpret_cast<const uint64_t *>(raw + i * 160 + 96);
+  const uint64_t *super = superCounts + ((b * 256) >> kSuperShift) * 8;
+  uint32_t w[3][8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const uint64_t c = base[j >> 1];
-    lines[b * kNucLineU4 + j] = make_uint4(src[j], src[8 + j], src[16 + j], (j & 1) ? (uint32_t)(c >> 32) : (uint32_t)c);
+  for (int v = 0; v < 3; v++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[v][j] = src[8 * v + j];
+  uint32_t rel[2][5];
+#pragma unroll
+  for (int c = 0; c < 5; c++) {
+    const uint32_t cc = nucCodeCare(c), code = cc & 0xFu, care = cc >> 4;
+    uint32_t firstHalf = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t sel = 0xFFFFFFFFu;
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+        if ((care >> v) & 1u) sel &= ((code >> v) & 1u) ? w[v][j] : ~w[v][j];
+      firstHalf += __popc(sel);
+    }
+    rel[0][c] = (uint32_t)(base[c] - super[c]);
+    rel[1][c] = rel[0][c] + firstHalf;
   }
-  xBase[b] = base[4];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      halves[(2 * b + h) * kNucHalfU4 + j] = make_uint4(w[0][4 * h + j], w[1][4 * h + j], w[2][4 * h + j], rel[h][j]);
+    xRel[2 * b + h] = rel[h][4];
+  }
 }
 
 __global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint4 *__restrict__ lines) {
@@ -339,20 +390,28 @@ __global__ void gatherProbe(const uint4 *__restrict__ data, uint64_t numRecords,
   const unsigned sub = threadIdx.x % LANES;
   const uint64_t numGroups = (uint64_t)gridDim.x * blockDim.x / LANES;
   uint64_t acc = 0;
-  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; i < numReads; i += numGroups) {
-    uint64_t z = i + 0x9E3779B97F4A7C15ull;  // splitmix64
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const uint64_t rec = z % numRecords;
+  constexpr int UNROLL = 4;  // independent records in flight per group
+  for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; i0 < numReads;
+       i0 += numGroups * UNROLL) {
+    uint4 v[UNROLL][PER_LANE];
 #pragma unroll
-    for (int k = 0; k < PER_LANE; k++) {
-      const int c = sub + LANES * k;
-      if (c < U4) {
-        const uint4 v = __ldg(data + rec * U4 + c);
-        acc += v.x ^ v.y ^ v.z ^ v.w;
+    for (int u = 0; u < UNROLL; u++) {
+      const uint64_t i = i0 + (uint64_t)u * numGroups;
+      uint64_t z = i + 0x9E3779B97F4A7C15ull;  // splitmix64
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      const uint64_t rec = z % numRecords;
+#pragma unroll
+      for (int k = 0; k < PER_LANE; k++) {
+        const int c = sub + LANES * k;
+        v[u][k] = (c < U4 && i < numReads) ? __ldg(data + rec * U4 + c) : make_uint4(0, 0, 0, 0);
       }
     }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int k = 0; k < PER_LANE; k++) acc += v[u][k].x ^ v[u][k].y ^ v[u][k].z ^ v[u][k].w;
   }
   if (acc == 0x1234567ull) sink[0] = acc;  // keep the loads alive
 }

@@ -155,6 +155,10 @@ int awfm_gpu_synth_letters(int device, uint8_t *dOut, uint64_t count, uint64_t s
 int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32_t bytesPerRead, uint64_t numReads,
                               int lanesPerRead, double *gbps);
 
+/* Sets (bytes = 32, 64, 128) or just queries (bytes = 0) the device's L2->DRAM fetch granularity hint
+ * (cudaLimitMaxL2FetchGranularity).  Random 64-B half-line reads waste half of every 128-B fetch otherwise. */
+int awfm_gpu_set_l2_fetch_granularity(int device, int bytes, int *actual);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,10 +18,10 @@ from avxwindowfmindex_b200 import GpuIndex, abi, capi, synth  # noqa: E402
 def gather_table(lib, out):
     gb = C.c_double()
     rows = []
-    for array_mb, rec, lanes, reads in [(2048, 128, 8, 1 << 26), (2048, 128, 4, 1 << 26), (2048, 128, 2, 1 << 26),
-                                        (2048, 128, 1, 1 << 26), (2048, 64, 4, 1 << 26), (2048, 32, 2, 1 << 26),
-                                        (2048, 32, 1, 1 << 26), (256, 16, 1, 1 << 26), (2048, 16, 1, 1 << 26),
-                                        (16384, 128, 8, 1 << 27)]:
+    for array_mb, rec, lanes, reads in [(2048, 256, 8, 1 << 26), (2048, 128, 8, 1 << 27), (2048, 128, 4, 1 << 27),
+                                        (2048, 64, 4, 1 << 27), (2048, 64, 2, 1 << 27), (2048, 64, 1, 1 << 27),
+                                        (2048, 32, 2, 1 << 27), (2048, 32, 1, 1 << 27), (256, 16, 1, 1 << 27),
+                                        (2048, 16, 1, 1 << 27), (16384, 64, 4, 1 << 27)]:
         capi.check(lib.awfm_gpu_gather_bandwidth(0, array_mb << 20, rec, reads, lanes, C.byref(gb)))
         rows.append({"array_MB": array_mb, "record_B": rec, "lanes": lanes, "GBps": round(gb.value, 1),
                      "Greads_per_s": round(gb.value / rec, 3)})
@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--queries", type=int, default=20_000_000)
     ap.add_argument("--seed-k", type=int, default=12)
     ap.add_argument("--skip-gather", action="store_true")
+    ap.add_argument("--only-gather", action="store_true")
     args = ap.parse_args()
     import torch
     from oracle import harness
@@ -43,6 +44,9 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     if not args.skip_gather:
         gather_table(lib, out)
+    if args.only_gather:
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe_gather.json"), "w"), indent=1)
+        return
     from avxwindowfmindex_b200 import DeviceBuiltIndex
     t0 = time.time()
     d_text = torch.empty(args.bp, dtype=torch.uint8, device="cuda")

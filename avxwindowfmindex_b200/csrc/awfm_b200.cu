@@ -62,7 +62,7 @@ struct EventPair {
 
 struct PipeSlot {  // one in-flight chunk of the search-list engine
   uint8_t *hLetters = nullptr, *dLetters = nullptr;
-  uint64_t lettersCap = 0;
+  uint64_t lettersCap = 0, dLettersCap = 0;
   uint64_t *hOffsets = nullptr, *dOffsets = nullptr;
   uint32_t *hCounts = nullptr, *dCounts = nullptr;
   uint4 *dRanges = nullptr;
@@ -81,7 +81,7 @@ struct awfm_gpu_ctx {
   bool hasSa = false;
   // tuning
   int countLpq = 2, locateLpq = 1, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
-  int64_t chunkQueries = 1 << 21;
+  int64_t chunkQueries = 1 << 18;
   // scratch
   void *scanTemp = nullptr;
   size_t scanTempBytes = 0;
@@ -556,44 +556,118 @@ static int ensureSlot(PipeSlot &s, uint64_t queries, uint64_t letterBytes, bool 
   if (wantRanges && !s.dRanges) CU(cudaMalloc(&s.dRanges, s.queryCap * 16));
   if (s.lettersCap < letterBytes) {
     if (s.hLetters) cudaFreeHost(s.hLetters);
-    cudaFree(s.dLetters);
-    s.hLetters = nullptr, s.dLetters = nullptr;
+    s.hLetters = nullptr;
     s.lettersCap = 0;
     const uint64_t cap = letterBytes + letterBytes / 4 + 64;
     CU(cudaHostAlloc(&s.hLetters, cap, cudaHostAllocDefault));
-    CU(cudaMalloc(&s.dLetters, cap));
     s.lettersCap = cap;
   }
   return AWFM_GPU_OK;
 }
 
-// Packs queries [first, first+n) into the slot's pinned staging.  Returns the uniform length, or 0 if lengths differ
-// (then hOffsets is authoritative).  Two passes so each thread knows where its letters go.
+static int ensureDeviceLetters(PipeSlot &s, uint64_t letterBytes) {
+  if (s.dLettersCap < letterBytes + 16) {
+    cudaFree(s.dLetters);
+    s.dLetters = nullptr;
+    s.dLettersCap = 0;
+    const uint64_t cap = letterBytes + letterBytes / 4 + 64;
+    CU(cudaMalloc(&s.dLetters, cap));
+    s.dLettersCap = cap;
+  }
+  return AWFM_GPU_OK;
+}
+
+// Small fixed-length copy without a libc call: two overlapping 16-B (or 8-/4-B) moves cover any length <= 32.
+static inline void copyLetters(uint8_t *dst, const uint8_t *src, uint64_t len) {
+  if (len >= 16 && len <= 32) {
+    uint64_t a0, a1, b0, b1;
+    memcpy(&a0, src, 8), memcpy(&a1, src + 8, 8);
+    memcpy(&b0, src + len - 16, 8), memcpy(&b1, src + len - 8, 8);
+    memcpy(dst, &a0, 8), memcpy(dst + 8, &a1, 8);
+    memcpy(dst + len - 16, &b0, 8), memcpy(dst + len - 8, &b1, 8);
+  } else if (len >= 8 && len < 16) {
+    uint64_t a, b;
+    memcpy(&a, src, 8), memcpy(&b, src + len - 8, 8);
+    memcpy(dst, &a, 8), memcpy(dst + len - 8, &b, 8);
+  } else {
+    memcpy(dst, src, len);
+  }
+}
+
+struct Packed {
+  uint32_t uniformLen = 0;        // != 0: every query of the chunk has this length (offsets not needed)
+  uint64_t letterBytes = 0;
+  const uint8_t *source = nullptr;  // where the H2D copy reads from: the slot's staging or the caller's own buffer
+};
+
+static bool isPinnedHost(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Packs queries [first, first+n) for shipping.  Fast path (one pass over the 32-B entries): all lengths equal; if the
+// strings are also laid out back to back in page-locked memory the copy is skipped and the DMA reads the caller's
+// buffer directly.  General path: two passes (lengths -> offsets, then copy).
 static int packChunk(PipeSlot &s, const awfm_kmer_search_data *data, uint64_t first, uint64_t n, int threads,
-                     bool wantRanges, uint32_t *uniformLen, uint64_t *letterBytes) {
-  threads = std::max(1, std::min<int>(threads, (int)std::max<uint64_t>(1, n / 4096)));
+                     bool wantRanges, bool sourcePinned, Packed *out) {
+  threads = std::max(1, std::min<int>(threads, (int)std::max<uint64_t>(1, n / 2048)));
+  const awfm_kmer_search_data *d0 = data + first;
+  const uint64_t len0 = d0[0].kmerLength;
+  if (len0 >= 1 && len0 <= 65536) {
+    const uint8_t *base = (const uint8_t *)d0[0].kmerString;
+    // cheap probe before committing to the copy-free variant
+    bool direct = sourcePinned && (const uint8_t *)d0[n - 1].kmerString == base + (n - 1) * len0 &&
+                  (const uint8_t *)d0[n / 2].kmerString == base + (n / 2) * len0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (int r = ensureSlot(s, n, direct ? 16 : n * len0 + 16, wantRanges)) return r;
+      uint8_t *dst = s.hLetters;
+      int uniform = 1, contiguous = 1;
+#pragma omp parallel num_threads(threads) reduction(&& : uniform, contiguous)
+      {
+        const int t = omp_get_thread_num();
+        const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
+        bool uni = true, con = true;
+        if (direct) {
+          for (uint64_t i = a; i < b; i++) {
+            uni &= d0[i].kmerLength == len0;
+            con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+          }
+        } else {
+          for (uint64_t i = a; i < b && uni; i++) {
+            uni = d0[i].kmerLength == len0;
+            if (uni) copyLetters(dst + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+          }
+        }
+        uniform = uni;
+        contiguous = con;
+      }
+      if (!uniform) break;  // general path below
+      if (direct && !contiguous) {
+        direct = false;  // the probe was too optimistic: pack with the copy
+        continue;
+      }
+      out->uniformLen = (uint32_t)len0;
+      out->letterBytes = n * len0;
+      out->source = direct ? base : s.hLetters;
+      return AWFM_GPU_OK;
+    }
+  }
   std::vector<uint64_t> partSum(threads + 1, 0);
-  std::vector<uint8_t> partUniform(threads, 1);
-  const uint64_t len0 = data[first].kmerLength;
 #pragma omp parallel num_threads(threads)
   {
     const int t = omp_get_thread_num();
     const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
     uint64_t sum = 0;
-    bool uni = true;
-    for (uint64_t i = a; i < b; i++) {
-      const uint64_t l = data[first + i].kmerLength;
-      sum += l;
-      uni &= (l == len0);
-    }
+    for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
     partSum[t + 1] = sum;
-    partUniform[t] = uni;
   }
   for (int t = 0; t < threads; t++) partSum[t + 1] += partSum[t];
   const uint64_t total = partSum[threads];
   if (int r = ensureSlot(s, n, total + 16, wantRanges)) return r;
-  bool uniform = len0 <= 0xFFFFFFFFull;
-  for (int t = 0; t < threads; t++) uniform &= partUniform[t] != 0;
   uint8_t *dst = s.hLetters;
   uint64_t *offs = s.hOffsets;
 #pragma omp parallel num_threads(threads)
@@ -602,78 +676,211 @@ static int packChunk(PipeSlot &s, const awfm_kmer_search_data *data, uint64_t fi
     const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
     uint64_t o = partSum[t];
     for (uint64_t i = a; i < b; i++) {
-      const awfm_kmer_search_data &d = data[first + i];
       offs[i] = o;
-      memcpy(dst + o, d.kmerString, d.kmerLength);
-      o += d.kmerLength;
+      memcpy(dst + o, d0[i].kmerString, d0[i].kmerLength);
+      o += d0[i].kmerLength;
     }
   }
   offs[n] = total;
-  *uniformLen = uniform ? (uint32_t)len0 : 0;
-  *letterBytes = total;
+  out->uniformLen = 0;
+  out->letterBytes = total;
+  out->source = s.hLetters;
   return AWFM_GPU_OK;
 }
 
-static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, uint32_t uniformLen, uint64_t letterBytes, bool wantRanges) {
-  const bool fixed = uniformLen != 0;
-  CU(cudaMemcpyAsync(s.dLetters, s.hLetters, letterBytes, cudaMemcpyHostToDevice, s.stream));
+static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, const Packed &pk, bool wantRanges) {
+  const bool fixed = pk.uniformLen != 0;
+  if (int r = ensureDeviceLetters(s, pk.letterBytes)) return r;
+  CU(cudaMemcpyAsync(s.dLetters, pk.source, pk.letterBytes, cudaMemcpyHostToDevice, s.stream));
   if (!fixed) CU(cudaMemcpyAsync(s.dOffsets, s.hOffsets, (s.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-  if (int r = countDeviceImpl(c, s.dLetters, fixed ? nullptr : s.dOffsets, uniformLen, s.n, s.dCounts,
+  if (int r = countDeviceImpl(c, s.dLetters, fixed ? nullptr : s.dOffsets, pk.uniformLen, s.n, s.dCounts,
                               wantRanges ? (awfm_range *)s.dRanges : nullptr, s.stream))
     return r;
-  c->stats.h2dBytes += letterBytes + (fixed ? 0 : (s.n + 1) * 8);
+  c->stats.h2dBytes += pk.letterBytes + (fixed ? 0 : (s.n + 1) * 8);
   return AWFM_GPU_OK;
 }
 
+// awFmParallelSearchCount over the reference's list layout.  One persistent OpenMP region runs the whole call: per
+// chunk the calling thread (the only one that talks to CUDA) waits for the slot that is being recycled, then ALL
+// threads scatter that slot's counts into the entries and pack the next chunk, then the calling thread ships it.
+// Chunks are small (default 2^18 queries / 3 slots in flight) so the 32-B entries written by the scatter are still
+// in the host caches from the packing pass two chunks earlier.
 extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
                                           uint32_t numThreads) {
   if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> lock(c->mu);
   if (int r = setDevice(c)) return r;
   beginCall(c);
-  const int threads = (int)std::max<uint32_t>(1, numThreads);
+  if (n == 0) return AWFM_GPU_OK;
   const uint64_t chunk = (uint64_t)c->chunkQueries;
+  const uint64_t numChunks = (n + chunk - 1) / chunk;
+  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(1, numThreads), std::min(n, chunk) / 1024 + 1));
   constexpr int NS = 3;
-  auto retire = [&](PipeSlot &s) -> int {
-    if (!s.busy) return AWFM_GPU_OK;
-    CU(cudaEventSynchronize(s.done));
-    const uint32_t *src = s.hCounts;
-    awfm_kmer_search_data *dst = data + s.first;
-    const int64_t cnt = (int64_t)s.n;
-#pragma omp parallel for num_threads(threads) schedule(static)
-    for (int64_t i = 0; i < cnt; i++) dst[i].count = src[i];  // src/AwFmParallelSearch.c:187-190
-    s.busy = false;
-    return AWFM_GPU_OK;
-  };
+  const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
+  const double tStart = omp_get_wtime();
+  double tWait = 0, tWork = 0, tSubmit = 0;
+
+  // state shared by the team (written by the calling thread between barriers)
   int rc = AWFM_GPU_OK;
-  uint64_t chunkIndex = 0;
-  for (uint64_t first = 0; first < n && rc == AWFM_GPU_OK; first += chunk, chunkIndex++) {
-    PipeSlot &s = c->slots[chunkIndex % NS];
-    if ((rc = retire(s))) break;
-    s.first = first;
-    s.n = std::min(chunk, n - first);
-    uint32_t uniformLen = 0;
-    uint64_t letterBytes = 0;
-    if ((rc = packChunk(s, data, first, s.n, threads, false, &uniformLen, &letterBytes))) break;
-    if ((rc = submitCount(c, s, uniformLen, letterBytes, false))) break;
-    cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
-    if (e != cudaSuccess) {
-      rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
-      break;
+  uint64_t oldFirst = 0, oldN = 0;  // chunk whose counts are scattered this round
+  const uint32_t *oldCounts = nullptr;
+  uint64_t newFirst = 0, newN = 0, len0 = 0;  // chunk packed this round
+  bool direct = false, optimistic = false, fallback = false;
+  uint8_t *staging = nullptr;
+  const uint8_t *base = nullptr;
+  int uniformAll = 1, contiguousAll = 1;
+  std::vector<uint64_t> partSum(T + 1, 0);
+  Packed pk;
+
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    for (uint64_t ci = 0; ci < numChunks + NS; ci++) {
+      PipeSlot &s = c->slots[ci % NS];
+#pragma omp master
+      {
+        const double t0 = omp_get_wtime();
+        oldN = 0;
+        if (s.busy) {  // recycle the slot: its D2H has to be complete
+          if (rc == AWFM_GPU_OK && cudaEventSynchronize(s.done) != cudaSuccess)
+            rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", "event synchronize failed");
+          else if (rc != AWFM_GPU_OK) cudaEventSynchronize(s.done);
+          if (rc == AWFM_GPU_OK) oldFirst = s.first, oldN = s.n, oldCounts = s.hCounts;
+          s.busy = false;
+        }
+        newN = 0;
+        if (ci < numChunks && rc == AWFM_GPU_OK) {
+          newFirst = ci * chunk;
+          newN = std::min(chunk, n - newFirst);
+          const awfm_kmer_search_data *d0 = data + newFirst;
+          len0 = d0[0].kmerLength;
+          optimistic = len0 >= 1 && len0 <= 65536;
+          base = (const uint8_t *)d0[0].kmerString;
+          direct = optimistic && sourcePinned && (const uint8_t *)d0[newN - 1].kmerString == base + (newN - 1) * len0 &&
+                   (const uint8_t *)d0[newN / 2].kmerString == base + (newN / 2) * len0;
+          if (optimistic) {
+            rc = ensureSlot(s, newN, direct ? 16 : newN * len0 + 16, false);
+            staging = s.hLetters;
+          }
+          uniformAll = contiguousAll = 1;
+          fallback = !optimistic;
+        }
+        tWait += omp_get_wtime() - t0;
+      }
+#pragma omp barrier
+      const double w0 = omp_get_wtime();
+      if (oldN) {  // src/AwFmParallelSearch.c:187-190: count = range length, stored as uint32
+        awfm_kmer_search_data *dst = data + oldFirst;
+        const uint64_t a = oldN * t / T, b = oldN * (t + 1) / T;
+        for (uint64_t i = a; i < b; i++) dst[i].count = oldCounts[i];
+      }
+      if (newN && rc == AWFM_GPU_OK && optimistic) {
+        const awfm_kmer_search_data *d0 = data + newFirst;
+        const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
+        bool uni = true, con = true;
+        if (direct) {
+          for (uint64_t i = a; i < b; i++) {
+            uni &= d0[i].kmerLength == len0;
+            con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+          }
+        } else {
+          for (uint64_t i = a; i < b && uni; i++) {
+            uni = d0[i].kmerLength == len0;
+            if (uni) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+          }
+        }
+        if (!uni) {
+#pragma omp atomic write
+          uniformAll = 0;
+        }
+        if (!con) {
+#pragma omp atomic write
+          contiguousAll = 0;
+        }
+      }
+#pragma omp barrier
+      if (newN && rc == AWFM_GPU_OK) {
+        // a direct (copy-free) attempt that found a gap, or mixed lengths: redo this chunk on the general path
+        if (optimistic && uniformAll && direct && !contiguousAll) {
+#pragma omp barrier
+#pragma omp master
+          {
+            direct = false;
+            rc = ensureSlot(s, newN, newN * len0 + 16, false);
+            staging = s.hLetters;
+          }
+#pragma omp barrier
+          if (rc == AWFM_GPU_OK) {
+            const awfm_kmer_search_data *d0 = data + newFirst;
+            const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
+            for (uint64_t i = a; i < b; i++) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+          }
+#pragma omp barrier
+        } else if (!optimistic || !uniformAll) {
+          const awfm_kmer_search_data *d0 = data + newFirst;
+          const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
+          uint64_t sum = 0;
+          for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
+          partSum[t + 1] = sum;
+#pragma omp barrier
+#pragma omp master
+          {
+            partSum[0] = 0;
+            for (int k = 0; k < T; k++) partSum[k + 1] += partSum[k];
+            rc = ensureSlot(s, newN, partSum[T] + 16, false);
+            staging = s.hLetters;
+            fallback = true;
+          }
+#pragma omp barrier
+          if (rc == AWFM_GPU_OK) {
+            uint64_t o = partSum[t];
+            uint64_t *offs = s.hOffsets;
+            for (uint64_t i = a; i < b; i++) {
+              offs[i] = o;
+              memcpy(staging + o, d0[i].kmerString, d0[i].kmerLength);
+              o += d0[i].kmerLength;
+            }
+          }
+#pragma omp barrier
+        }
+      }
+      const double w1 = omp_get_wtime();
+#pragma omp master
+      {
+        tWork += w1 - w0;
+        if (newN && rc == AWFM_GPU_OK) {
+          if (fallback) {
+            s.hOffsets[newN] = partSum[T];
+            pk.uniformLen = 0, pk.letterBytes = partSum[T], pk.source = s.hLetters;
+          } else {
+            pk.uniformLen = (uint32_t)len0, pk.letterBytes = newN * len0, pk.source = direct ? base : s.hLetters;
+          }
+          s.first = newFirst, s.n = newN;
+          rc = submitCount(c, s, pk, false);
+          if (rc == AWFM_GPU_OK) {
+            cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+            if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
+            else {
+              c->stats.d2hBytes += s.n * 4;
+              s.busy = true;
+            }
+          }
+        }
+        tSubmit += omp_get_wtime() - w1;
+      }
+#pragma omp barrier
     }
-    c->stats.d2hBytes += s.n * 4;
-    s.busy = true;
   }
-  // drain in submission order
-  for (int k = 0; k < NS; k++) {
-    PipeSlot &s = c->slots[(chunkIndex + k) % NS];
-    if (rc == AWFM_GPU_OK) rc = retire(s);
-    else if (s.busy) {
+  for (auto &s : c->slots)  // only reachable with rc != OK: never leave a DMA in flight
+    if (s.busy) {
       cudaEventSynchronize(s.done);
       s.busy = false;
     }
-  }
+  if (getenv("AWFM_GPU_VERBOSE"))
+    fprintf(stderr, "[awfm_gpu] count list: %llu queries, %llu chunks, %d threads, pinned=%d: total %.1f ms = wait %.1f + scatter/pack %.1f + submit %.1f\n",
+            (unsigned long long)n, (unsigned long long)numChunks, T, (int)sourcePinned, 1e3 * (omp_get_wtime() - tStart),
+            1e3 * tWait, 1e3 * tWork, 1e3 * tSubmit);
   return rc;
 }
 
@@ -687,6 +894,7 @@ extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_dat
   const int threads = (int)std::max<uint32_t>(1, numThreads);
   const uint64_t chunk = (uint64_t)c->chunkQueries;
   PipeSlot &s = c->slots[0];
+  const bool sourcePinned = n > 0 && data[0].kmerString && isPinnedHost(data[0].kmerString);
   uint64_t *hHit = nullptr, *hPos = nullptr, *dHit = nullptr, *dPos = nullptr;
   uint64_t hitCap = 0, posCap = 0;
   int rc = AWFM_GPU_OK;
@@ -709,10 +917,9 @@ extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_dat
   for (uint64_t first = 0; first < n; first += chunk) {
     s.first = first;
     s.n = std::min(chunk, n - first);
-    uint32_t uniformLen = 0;
-    uint64_t letterBytes = 0;
-    if ((rc = packChunk(s, data, first, s.n, threads, true, &uniformLen, &letterBytes))) break;
-    if ((rc = submitCount(c, s, uniformLen, letterBytes, true))) break;
+    Packed pk;
+    if ((rc = packChunk(s, data, first, s.n, threads, true, sourcePinned, &pk))) break;
+    if ((rc = submitCount(c, s, pk, true))) break;
     if (hitCap < s.n + 1) {
       if (hHit) cudaFreeHost(hHit);
       cudaFree(dHit);

@@ -55,46 +55,63 @@ def parse_args():
 
 # ----------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region through NVML (the same counters the
+    nvidia-smi line of B200_PROFILING.md prints), every 5 ms from a side thread."""
 
     def __init__(self, device):
         self.device = device
         self.rows = []
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else device
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
 
     def _run(self):
-        cmd = ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"]
+        n = self._nvml
         while not self._stop.is_set():
             try:
-                out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.rows.append((n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM),
+                                  n.nvmlDeviceGetPowerUsage(self._h) / 1000.0,
+                                  n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005)
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        if self._nvml:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._thread.join(timeout=6)
+        if self._thread:
+            self._thread.join(timeout=2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        n = self._nvml
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        names = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.sm_max),
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows),
+                "reasons": [k for k, v in names.items() if bits & v]}
 
 
 def measured_peak():
@@ -230,7 +247,7 @@ def run_ours(args):
     built = build_on_device(args, local, lib)
     gpu = built.gpu_index()
     build_s = time.time() - t0
-    need_host = (not args.no_e2e) or (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    need_host = (not args.no_e2e) or rank == 0
     arrays = built.to_host() if need_host else None
     tie_suffixes, build_ms = built.tie_suffixes, built.build_ms
     built.close()
@@ -300,12 +317,7 @@ def run_ours(args):
     sample = min(n, 1_000_000)
     h_counts_sample = d_counts[:sample].cpu().numpy().astype(np.uint32)
     h_letters_sample = d_letters[: sample * L].cpu().numpy()
-    if arrays is not None or rank == 0:
-        if arrays is None:
-            # rebuilt only when the host copy was skipped
-            b2 = build_on_device(args, local, lib)
-            arrays = b2.to_host()
-            b2.close()
+    if arrays is not None:
         o_counts, _, work = harness.Oracle(arrays).count(h_letters_sample, fixed_len=L, threads=os.cpu_count())
         parity = bool(np.array_equal(o_counts, h_counts_sample))
         bytes_per_query = work["countBytes"] / sample

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions(header):
     text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(awfm_gpu_[a-z_]+|awFm[A-Za-z]+)\s*\(", text)
+    names = re.findall(r"\b(awfm_gpu_[a-z0-9_]+|awFm[A-Za-z]+)\s*\(", text)
     return sorted(set(names))
 
 

@@ -80,13 +80,14 @@ struct awfm_gpu_ctx {
   uint64_t deviceBytes = 0;
   bool hasSa = false;
   // tuning
-  int countLpq = 2, locateLpq = 1, countVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
+  int countLpq = 2, locateLpq = 2, countVariant = 1, locateVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
   int64_t chunkQueries = 1 << 18;
   // scratch
   void *scanTemp = nullptr;
   size_t scanTempBytes = 0;
   uint64_t *dLengths = nullptr;
   uint64_t lengthsCap = 0;
+  unsigned long long *dWorkCounter = nullptr;  // locateKernelRefill's chunk dispenser
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
   awfm_gpu_stats stats{};
@@ -142,26 +143,31 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   else memcpy(prefix, v->prefixSums, numPrefix * 8);
 
   // blocks -> lines.  The raw copy is staged in slabs so peak extra memory stays small next to a 180 GB HBM.
-  const uint64_t lineBytes = amino ? 384u : 128u;  // per 256 positions (nucleotide: two 64-B half-lines)
+  const uint64_t lineBytes = amino ? 512u : 128u;  // per 256 positions: 4 amino quarter-lines / 2 nucleotide half-lines
   CUB_(cudaMalloc(&c->dLines, v->numBlocks * lineBytes));
   c->deviceBytes += v->numBlocks * lineBytes;
   uint64_t *dSuperCounts = nullptr;
   if (!amino) {
     CUB_(cudaMalloc(&c->dXBase, v->numBlocks * 2 * 4));
     c->deviceBytes += v->numBlocks * 8;
-    // superblock tables: counts at the first block of every 2^31-position superblock (5 letters, padded to 8)
+  }
+  {
+    // superblock tables: counts at the first block of every 2^31-position superblock (the searchable letters,
+    // row padded to 8 / 24 entries); superC folds the prefix sums C[c] in
+    const int numLetters = amino ? 21 : 5, stride = amino ? kAminoSuperStride : kNucSuperStride;
+    const uint32_t baseOffset = amino ? 160u : 96u;
     const uint64_t numSuper = ((v->bwtLength - 1) >> kSuperShift) + 1;
-    std::vector<uint64_t> superCounts(numSuper * 8, 0), superC(numSuper * 8, 0);
+    std::vector<uint64_t> superCounts(numSuper * stride, 0), superC(numSuper * stride, 0);
     for (uint64_t s = 0; s < numSuper; s++) {
-      const uint8_t *src = (const uint8_t *)v->blocks + ((s << kSuperShift) >> 8) * rawBlockBytes + 96;
-      if (fromDevice) CUB_(cudaMemcpy(&superCounts[s * 8], src, 5 * 8, cudaMemcpyDeviceToHost));
-      else memcpy(&superCounts[s * 8], src, 5 * 8);
-      for (int l = 0; l < 5; l++) superC[s * 8 + l] = prefix[l] + superCounts[s * 8 + l];
+      const uint8_t *src = (const uint8_t *)v->blocks + ((s << kSuperShift) >> 8) * rawBlockBytes + baseOffset;
+      if (fromDevice) CUB_(cudaMemcpy(&superCounts[s * stride], src, numLetters * 8, cudaMemcpyDeviceToHost));
+      else memcpy(&superCounts[s * stride], src, numLetters * 8);
+      for (int l = 0; l < numLetters; l++) superC[s * stride + l] = prefix[l] + superCounts[s * stride + l];
     }
-    CUB_(cudaMalloc(&dSuperCounts, numSuper * 64));
-    CUB_(cudaMemcpy(dSuperCounts, superCounts.data(), numSuper * 64, cudaMemcpyHostToDevice));
-    CUB_(cudaMalloc(&c->dSuperC, numSuper * 64));
-    CUB_(cudaMemcpy(c->dSuperC, superC.data(), numSuper * 64, cudaMemcpyHostToDevice));
+    CUB_(cudaMalloc(&dSuperCounts, numSuper * stride * 8));
+    CUB_(cudaMemcpy(dSuperCounts, superCounts.data(), numSuper * stride * 8, cudaMemcpyHostToDevice));
+    CUB_(cudaMalloc(&c->dSuperC, numSuper * stride * 8));
+    CUB_(cudaMemcpy(c->dSuperC, superC.data(), numSuper * stride * 8, cudaMemcpyHostToDevice));
   }
   {
     const uint64_t slabBlocks = std::min<uint64_t>(v->numBlocks, 1u << 20);  // <= 352 MB staging
@@ -172,7 +178,7 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
       cudaError_t e = cudaMemcpy(dRaw, (const uint8_t *)v->blocks + b0 * rawBlockBytes, nb * rawBlockBytes, kind);
       if (e == cudaSuccess) {
         const unsigned grid = (unsigned)((nb + 255) / 256);
-        if (amino) relayoutAmino<<<grid, 256>>>(dRaw, nb, (uint4 *)c->dLines + b0 * kAminoLineU4);
+        if (amino) relayoutAmino<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines);
         else relayoutNucleotide<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines, (uint32_t *)c->dXBase);
         e = cudaDeviceSynchronize();
       }
@@ -218,6 +224,7 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   }
   ix.seedK = v->seedK;
   ix.amino = amino;
+  CUB_(cudaMalloc(&c->dWorkCounter, 64));
   for (auto &s : c->slots) {
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -263,6 +270,7 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dSa);
   cudaFree(c->scanTemp);
   cudaFree(c->dLengths);
+  cudaFree(c->dWorkCounter);
   cudaGetLastError();
   delete c;
 }
@@ -276,6 +284,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   if (k == "count_lpq" && lpqOk(value)) c->countLpq = (int)value;
   else if (k == "locate_lpq" && lpqOk(value)) c->locateLpq = (int)value;
   else if (k == "count_variant" && (value == 0 || value == 1)) c->countVariant = (int)value;
+  else if (k == "locate_variant" && (value == 0 || value == 1)) c->locateVariant = (int)value;
   else if (k == "chunk_queries" && value >= 1024) c->chunkQueries = value;
   else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
   else return fail(AWFM_GPU_ERR_ARG, "unknown tuning key or bad value", key);
@@ -355,6 +364,16 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
     expandHits<<<std::max(g, 1), 256, 0, st>>>(dRanges, dHitOffsets, n, hb, he, dPos);
     CU(cudaGetLastError());
   }
+  if (c->locateVariant == 1) {  // group per hit with refill from a chunk dispenser
+    auto k = locateKernelRefill<LPQ, AMINO>;
+    if (int r = gridFor(c, k, 256, &grid)) return r;
+    const uint64_t need = ((he - hb) * LPQ + 255) / 256;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, need);
+    CU(cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), st));
+    k<<<grid, 256, 0, st>>>(c->ix, he - hb, dPos, c->dWorkCounter);
+    CU(cudaGetLastError());
+    return AWFM_GPU_OK;
+  }
   auto k = locateKernel<LPQ, AMINO>;
   if (int r = gridFor(c, k, 256, &grid)) return r;
   const uint64_t need = ((he - hb) * LPQ + 255) / 256;
@@ -364,12 +383,11 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
   return AWFM_GPU_OK;
 }
 
-// nucleotide half-lines have 4 chunks (groups of 1, 2 or 4 lanes); amino blocks 8 chunks (1, 2, 4 or 8 lanes)
+// nucleotide half-lines have 4 chunks (groups of 1, 2 or 4 lanes); amino quarter-lines 2 chunks (1 or 2 lanes);
+// larger requests are clamped
 #define DISPATCH_LPQ(fn, lpq, amino, ...)                                  \
   ((amino) ? ((lpq) == 1   ? fn<1, true>(__VA_ARGS__)                      \
-              : (lpq) == 2 ? fn<2, true>(__VA_ARGS__)                      \
-              : (lpq) == 4 ? fn<4, true>(__VA_ARGS__)                      \
-                           : fn<8, true>(__VA_ARGS__))                     \
+                           : fn<2, true>(__VA_ARGS__))                     \
            : ((lpq) == 1   ? fn<1, false>(__VA_ARGS__)                     \
               : (lpq) == 2 ? fn<2, false>(__VA_ARGS__)                     \
                            : fn<4, false>(__VA_ARGS__)))

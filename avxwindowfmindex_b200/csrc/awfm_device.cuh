@@ -15,12 +15,17 @@
 //    path (128-B lines holding 256 positions + 64-bit counts) was replaced.
 //    Reference layout: struct AwFmNucleotideBlock, 160 B per 256 positions, 32-B aligned (src/AwFmIndex.h:61-65).
 //
-//  amino "line triple" = 384 B, 128-B aligned, one per 256 positions:
-//      [  0,128)  8 chunks { b0[j], b1[j], b2[j], b3[j] }
-//      [128,160)  b4[0..7]
-//      [160,328)  baseOccurrences[0..20] as u64 (A..Y, Z)
-//      [328,384)  padding
-//    Reference layout: struct AwFmAminoBlock, 352 B (src/AwFmIndex.h:55-59).
+//  amino "quarter-line" = 128 B, 128-B aligned, one per 64 BWT positions (32 words):
+//      w[0..3]   b0..b3 of positions 64*q +  0..31     (bit t <-> position t)
+//      w[4..7]   b0..b3 of positions 64*q + 32..63
+//      w[8], w[9] b4 of the low / high 32 positions;  w[10] = 0
+//      w[11 + c] occurrences of letter c (A..Y = 0..19, Z = 20) in BWT[0, 64*q), relative to the enclosing
+//                2^31-position superblock (32 bits); absolute 64-bit superblock counts + C[c] sit in superC.
+//    One rank = ONE 128-B line (the unit the memory system fetches per missing request anyway, see
+//    profiles/r01_granularity_probe.json): code bits, the letter's count and nothing else.  The first amino layout
+//    of this path kept the reference's 256-position granularity (384-B line triples: 128 B of b0..b3, then b4,
+//    then 21 64-bit counts) and paid ~3 line misses per rank.
+//    Reference layout: struct AwFmAminoBlock, 352 B per 256 positions (src/AwFmIndex.h:55-59).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,14 +33,16 @@
 namespace awfm {
 
 constexpr int kNucHalfU4 = 4;     // uint4 per nucleotide half-line (128 positions)
-constexpr int kAminoLineU4 = 24;  // uint4 per amino line triple (256 positions)
+constexpr int kAminoLineU4 = 8;   // uint4 per amino quarter-line (64 positions)
+constexpr int kAminoRelWord = 11;  // first relative-count word of a quarter-line
+constexpr int kAminoSuperStride = 24, kNucSuperStride = 8;  // u64 per superblock row of superC
 constexpr int kSuperShift = 31;   // nucleotide superblock = 2^31 positions
 constexpr uint32_t kNucSentinel = 5, kAminoSentinel = 21;
 
 struct DevIndex {
-  const uint4 *lines;        // nucleotide: half-lines; amino: line triples
+  const uint4 *lines;        // nucleotide: half-lines; amino: quarter-lines
   const uint32_t *xRel;      // nucleotide only: relative count of the ambiguity letter per half-line
-  const uint64_t *superC;    // nucleotide only: [superblock][8] = C[c] + count of c before the superblock, c = 0..4
+  const uint64_t *superC;    // [superblock][8 | 24] = C[c] + count of c before the superblock (c = 0..4 | 0..20)
   const uint4 *seedTable;    // {startLo, startHi, endLo, endHi}
   const uint64_t *sa;        // bit-packed sampled SA viewed as little-endian u64 words (+16 B zero padding)
   uint64_t numBlocks, bwtLength, numSeeds;
@@ -188,31 +195,31 @@ __device__ __forceinline__ uint32_t nucRel(const NucLoad<LPQ> &l, uint32_t lette
 }
 
 // ================================================================================================ amino
+// LPQ lanes (1 or 2) cooperate on one quarter-line; lane `sub` holds the 32-position chunks sub, sub+LPQ.
 template <int LPQ>
 struct AminoLoad {
-  uint4 v[8 / LPQ];
-  uint32_t b4[8 / LPQ];
-  uint64_t base;
+  uint4 v[2 / LPQ];
+  uint32_t b4[2 / LPQ];
 };
 template <int LPQ>
-__device__ __forceinline__ AminoLoad<LPQ> aminoIssue(const DevIndex &ix, uint64_t block, uint32_t letter,
-                                                     unsigned sub) {
+__device__ __forceinline__ AminoLoad<LPQ> aminoIssue(const uint4 *line, unsigned sub) {
   AminoLoad<LPQ> l;
-  const uint4 *line = ix.lines + block * kAminoLineU4;
 #pragma unroll
-  for (int i = 0; i < 8 / LPQ; i++) {
+  for (int i = 0; i < 2 / LPQ; i++) {
     l.v[i] = __ldg(line + sub + LPQ * i);
-    l.b4[i] = __ldg(reinterpret_cast<const uint32_t *>(line + 8) + sub + LPQ * i);
+    l.b4[i] = __ldg(reinterpret_cast<const uint32_t *>(line + 2) + sub + LPQ * i);
   }
-  l.base = __ldg(reinterpret_cast<const uint64_t *>(line + 10) + letter);
   return l;
+}
+__device__ __forceinline__ uint32_t aminoRel(const uint4 *line, uint32_t letter) {
+  return __ldg(reinterpret_cast<const uint32_t *>(line) + kAminoRelWord + letter);
 }
 template <int LPQ>
 __device__ __forceinline__ uint32_t aminoPop(const AminoLoad<LPQ> &l, const Selector &s, uint32_t local,
                                              unsigned sub) {
   uint32_t acc = 0;
 #pragma unroll
-  for (int i = 0; i < 8 / LPQ; i++) {
+  for (int i = 0; i < 2 / LPQ; i++) {
     const uint4 v = l.v[i];
     const uint32_t sel = ((v.x ^ s.flip[0]) | s.dontcare[0]) & ((v.y ^ s.flip[1]) | s.dontcare[1]) &
                          ((v.z ^ s.flip[2]) | s.dontcare[2]) & ((v.w ^ s.flip[3]) | s.dontcare[3]) &
@@ -226,28 +233,32 @@ __device__ __forceinline__ uint32_t aminoPop(const AminoLoad<LPQ> &l, const Sele
 // One LF-mapping step (src/AwFmSearch.c:42-159): sp' = C[c] + Occ(c, sp-1), ep' = C[c] + Occ(c, ep) - 1.
 // Both blocks are requested before either is consumed (two independent misses in flight per group); the two
 // partial popcounts travel through the group reduction packed in one 32-bit register.
-// Nucleotide groups are 1, 2 or 4 lanes (half-line = 4 chunks); amino groups 1, 2, 4 or 8 lanes (8 chunks).
+// Nucleotide groups are 1, 2 or 4 lanes (half-line = 4 chunks); amino groups 1 or 2 lanes (quarter-line = 2 chunks).
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_t &ep, uint32_t letter,
                                        unsigned sub, unsigned mask) {
   const uint64_t pa = sp - 1, pb = ep;
   const Selector s = makeSelector<AMINO>(letter);
   if constexpr (AMINO) {
-    const AminoLoad<LPQ> la = aminoIssue<LPQ>(ix, pa >> 8, letter, sub);
-    const AminoLoad<LPQ> lb = aminoIssue<LPQ>(ix, pb >> 8, letter, sub);
-    const uint32_t packed = groupSum32<LPQ>(aminoPop<LPQ>(la, s, (uint32_t)pa & 255u, sub) |
-                                                (aminoPop<LPQ>(lb, s, (uint32_t)pb & 255u, sub) << 16),
+    static_assert(!AMINO || LPQ <= 2, "amino quarter-lines have 2 chunks");
+    const uint4 *lineA = ix.lines + (pa >> 6) * kAminoLineU4, *lineB = ix.lines + (pb >> 6) * kAminoLineU4;
+    const AminoLoad<LPQ> la = aminoIssue<LPQ>(lineA, sub);
+    const AminoLoad<LPQ> lb = aminoIssue<LPQ>(lineB, sub);
+    const uint32_t ra = aminoRel(lineA, letter), rb = aminoRel(lineB, letter);
+    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * kAminoSuperStride + letter);
+    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * kAminoSuperStride + letter);
+    const uint32_t packed = groupSum32<LPQ>(aminoPop<LPQ>(la, s, (uint32_t)pa & 63u, sub) |
+                                                (aminoPop<LPQ>(lb, s, (uint32_t)pb & 63u, sub) << 16),
                                             mask);
-    const uint64_t c = ix.prefixSums[letter];
-    sp = c + la.base + (packed & 0xFFFFu);
-    ep = c + lb.base + (packed >> 16) - 1;
+    sp = ca + ra + (packed & 0xFFFFu);
+    ep = cb + rb + (packed >> 16) - 1;
   } else {
     static_assert(AMINO || LPQ <= 4, "nucleotide half-lines have 4 chunks");
     const uint64_t ha = pa >> 7, hb = pb >> 7;
     const NucLoad<LPQ> la = nucIssue<LPQ>(ix, ha, sub);
     const NucLoad<LPQ> lb = nucIssue<LPQ>(ix, hb, sub);
-    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * 8 + letter);
-    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * 8 + letter);
+    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * kNucSuperStride + letter);
+    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * kNucSuperStride + letter);
     uint32_t ra, rb;
     if (letter == 4u) {  // ambiguity letter: relative count from the side array
       ra = __ldg(ix.xRel + ha);
@@ -269,18 +280,16 @@ __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p, unsigned sub, unsigned mask) {
   if constexpr (AMINO) {
-    const uint64_t block = p >> 8;
-    const uint32_t local = (uint32_t)p & 255u, ownerChunk = local >> 5, bit = local & 31u;
-    const uint4 *line = ix.lines + block * kAminoLineU4;
-    AminoLoad<LPQ> l;
+    const uint32_t local = (uint32_t)p & 63u, ownerChunk = local >> 5, bit = local & 31u;
+    const uint4 *line = ix.lines + (p >> 6) * kAminoLineU4;
+    const AminoLoad<LPQ> l = aminoIssue<LPQ>(line, sub);
+    // the count word depends on the letter just being read: pull the line's other two sectors towards L1 now so
+    // that dependent load does not pay a second trip to L2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(line) + 64));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(line) + 96));
     uint32_t code = 0;
 #pragma unroll
-    for (int i = 0; i < 8 / LPQ; i++) {
-      l.v[i] = __ldg(line + sub + LPQ * i);
-      l.b4[i] = __ldg(reinterpret_cast<const uint32_t *>(line + 8) + sub + LPQ * i);
-    }
-#pragma unroll
-    for (int i = 0; i < 8 / LPQ; i++) {
+    for (int i = 0; i < 2 / LPQ; i++) {
       const uint4 v = l.v[i];
       const uint32_t c = ((v.x >> bit) & 1u) | (((v.y >> bit) & 1u) << 1) | (((v.z >> bit) & 1u) << 2) |
                          (((v.w >> bit) & 1u) << 3) | (((l.b4[i] >> bit) & 1u) << 4);
@@ -289,10 +298,10 @@ __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p
     if (LPQ > 1) code = __shfl_sync(mask, code, groupBaseLane<LPQ>() + (ownerChunk % LPQ));
     const uint32_t letter = kAminoCodeToLetter[code];
     if (letter == kAminoSentinel) return 0;
-    const uint64_t base = __ldg(reinterpret_cast<const uint64_t *>(line + 10) + letter);
+    const uint32_t rel = aminoRel(line, letter);
     const Selector s = makeSelector<true>(letter);
     const uint32_t pop = groupSum32<LPQ>(aminoPop<LPQ>(l, s, local, sub), mask);
-    return ix.prefixSums[letter] + base + pop - 1;
+    return __ldg(ix.superC + (p >> kSuperShift) * kAminoSuperStride + letter) + rel + pop - 1;
   } else {
     const uint64_t half = p >> 7;
     const uint32_t local = (uint32_t)p & 127u, ownerChunk = local >> 5, bit = local & 31u;
@@ -310,7 +319,7 @@ __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p
     const Selector s = makeSelector<false>(letter);
     const uint32_t rel = (letter == 4u) ? __ldg(ix.xRel + half) : nucRel<LPQ>(l, letter, sub, mask);
     const uint32_t pop = groupSum32<LPQ>(nucPop<LPQ>(l, s, local, sub), mask);
-    return __ldg(ix.superC + (p >> kSuperShift) * 8 + letter) + rel + pop - 1;
+    return __ldg(ix.superC + (p >> kSuperShift) * kNucSuperStride + letter) + rel + pop - 1;
   }
 }
 

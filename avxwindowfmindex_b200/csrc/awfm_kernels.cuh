@@ -292,6 +292,15 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// (value + offset) mod bwtLength (src/AwFmSuffixArray.c:179-203).  A walk passes BWT position 0 (always sampled)
+// within bwtLength steps, so the sum is below 2*bwtLength on any well-formed index: one compare-and-subtract; the
+// 64-bit division only runs on malformed input.
+__device__ __forceinline__ uint64_t wrapPosition(uint64_t v, uint64_t n) {
+  if (v < n) return v;
+  v -= n;
+  return v < n ? v : v % n;
+}
+
 // Step 2, locateKernel: in place, positions[i] holds a BWT position on entry and the text position on exit.
 template <int LPQ, bool AMINO>
 __global__ void __launch_bounds__(256)
@@ -307,7 +316,69 @@ __global__ void __launch_bounds__(256)
       p = backtraceStep<LPQ, AMINO>(ix, p, sub, mask);
       offset++;
     }
-    if (sub == 0) positions[h] = (saValue(ix, sampleIndexOf(ix, p)) + offset) % ix.bwtLength;
+    if (sub == 0) positions[h] = wrapPosition(saValue(ix, sampleIndexOf(ix, p)) + offset, ix.bwtLength);
+  }
+}
+
+// Step 2, default variant: one LPQ-lane GROUP per hit with immediate refill.  The walk length of a hit is geometric
+// (mean ratio-1, unbounded: sampling is by BWT position, src/AwFmIndexStruct.c:88-91), so a group bound to one hit
+// per warp round idles for most of the round (the slowest of 32 geometric walks is ~4x the mean).  Here a group
+// that reaches a sampled position finishes its hit (sampled-SA read, add, mod, store) and takes the next hit in the
+// same round: every group keeps one independent DRAM request in flight.  Hits are handed out in 64-hit chunks from
+// a global counter (one atomic per chunk per warp), so the tail of the launch is one chunk, not the slowest thread.
+// All lanes of a group carry the same (h, p, offset).
+constexpr uint32_t kLocateChunk = 64;
+template <int LPQ, bool AMINO>
+__global__ void __launch_bounds__(256, 8)
+    locateKernelRefill(const __grid_constant__ DevIndex ix, uint64_t numHits, uint64_t *__restrict__ positions,
+                       unsigned long long *__restrict__ workCounter) {
+  constexpr uint64_t kIdle = ~0ull;
+  constexpr unsigned kLeaders = LPQ == 1 ? 0xFFFFFFFFu : LPQ == 2 ? 0x55555555u : LPQ == 4 ? 0x11111111u : 0x01010101u;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned sub = lane % LPQ;
+  const unsigned mask = groupMaskOf<LPQ>();
+  const unsigned leadersBelow = kLeaders & ((1u << (lane - sub)) - 1u);  // group leaders of lower-numbered groups
+  uint64_t chunkNext = 0, chunkEnd = 0;  // warp-uniform: hits of the current chunk not handed out yet
+  bool exhausted = false;                // warp-uniform: the global counter ran past numHits
+  uint64_t h = kIdle, p = 0;
+  uint32_t offset = 0;
+  for (;;) {
+    unsigned needMask = __ballot_sync(0xFFFFFFFFu, h == kIdle) & kLeaders;
+    while (needMask) {
+      if (chunkNext >= chunkEnd) {
+        if (exhausted) break;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(workCounter, (unsigned long long)kLocateChunk);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= numHits) {
+          exhausted = true;
+          break;
+        }
+        chunkNext = base;
+        chunkEnd = min((uint64_t)base + kLocateChunk, numHits);
+      }
+      const uint32_t avail = (uint32_t)(chunkEnd - chunkNext);
+      const uint32_t rank = __popc(needMask & leadersBelow);
+      if (h == kIdle && rank < avail) {
+        h = chunkNext + rank;
+        p = positions[h];
+        offset = 0;
+      }
+      chunkNext += min(avail, (uint32_t)__popc(needMask));
+      needMask = __ballot_sync(0xFFFFFFFFu, h == kIdle) & kLeaders;
+    }
+    if (needMask == kLeaders) break;  // no group holds a hit and none is left to hand out
+    if (h != kIdle) {                 // uniform within a group
+      if (isSampled(ix, p)) {
+        const uint64_t v = wrapPosition(saValue(ix, sampleIndexOf(ix, p)) + offset, ix.bwtLength);
+        if (LPQ > 1) __syncwarp(mask);  // every lane of the group has read positions[h] before it is overwritten
+        if (sub == 0) positions[h] = v;
+        h = kIdle;
+      } else {
+        p = backtraceStep<LPQ, AMINO>(ix, p, sub, mask);
+        offset++;
+      }
+    }
   }
 }
 
@@ -357,19 +428,52 @@ __global__ void relayoutNucleotide(const uint8_t *__restrict__ raw, uint64_t num
   }
 }
 
-__global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint4 *__restrict__ lines) {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= numBlocks) return;
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + b * 352);
-  const uint32_t *base = reinterpret_cast<const uint32_t *>(raw + b * 352 + 160);
-  uint4 *dst = lines + b * kAminoLineU4;
+// One thread per reference block (256 positions) -> four quarter-lines (see awfm_device.cuh).  The count of letter c
+// at the start of quarter q = baseOccurrences[c] (block start) + popcount of c's selector over the 2q words before
+// it, made relative to the enclosing superblock.
+__global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+                              const uint64_t *__restrict__ superCounts /* [numSuper][24] */,
+                              uint4 *__restrict__ lines) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numBlocks) return;
+  const uint64_t b = firstBlock + i;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + i * 352);
+  const uint64_t *base = reinterpret_cast<const uint64_t *>(raw + i * 352 + 160);
+  const uint64_t *super = superCounts + ((b * 256) >> kSuperShift) * kAminoSuperStride;
+  uint32_t w[5][8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) dst[j] = make_uint4(src[j], src[8 + j], src[16 + j], src[24 + j]);
-  uint32_t *tail = reinterpret_cast<uint32_t *>(dst + 8);  // byte 128
+  for (int v = 0; v < 5; v++)
 #pragma unroll
-  for (int j = 0; j < 8; j++) tail[j] = src[32 + j];                    // b4 -> [128,160)
-  for (int j = 0; j < 42; j++) tail[8 + j] = base[j];                   // 21 u64 -> [160,328)
-  for (int j = 50; j < 64; j++) tail[j] = 0;                            // padding -> [328,384)
+    for (int j = 0; j < 8; j++) w[v][j] = src[8 * v + j];
+  uint32_t *dst = reinterpret_cast<uint32_t *>(lines + (4 * b) * kAminoLineU4);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t *o = dst + 32 * q;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      o[v] = w[v][2 * q];
+      o[4 + v] = w[v][2 * q + 1];
+    }
+    o[8] = w[4][2 * q];
+    o[9] = w[4][2 * q + 1];
+    o[10] = 0;
+  }
+  for (int c = 0; c < 21; c++) {
+    const uint32_t cc = kAminoCodeCare[c], code = cc & 0xFFu, care = cc >> 8;
+    uint32_t rel = (uint32_t)(base[c] - super[c]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      dst[32 * q + kAminoRelWord + c] = rel;
+#pragma unroll
+      for (int j = 2 * q; j < 2 * q + 2; j++) {
+        uint32_t sel = 0xFFFFFFFFu;
+#pragma unroll
+        for (int v = 0; v < 5; v++)
+          if ((care >> v) & 1u) sel &= ((code >> v) & 1u) ? w[v][j] : ~w[v][j];
+        rel += __popc(sel);
+      }
+    }
+  }
 }
 
 // range lengths (u32-truncated, src/AwFmParallelSearch.c:328,367) for the exclusive scan that builds hitOffsets

@@ -96,7 +96,9 @@ void awfm_gpu_ctx_destroy(awfm_gpu_ctx *ctx);
 uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *ctx);
 int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
 /* Tuning knobs (kernel variant selection for measurement; defaults are the shipped configuration).
- * keys: "count_lpq" (lanes per query: 1,2,4,8), "locate_lpq", "count_variant", "chunk_queries", "cta_threads". */
+ * keys: "count_lpq" (lanes per query: 1,2,4,8; clamped to what the alphabet's line layout supports), "locate_lpq",
+ * "count_variant" (0 group-per-query from global memory, 1 CTA tiles staged in shared memory), "locate_variant"
+ * (0 group-per-hit, 1 lane-per-hit with refill), "chunk_queries", "blocks_per_sm". */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 
 /* ---- packed batch, HOST buffers (H2D, kernels, D2H inside the call) ---- */

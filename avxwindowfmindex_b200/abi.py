@@ -8,6 +8,7 @@ import ctypes as C
 AwFmAlphabetAmino, AwFmAlphabetDna, AwFmAlphabetRna = 1, 2, 3
 AwFmSuccess, AwFmFileReadOkay = 1, 2
 AwFmGeneralFailure, AwFmAllocationFailure, AwFmFileReadFail = -1, -3, -11
+AwFmUnsupportedVersionError, AwFmNullPtrError, AwFmIllegalPositionError = -2, -4, -6
 NUC_BLOCK_BYTES, AMINO_BLOCK_BYTES = 160, 352
 
 

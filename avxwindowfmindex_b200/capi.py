@@ -18,10 +18,11 @@ GPU_SYMBOLS = [
     "awfm_gpu_locate_device", "awfm_gpu_search_list_count", "awfm_gpu_search_list_locate",
     "awfm_gpu_gather_bandwidth", "awfm_gpu_build_index", "awfm_gpu_build_index_host", "awfm_gpu_built_view",
     "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
+    "awfm_gpu_ctx_set_sequences", "awfm_gpu_map_positions_device", "awfm_gpu_map_positions_host",
 ]
 DROPIN_SYMBOLS = [
     "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",
-    "awFmGpuReleaseIndex", "awFmGpuPrepareIndex", "awFmGpuLastCountStatus",
+    "awFmGpuReleaseIndex", "awFmGpuPrepareIndex", "awFmGpuLastCountStatus", "awFmGpuGetLocalSequencePositions",
 ]
 
 _lib = None
@@ -84,7 +85,12 @@ def load():
     lib.awfm_gpu_built_destroy.restype = None
     lib.awfm_gpu_synth_letters.argtypes = [C.c_int, vp, u64, u64, u64, C.c_int]
     lib.awfm_gpu_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.awfm_gpu_ctx_set_sequences.argtypes = [vp, vp, u64]
+    lib.awfm_gpu_map_positions_device.argtypes = [vp, vp, u64, vp, vp, vp]
+    lib.awfm_gpu_map_positions_host.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]
     declare_search_list_api(lib)
+    lib.awFmGpuGetLocalSequencePositions.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    lib.awFmGpuGetLocalSequencePositions.restype = C.c_int
     lib.awFmGpuReleaseIndex.argtypes = [vp]
     lib.awFmGpuReleaseIndex.restype = None
     lib.awFmGpuPrepareIndex.argtypes = [vp]

@@ -77,6 +77,7 @@ struct awfm_gpu_ctx {
   int device = 0, numSMs = 0;
   DevIndex ix{};
   void *dLines = nullptr, *dXBase = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
+  uint64_t *dSequenceEnds = nullptr;
   uint64_t deviceBytes = 0;
   bool hasSa = false;
   // tuning
@@ -268,6 +269,7 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dSuperC);
   cudaFree(c->dSeed);
   cudaFree(c->dSa);
+  cudaFree(c->dSequenceEnds);
   cudaFree(c->scanTemp);
   cudaFree(c->dLengths);
   cudaFree(c->dWorkCounter);
@@ -465,6 +467,86 @@ extern "C" int awfm_gpu_locate_device(awfm_gpu_ctx *c, const awfm_range *dRanges
   if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return fail(AWFM_GPU_ERR_ARG, "null argument");
   if (int r = setDevice(c)) return r;
   return locateDeviceImpl(c, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ contig mapping
+extern "C" int awfm_gpu_ctx_set_sequences(awfm_gpu_ctx *c, const void *metadata, uint64_t numSequences) {
+  if (!c || (numSequences && !metadata)) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  CU(cudaDeviceSynchronize());
+  cudaFree(c->dSequenceEnds);
+  c->dSequenceEnds = nullptr;
+  c->ix.sequenceEnds = nullptr;
+  c->ix.numSequences = 0;
+  if (numSequences == 0) return AWFM_GPU_OK;
+  // struct FastaVectorMetadata { size_t headerEndPosition; size_t sequenceEndPosition; } -> dense array of ends
+  std::vector<uint64_t> ends(numSequences);
+  const uint64_t *m = (const uint64_t *)metadata;
+  for (uint64_t i = 0; i < numSequences; i++) {
+    ends[i] = m[2 * i + 1];
+    if (i && ends[i] < ends[i - 1]) return fail(AWFM_GPU_ERR_ARG, "sequenceEndPosition must be non-decreasing");
+  }
+  CU(cudaMalloc(&c->dSequenceEnds, numSequences * 8));
+  CU(cudaMemcpy(c->dSequenceEnds, ends.data(), numSequences * 8, cudaMemcpyHostToDevice));
+  c->deviceBytes += numSequences * 8;
+  c->ix.sequenceEnds = c->dSequenceEnds;
+  c->ix.numSequences = numSequences;
+  return AWFM_GPU_OK;
+}
+
+static int mapDeviceImpl(awfm_gpu_ctx *c, const uint64_t *dPos, uint64_t n, uint64_t *dSeq, uint64_t *dLocal,
+                         cudaStream_t st) {
+  if (!c->ix.sequenceEnds) return fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
+  if (n == 0) return AWFM_GPU_OK;
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8);
+  EventPair *ev = nextEvents(c);
+  if (ev) CU(cudaEventRecord(ev->a, st));
+  mapPositionsKernel<<<grid, 256, 0, st>>>(c->ix.sequenceEnds, c->ix.numSequences, dPos, n, dSeq, dLocal);
+  CU(cudaGetLastError());
+  if (ev) CU(cudaEventRecord(ev->b, st));
+  c->stats.launches += 1;
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_map_positions_device(awfm_gpu_ctx *c, const uint64_t *dPositions, uint64_t n,
+                                             uint64_t *dSequenceIndex, uint64_t *dLocalPosition, void *stream) {
+  if (!c || (n && (!dPositions || !dSequenceIndex || !dLocalPosition))) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = setDevice(c)) return r;
+  return mapDeviceImpl(c, dPositions, n, dSequenceIndex, dLocalPosition, (cudaStream_t)stream);
+}
+
+extern "C" int awfm_gpu_map_positions_host(awfm_gpu_ctx *c, const uint64_t *positions, uint64_t n,
+                                           uint64_t *sequenceIndex, uint64_t *localPosition, uint64_t *numIllegal) {
+  if (!c || (n && (!positions || !sequenceIndex || !localPosition))) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  beginCall(c);
+  if (numIllegal) *numIllegal = 0;
+  if (!c->ix.sequenceEnds) return fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
+  if (n == 0) return AWFM_GPU_OK;
+  cudaStream_t st = c->slots[0].stream;
+  const uint64_t batch = std::min<uint64_t>(n, 1ull << 27);  // bounded staging: 3 x 1 GiB
+  uint64_t *d = nullptr;
+  CU(cudaMalloc(&d, batch * 24));
+  int rc = AWFM_GPU_OK;
+  uint64_t illegal = 0;
+  for (uint64_t b0 = 0; b0 < n && rc == AWFM_GPU_OK; b0 += batch) {
+    const uint64_t nb = std::min(batch, n - b0);
+    cudaError_t e = cudaMemcpyAsync(d, positions + b0, nb * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = mapDeviceImpl(c, d, nb, d + batch, d + 2 * batch, st);
+    if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaMemcpyAsync(sequenceIndex + b0, d + batch, nb * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaMemcpyAsync(localPosition + b0, d + 2 * batch, nb * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "map positions", cudaGetErrorString(e));
+    if (rc == AWFM_GPU_OK && numIllegal)
+      for (uint64_t i = b0; i < b0 + nb; i++) illegal += sequenceIndex[i] == ~0ull;
+  }
+  cudaFree(d);
+  if (numIllegal) *numIllegal = illegal;
+  c->stats.h2dBytes = n * 8;
+  c->stats.d2hBytes = n * 16;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer calls

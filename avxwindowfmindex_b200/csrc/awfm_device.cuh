@@ -45,6 +45,8 @@ struct DevIndex {
   const uint64_t *superC;    // [superblock][8 | 24] = C[c] + count of c before the superblock (c = 0..4 | 0..20)
   const uint4 *seedTable;    // {startLo, startHi, endLo, endHi}
   const uint64_t *sa;        // bit-packed sampled SA viewed as little-endian u64 words (+16 B zero padding)
+  const uint64_t *sequenceEnds;  // cumulative end offset of every FASTA record (incl. its separator), or nullptr
+  uint64_t numSequences;
   uint64_t numBlocks, bwtLength, numSeeds;
   uint64_t prefixSums[24];
   uint32_t saBitWidth, saRatio, saRatioShift /* log2 if power of two else 0xFFFFFFFF */, seedK, amino;

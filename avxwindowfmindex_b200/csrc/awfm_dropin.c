@@ -118,6 +118,15 @@ static int contextFor(const struct AwFmIndex *index, awfm_gpu_ctx **out) {
     if ((e = getenv("AWFM_GPU_LOCATE_LPQ"))) awfm_gpu_ctx_set_tuning(ctx, "locate_lpq", atoll(e));
     if ((e = getenv("AWFM_GPU_COUNT_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "count_variant", atoll(e));
     if ((e = getenv("AWFM_GPU_CHUNK_QUERIES"))) awfm_gpu_ctx_set_tuning(ctx, "chunk_queries", atoll(e));
+    if ((e = getenv("AWFM_GPU_LOCATE_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "locate_variant", atoll(e));
+    /* multi-sequence index: the record table rides along for awFmGpuGetLocalSequencePositions */
+    if (index->fastaVector && index->fastaVector->metadata.count)
+      rc = awfm_gpu_ctx_set_sequences(ctx, index->fastaVector->metadata.data, index->fastaVector->metadata.count);
+    if (rc != AWFM_GPU_OK) {
+      awfm_gpu_ctx_destroy(ctx);
+      pthread_mutex_unlock(&gCacheLock);
+      return rc;
+    }
     struct CachedIndex *c = &gCache[freeSlot];
     c->index = index;
     c->blocks = index->bwtBlockList.asNucleotide;
@@ -148,6 +157,24 @@ enum AwFmReturnCode awFmGpuPrepareIndex(const struct AwFmIndex *index) {
 }
 
 enum AwFmReturnCode awFmGpuLastCountStatus(void) { return gLastCountStatus; }
+
+enum AwFmReturnCode awFmGpuGetLocalSequencePositions(const struct AwFmIndex *index, const size_t *globalPositions,
+                                                     size_t count, size_t *sequenceNumbers,
+                                                     size_t *localSequencePositions) {
+  if (!index || (count && (!globalPositions || !sequenceNumbers || !localSequencePositions))) return AwFmNullPtrError;
+  if (!index->fastaVector) return AwFmUnsupportedVersionError; /* src/AwFmSearch.c:287-289 */
+  awfm_gpu_ctx *ctx = NULL;
+  int rc = contextFor(index, &ctx);
+  uint64_t illegal = 0;
+  if (rc == AWFM_GPU_OK)
+    rc = awfm_gpu_map_positions_host(ctx, (const uint64_t *)globalPositions, count, (uint64_t *)sequenceNumbers,
+                                     (uint64_t *)localSequencePositions, &illegal);
+  if (rc != AWFM_GPU_OK) {
+    fprintf(stderr, "awFmGpuGetLocalSequencePositions (B200): %s\n", awfm_gpu_last_error());
+    return mapStatus(rc);
+  }
+  return illegal ? AwFmIllegalPositionError : AwFmSuccess;
+}
 
 /* src/AwFmParallelSearch.c:36-84: the list, its 32-B entries, and one 4-slot position list per entry */
 struct AwFmKmerSearchList *awFmCreateKmerSearchList(const size_t capacity) {

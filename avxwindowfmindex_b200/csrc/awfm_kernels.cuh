@@ -383,6 +383,53 @@ __global__ void __launch_bounds__(256, 8)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// contig mapping: global text position -> (sequence index, offset inside that sequence).
+// awFmGetLocalSequencePositionFromIndexPosition (src/AwFmSearch.c:284-301) = fastaVectorGetLocalSequencePosition-
+// FromGlobal (lib/FastaVector/src/FastaVector.c:338-381): E[s] = cumulative end of record s INCLUDING its one-byte
+// separator; sequence = number of records with E[s] <= g (so g == E[last] yields numSequences, offset 0, exactly as
+// the reference's binary search does); offset = g - E[sequence-1]; g > E[last] is the reference's
+// AwFmIllegalPositionError and is reported as (UINT64_MAX, UINT64_MAX).
+// The first levels of the search run on a 256-entry sample of E staged in shared memory; the record table itself
+// (16 B x 10 k contigs for BASELINE cfg 5) stays L1/L2-resident.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMapSample = 256;
+__global__ void __launch_bounds__(256)
+    mapPositionsKernel(const uint64_t *__restrict__ ends, uint64_t numSequences, const uint64_t *__restrict__ positions,
+                       uint64_t n, uint64_t *__restrict__ sequenceIndex, uint64_t *__restrict__ localPosition) {
+  __shared__ uint64_t sample[kMapSample];  // sample[j] = E[min((j+1)*stride, numSequences) - 1]
+  const uint64_t stride = (numSequences + kMapSample - 1) / kMapSample;
+  for (uint32_t j = threadIdx.x; j < kMapSample; j += blockDim.x) {
+    const uint64_t last = min((uint64_t)(j + 1) * stride, numSequences);
+    sample[j] = last ? __ldg(ends + last - 1) : 0;
+  }
+  __syncthreads();
+  const uint64_t limit = numSequences ? __ldg(ends + numSequences - 1) : 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = positions[i];
+    if (numSequences == 0 || g > limit) {
+      sequenceIndex[i] = ~0ull;
+      localPosition[i] = ~0ull;
+      continue;
+    }
+    // bucket = number of sample entries <= g; records before bucket*stride all end at or before g
+    uint32_t lo = 0, hi = kMapSample;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (g < sample[mid]) hi = mid;
+      else lo = mid + 1;
+    }
+    uint64_t a = min((uint64_t)lo * stride, numSequences), b = min(a + stride, numSequences);
+    while (a < b) {  // invariant: every record before a has E <= g, every record from b on has E > g
+      const uint64_t mid = a + ((b - a) >> 1);
+      if (g < __ldg(ends + mid)) b = mid;
+      else a = mid + 1;
+    }
+    sequenceIndex[i] = a;
+    localPosition[i] = a ? g - __ldg(ends + a - 1) : g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // upload-time relayout: reference blocks -> lines (one thread per block)
 // ---------------------------------------------------------------------------------------------------------------
 // One thread per reference block (256 positions) -> two half-lines.  `superCounts[s][c]` = baseOccurrences[c] of the

@@ -38,6 +38,8 @@ class GpuIndex:
         self._ctx = C.c_void_p()
         view = arrays.view()
         capi.check(self.lib.awfm_gpu_ctx_create(C.byref(self._ctx), device, C.byref(view)))
+        if arrays.fasta_metadata is not None and len(arrays.fasta_metadata):
+            self.set_sequences(arrays.fasta_metadata)
 
     @classmethod
     def from_device_view(cls, view, device=0):
@@ -64,6 +66,26 @@ class GpuIndex:
             self.close()
         except Exception:
             pass
+
+    def set_sequences(self, fasta_metadata):
+        """Record table of a multi-sequence index: uint64 (numSequences, 2) = (headerEnd, sequenceEnd) per record, the
+        reference's struct FastaVectorMetadata array as stored in the `.awfmi` file (IndexArrays.fasta_metadata)."""
+        meta = np.ascontiguousarray(fasta_metadata, dtype=np.uint64).reshape(-1, 2)
+        capi.check(self.lib.awfm_gpu_ctx_set_sequences(self._ctx, _ptr(meta), len(meta)))
+
+    def map_positions(self, positions):
+        """Batched awFmGetLocalSequencePositionFromIndexPosition: (sequence_index, local_position, num_illegal)."""
+        positions = np.ascontiguousarray(positions, dtype=np.uint64)
+        seq = np.zeros(len(positions), np.uint64)
+        loc = np.zeros(len(positions), np.uint64)
+        bad = C.c_uint64()
+        capi.check(self.lib.awfm_gpu_map_positions_host(self._ctx, _ptr(positions), len(positions), _ptr(seq), _ptr(loc),
+                                                        C.byref(bad)))
+        return seq, loc, int(bad.value)
+
+    def map_positions_device(self, d_positions, n, d_sequence_index, d_local_position, stream=0):
+        capi.check(self.lib.awfm_gpu_map_positions_device(self._ctx, d_positions, n, d_sequence_index, d_local_position,
+                                                          stream or None))
 
     def set_tuning(self, **kv):
         for k, v in kv.items():

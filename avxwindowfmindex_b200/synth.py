@@ -44,3 +44,51 @@ def sampled_queries(text, num, length, seed=QUERY_SEED):
     starts = (z % np.uint64(len(text) - length + 1)).astype(np.int64)
     idx = starts[:, None] + np.arange(length)[None, :]
     return text[idx].reshape(-1).copy(), starts
+
+
+def multi_fasta_lengths(num_records, min_len, max_len, seed=TEXT_SEED):
+    """record lengths, uniform in [min_len, max_len] (BASELINE cfg 5: 10 000 contigs of 50 k-150 k)"""
+    z = splitmix64(seed ^ 0x5EC0, 0, num_records)
+    return (np.uint64(min_len) + z % np.uint64(max_len - min_len + 1)).astype(np.int64)
+
+
+def multi_fasta_text(lengths, amino=False, seed=TEXT_SEED):
+    """The text awFmCreateIndexFromFasta indexes (lib/FastaVector/src/FastaVector.c:54-170): records concatenated,
+    each followed by one NUL separator; plus the reference's record table (headerEnd, sequenceEnd) for headers
+    `contig{i}`.  Returns (text uint8, metadata uint64 (n, 2), header bytes)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    ends = np.cumsum(lengths + 1)
+    text = letters(seed, int(ends[-1]), amino)
+    text[ends - 1] = 0
+    header = b"".join(b"contig%d\0" % i for i in range(len(lengths)))
+    header_ends = np.cumsum([len(b"contig%d" % i) + 1 for i in range(len(lengths))])
+    meta = np.stack([header_ends.astype(np.uint64), ends.astype(np.uint64)], axis=1)
+    return text, meta, header
+
+
+def write_fasta(path, text, metadata, line=60):
+    """FASTA file (60-column lines, headers >contig{i}) that fastaVectorReadFasta turns back into `text`."""
+    ends = metadata[:, 1].astype(np.int64)
+    with open(path, "wb") as f:
+        start = 0
+        for i, e in enumerate(ends):
+            f.write(b">contig%d\n" % i)
+            rec = text[start:e - 1].tobytes()
+            for o in range(0, len(rec), line):
+                f.write(rec[o:o + line] + b"\n")
+            start = e
+
+
+def sampled_record_queries(text, metadata, num, length, seed=QUERY_SEED):
+    """`num` queries of `length` letters cut from inside random records (never across a separator), with the
+    by-construction answer: (record index, offset in record, global position)."""
+    ends = metadata[:, 1].astype(np.int64)
+    starts = np.concatenate([[0], ends[:-1]])
+    lens = ends - starts - 1
+    ok = np.nonzero(lens >= length)[0]
+    z = splitmix64(seed, 0, 2 * num)
+    rec = ok[(z[:num] % np.uint64(len(ok))).astype(np.int64)]
+    off = (z[num:] % (lens[rec] - length + 1).astype(np.uint64)).astype(np.int64)
+    g = starts[rec] + off
+    idx = g[:, None] + np.arange(length)[None, :]
+    return text[idx].reshape(-1).copy(), rec, off, g

@@ -73,7 +73,27 @@ struct AwFmSearchRange { /* src/AwFmIndex.h:88-91; inclusive [startPtr, endPtr],
   uint64_t endPtr;
 };
 
-struct FastaVector; /* lib/FastaVector/src/FastaVector.h — opaque on this path */
+/* lib/FastaVector (submodule @7ac0534): only the record table is read on this path (contig mapping of hits,
+ * src/AwFmSearch.c:284-301).  FastaVectorString.h, FastaVectorMetadataVector.h:10-19, FastaVector.h:23-32. */
+struct FastaVectorString {
+  char *charData;
+  size_t capacity;
+  size_t count;
+};
+struct FastaVectorMetadata {
+  size_t headerEndPosition;
+  size_t sequenceEndPosition; /* cumulative end of the record in the concatenated text, separator included */
+};
+struct FastaVectorMetadataVector {
+  struct FastaVectorMetadata *data;
+  size_t capacity;
+  size_t count;
+};
+struct FastaVector {
+  struct FastaVectorString sequence;
+  struct FastaVectorString header;
+  struct FastaVectorMetadataVector metadata;
+};
 
 struct AwFmIndex { /* src/AwFmIndex.h:94-109 */
   uint32_t versionNumber;
@@ -149,6 +169,14 @@ void awFmGpuReleaseIndex(const struct AwFmIndex *index);
 enum AwFmReturnCode awFmGpuPrepareIndex(const struct AwFmIndex *index);
 /* Return code of the most recent awFmParallelSearchCount on this thread (the reference's is void). */
 enum AwFmReturnCode awFmGpuLastCountStatus(void);
+/* Batched awFmGetLocalSequencePositionFromIndexPosition (src/AwFmIndex.h, src/AwFmSearch.c:284-301) on the device:
+ * for each of `count` global positions, the record number and the offset inside that record.  Returns
+ * AwFmUnsupportedVersionError when the index holds no FastaVector (as the reference does), AwFmIllegalPositionError
+ * when at least one position lies beyond the last record (those entries are set to SIZE_MAX, the others are valid),
+ * else AwFmSuccess. */
+enum AwFmReturnCode awFmGpuGetLocalSequencePositions(const struct AwFmIndex *index, const size_t *globalPositions,
+                                                     size_t count, size_t *sequenceNumbers,
+                                                     size_t *localSequencePositions);
 
 #ifndef __cplusplus
 _Static_assert(sizeof(struct AwFmNucleotideBlock) == 160, "nucleotide block is 160 B");
@@ -163,6 +191,9 @@ _Static_assert(sizeof(struct AwFmKmerSearchList) == 24, "search list is 24 B");
 _Static_assert(sizeof(struct AwFmIndex) == 112, "index struct is 112 B");
 _Static_assert(offsetof(struct AwFmIndex, config) == 48, "config at 48");
 _Static_assert(offsetof(struct AwFmIndex, suffixArray) == 88, "suffixArray at 88");
+_Static_assert(sizeof(struct FastaVector) == 72, "FastaVector is 72 B");
+_Static_assert(offsetof(struct FastaVector, metadata) == 48, "metadata vector at 48");
+_Static_assert(sizeof(struct FastaVectorMetadata) == 16, "record metadata is 16 B");
 #endif
 
 #ifdef __cplusplus

@@ -125,6 +125,21 @@ int awfm_gpu_locate_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, const u
                            uint64_t numQueries, uint64_t hitBegin, uint64_t hitEnd, uint64_t *dPositions,
                            void *stream);
 
+/* ---- contig mapping for multi-sequence (FASTA) indexes — SURVEY.md §8 row f2.  Replaces, for whole batches of
+ *      hits, awFmGetLocalSequencePositionFromIndexPosition (src/AwFmSearch.c:284-301), i.e.
+ *      fastaVectorGetLocalSequencePositionFromGlobal (lib/FastaVector/src/FastaVector.c:338-381). ---- */
+/* `metadata` = the reference's own struct FastaVectorMetadata[numSequences] (two size_t per record:
+ * headerEndPosition, sequenceEndPosition; lib/FastaVector/src/FastaVectorMetadataVector.h:10-13), HOST memory, copied. */
+int awfm_gpu_ctx_set_sequences(awfm_gpu_ctx *ctx, const void *metadata, uint64_t numSequences);
+/* For every position: sequenceIndex = number of records ending at or before it, localPosition = offset inside that
+ * record.  A position beyond the last record's end (the reference's AwFmIllegalPositionError) gives UINT64_MAX in
+ * both outputs.  Device buffers, asynchronous on `stream`. */
+int awfm_gpu_map_positions_device(awfm_gpu_ctx *ctx, const uint64_t *dPositions, uint64_t numPositions,
+                                  uint64_t *dSequenceIndex, uint64_t *dLocalPosition, void *stream);
+/* Same on HOST buffers; *numIllegal (may be NULL) receives the number of illegal positions. */
+int awfm_gpu_map_positions_host(awfm_gpu_ctx *ctx, const uint64_t *positions, uint64_t numPositions,
+                                uint64_t *sequenceIndex, uint64_t *localPosition, uint64_t *numIllegal);
+
 /* ---- the reference's own search-list layout (used by the drop-in shim) ---- */
 /* Fills data[i].count for i < numQueries (uint32 truncation as in src/AwFmParallelSearch.c:187-190). */
 int awfm_gpu_search_list_count(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,

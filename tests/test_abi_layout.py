@@ -26,6 +26,10 @@ O(AwFmIndex,kmerSeedTable);O(AwFmIndex,fileHandle);O(AwFmIndex,config);O(AwFmInd
 O(AwFmIndex,sequenceFileOffset);O(AwFmIndex,fastaVector);O(AwFmIndex,suffixArray);
 O(AwFmKmerSearchData,kmerString);O(AwFmKmerSearchData,kmerLength);O(AwFmKmerSearchData,positionList);O(AwFmKmerSearchData,count);O(AwFmKmerSearchData,capacity);
 O(AwFmKmerSearchList,capacity);O(AwFmKmerSearchList,count);O(AwFmKmerSearchList,kmerSearchData);
+P(FastaVector);P(FastaVectorString);P(FastaVectorMetadata);P(FastaVectorMetadataVector);
+O(FastaVector,sequence);O(FastaVector,header);O(FastaVector,metadata);O(FastaVectorMetadata,headerEndPosition);
+O(FastaVectorMetadata,sequenceEndPosition);O(FastaVectorMetadataVector,data);O(FastaVectorMetadataVector,count);
+O(FastaVectorString,charData);O(FastaVectorString,count);
 printf("codes %d %d %d %d %d\n", AwFmSuccess, AwFmFileReadOkay, AwFmGeneralFailure, AwFmAllocationFailure, AwFmFileReadFail);
 printf("alphabets %d %d %d\n", AwFmAlphabetAmino, AwFmAlphabetDna, AwFmAlphabetRna);
 return 0;}

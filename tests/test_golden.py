@@ -58,10 +58,13 @@ def test_cuda_reproduces_golden(case):
     gpu = GpuIndex(arrays)
     for lpq in (8, 4, 2, 1):
         for variant in (0, 1):
-            gpu.set_tuning(count_lpq=lpq, locate_lpq=lpq, count_variant=variant)
+            gpu.set_tuning(count_lpq=lpq, locate_lpq=lpq, count_variant=variant, locate_variant=variant)
             counts = gpu.count(g["letters"], g["offsets"])
             assert np.array_equal(counts, g["counts"]), (case, lpq, variant)
             hit_offsets, positions = gpu.locate(g["letters"], g["offsets"])
             assert np.array_equal(hit_offsets, g["hit_offsets"]), (case, lpq, variant)
             assert np.array_equal(positions, g["positions"]), (case, lpq, variant)
+    if "contig_of_hit" in g.files:  # the FASTA case: every hit mapped to (record, offset) as the reference does
+        seq, loc, bad = gpu.map_positions(g["positions"])
+        assert bad == 0 and np.array_equal(np.stack([seq, loc], axis=1), g["contig_of_hit"])
     gpu.close()

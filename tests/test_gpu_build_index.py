@@ -95,3 +95,19 @@ def test_amino_device_text(reference, tmp_path):
     assert_same(built, reference.arrays(ptr), "amino")
     built.close()
     reference.dealloc_index(ptr)
+
+
+def test_multi_fasta_text_matches_create_index_from_fasta(reference, tmp_path):
+    """The text awFmCreateIndexFromFasta indexes is the records joined by NUL separators, one after the last record
+    too (lib/FastaVector/src/FastaVector.c:54-170); the separators are sanitised to the ambiguity letter
+    (src/AwFmLetter.c:24-42).  Built on the device from that text, the arrays equal the reference's."""
+    lengths = synth.multi_fasta_lengths(300, 0, 900, seed=21)
+    text, meta, header = synth.multi_fasta_text(lengths, seed=22)
+    fasta = str(tmp_path / "m.fa")
+    synth.write_fasta(fasta, text, meta)
+    ptr = reference.create_index_from_fasta(fasta, str(tmp_path / "m.awfmi"), abi.AwFmAlphabetDna, 5, 8)
+    ref_arrays = reference.arrays(ptr)
+    assert np.array_equal(ref_arrays.fasta_metadata, meta)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetDna, 5, 8)
+    assert_same(built, ref_arrays, "multi-fasta")
+    built.close()

@@ -34,7 +34,7 @@ def test_packed_batch_matches_oracle_and_reference(small_indexes, reference, nam
     gpu = GpuIndex(b.arrays)
     for lpq in (8, 4, 2, 1):
         for variant in (1, 0):
-            gpu.set_tuning(count_lpq=lpq, locate_lpq=lpq, count_variant=variant)
+            gpu.set_tuning(count_lpq=lpq, locate_lpq=lpq, count_variant=variant, locate_variant=variant)
             counts, ranges = gpu.count(letters, offsets, want_ranges=True)
             assert np.array_equal(counts, r_counts), (name, lpq, variant)
             assert np.array_equal(ranges, o_ranges), (name, lpq, variant)

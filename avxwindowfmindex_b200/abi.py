@@ -114,3 +114,10 @@ class awfm_gpu_stats(C.Structure):  # include/awfm_gpu.h
 assert C.sizeof(AwFmIndex) == 112 and AwFmIndex.config.offset == 48 and AwFmIndex.suffixArray.offset == 88
 assert C.sizeof(AwFmKmerSearchData) == 32 and C.sizeof(AwFmKmerSearchList) == 24
 assert C.sizeof(AwFmIndexConfiguration) == 12 and C.sizeof(AwFmCompressedSuffixArray) == 24
+
+
+class awfm_file_info(C.Structure):  # include/awfm_gpu.h
+    _fields_ = [("bwtLength", C.c_uint64), ("numSequences", C.c_uint64), ("suffixArrayByteLength", C.c_uint64),
+                ("versionNumber", C.c_uint32), ("featureFlags", C.c_uint32),
+                ("suffixArrayCompressionRatio", C.c_uint8), ("kmerLengthInSeedTable", C.c_uint8),
+                ("alphabetType", C.c_uint8), ("storeOriginalSequence", C.c_uint8)]

@@ -4,7 +4,11 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Xcompiler -fPIC,-fopenmp -shared
 // There is NO CPU fallback anywhere in this file: every entry point fails when CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -78,6 +82,11 @@ struct awfm_gpu_ctx {
   DevIndex ix{};
   void *dLines = nullptr, *dXBase = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
   uint64_t *dSequenceEnds = nullptr;
+  void *dDeepSeed = nullptr, *dDenseSa = nullptr;  // derived structures (extend_seed_table / densify_suffix_array)
+  uint64_t deepSeedBytes = 0, denseSaBytes = 0;
+  uint32_t deepSeedKBuilt = 0;
+  const void *origSa = nullptr;                    // the index's own sampled SA, restored when the dense one is dropped
+  uint32_t origSaBitWidth = 0, origSaRatio = 0, origSaRatioShift = 0;
   uint64_t deviceBytes = 0;
   bool hasSa = false;
   // tuning
@@ -225,6 +234,8 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   }
   ix.seedK = v->seedK;
   ix.amino = amino;
+  ix.deepSeedTable = nullptr;
+  ix.deepSeedK = ix.deepSeedWide = 0;
   CUB_(cudaMalloc(&c->dWorkCounter, 64));
   for (auto &s : c->slots) {
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -240,6 +251,115 @@ extern "C" int awfm_gpu_ctx_create(awfm_gpu_ctx **ctx, int device, const awfm_in
 }
 extern "C" int awfm_gpu_ctx_create_from_device(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view) {
   return ctxCreateCommon(ctx, device, view, true);
+}
+
+// ------------------------------------------------------------------------------------------------ .awfmi loader
+// SURVEY.md §8 row f3.  The reference reads an index with fread() into freshly malloc'ed host arrays
+// (awFmReadIndexFromFile, src/AwFmFile.c:195-449) and the drop-in then uploads those.  Here the version-8 file
+// (layout: src/AwFmFile.c:48-187, offsets :524-558) is mapped read-only and its sections are copied from the page
+// cache straight into device staging, re-laid out slab by slab; no host copy of the index is ever built.
+struct AwfmiSections {
+  uint64_t fileBytes, bwtLength, numBlocks, blockBytes, blocksOff, prefixOff, numPrefix, seedOff, numSeeds, saOff,
+      saBytes, headerOff, headerBytes, metaOff, numSequences;
+  uint32_t version, featureFlags;
+  uint8_t saRatio, seedK, alphabet, storesSequence, saBitWidth;
+};
+
+static int parseAwfmi(const uint8_t *f, uint64_t fileBytes, AwfmiSections *o) {
+  memset(o, 0, sizeof *o);
+  o->fileBytes = fileBytes;
+  if (fileBytes < 30 || memcmp(f, "AwFmIndex\n", 10) != 0) return fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (bad magic)");
+  memcpy(&o->version, f + 10, 4);
+  memcpy(&o->featureFlags, f + 14, 4);
+  if (o->version != 8) return fail(AWFM_GPU_ERR_ARG, "unsupported .awfmi version (this loader reads version 8)");
+  o->saRatio = f[18], o->seedK = f[19], o->alphabet = f[20], o->storesSequence = f[21];
+  memcpy(&o->bwtLength, f + 22, 8);
+  if (o->alphabet < 1 || o->alphabet > 3 || o->saRatio == 0 || o->bwtLength < 2) return fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header");
+  const bool amino = o->alphabet == 1;
+  o->numBlocks = 1 + (o->bwtLength - 1) / 256;
+  o->blockBytes = amino ? 352 : 160;
+  o->numPrefix = amino ? 22 : 6;
+  if (o->seedK > (amino ? 14 : 31)) return fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header (seed length)");
+  o->numSeeds = numSeedsOf(o->alphabet, o->seedK);
+  o->blocksOff = 30;
+  o->prefixOff = o->blocksOff + o->numBlocks * o->blockBytes;
+  o->seedOff = o->prefixOff + o->numPrefix * 8;
+  o->saOff = o->seedOff + o->numSeeds * 16 + (o->storesSequence ? o->bwtLength - 1 : 0);
+  o->saBitWidth = (uint8_t)(64 - __builtin_clzll(o->bwtLength - 1 ? o->bwtLength - 1 : 1));  // src/AwFmSuffixArray.c:12-18
+  const uint64_t samples = (o->bwtLength + o->saRatio - 1) / o->saRatio;                     // :144-147
+  o->saBytes = (samples * o->saBitWidth + 7) / 8 + 8;                                        // :41-53
+  uint64_t end = o->saOff + o->saBytes;
+  if (end > fileBytes) return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file");
+  if (o->featureFlags & 1u) {  // FastaVector section: header length, record count, header chars, record table
+    if (end + 16 > fileBytes) return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
+    memcpy(&o->headerBytes, f + end, 8);
+    memcpy(&o->numSequences, f + end + 8, 8);
+    o->headerOff = end + 16;
+    o->metaOff = o->headerOff + o->headerBytes;
+    if (o->metaOff < o->headerOff || o->numSequences > (fileBytes - o->metaOff) / 16 || o->metaOff > fileBytes)
+      return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
+  }
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_ctx_create_from_file(awfm_gpu_ctx **ctx, int device, const char *path, int wantSuffixArray,
+                                             awfm_file_info *info) {
+  if (!ctx || !path) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(AWFM_GPU_ERR_ARG, "cannot open index file", path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 30) {
+    close(fd);
+    return fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (too short)", path);
+  }
+  const uint64_t bytes = (uint64_t)st.st_size;
+  void *map = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return fail(AWFM_GPU_ERR_ALLOC, "mmap of the index file failed", path);
+  madvise(map, bytes, MADV_SEQUENTIAL);
+  const uint8_t *f = (const uint8_t *)map;
+  AwfmiSections sec;
+  int rc = parseAwfmi(f, bytes, &sec);  // format errors are reported before any CUDA call
+  if (rc == AWFM_GPU_OK) {
+    uint64_t prefix[24] = {0};
+    memcpy(prefix, f + sec.prefixOff, sec.numPrefix * 8);  // unaligned in the file
+    awfm_index_view v;
+    memset(&v, 0, sizeof v);
+    v.blocks = f + sec.blocksOff;
+    v.numBlocks = sec.numBlocks;
+    v.prefixSums = prefix;
+    v.seedTable = f + sec.seedOff;
+    v.saBytes = wantSuffixArray ? f + sec.saOff : nullptr;
+    v.saByteLength = sec.saBytes;
+    v.bwtLength = sec.bwtLength;
+    v.saBitWidth = sec.saBitWidth;
+    v.saRatio = sec.saRatio;
+    v.seedK = sec.seedK;
+    v.alphabet = sec.alphabet;
+    rc = ctxCreateCommon(ctx, device, &v, false);
+    if (rc == AWFM_GPU_OK && sec.numSequences) {
+      std::vector<uint64_t> meta(sec.numSequences * 2);
+      memcpy(meta.data(), f + sec.metaOff, sec.numSequences * 16);
+      rc = awfm_gpu_ctx_set_sequences(*ctx, meta.data(), sec.numSequences);
+      if (rc != AWFM_GPU_OK) {
+        awfm_gpu_ctx_destroy(*ctx);
+        *ctx = nullptr;
+      }
+    }
+  }
+  if (info) {
+    info->bwtLength = sec.bwtLength;
+    info->numSequences = sec.numSequences;
+    info->suffixArrayByteLength = sec.saBytes;
+    info->versionNumber = sec.version;
+    info->featureFlags = sec.featureFlags;
+    info->suffixArrayCompressionRatio = sec.saRatio;
+    info->kmerLengthInSeedTable = sec.seedK;
+    info->alphabetType = sec.alphabet;
+    info->storeOriginalSequence = sec.storesSequence;
+  }
+  munmap(map, bytes);
+  return rc;
 }
 
 static void freeSlot(PipeSlot &s) {
@@ -270,6 +390,8 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dSeed);
   cudaFree(c->dSa);
   cudaFree(c->dSequenceEnds);
+  cudaFree(c->dDeepSeed);
+  cudaFree(c->dDenseSa);
   cudaFree(c->scanTemp);
   cudaFree(c->dLengths);
   cudaFree(c->dWorkCounter);
@@ -287,8 +409,11 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "locate_lpq" && lpqOk(value)) c->locateLpq = (int)value;
   else if (k == "count_variant" && (value == 0 || value == 1)) c->countVariant = (int)value;
   else if (k == "locate_variant" && (value == 0 || value == 1)) c->locateVariant = (int)value;
-  else if (k == "chunk_queries" && value >= 1024) c->chunkQueries = value;
-  else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
+  else if (k == "use_deep_seed_table" && (value == 0 || value == 1)) {  // A/B switch for a table already derived
+    const bool on = value && c->dDeepSeed;
+    c->ix.deepSeedTable = on ? c->dDeepSeed : nullptr;
+    c->ix.deepSeedK = on ? c->deepSeedKBuilt : 0;
+  }
   else return fail(AWFM_GPU_ERR_ARG, "unknown tuning key or bad value", key);
   return AWFM_GPU_OK;
 }
@@ -356,33 +481,39 @@ static int launchCount(awfm_gpu_ctx *c, const QueryBatch &qb, uint32_t *dCounts,
   return AWFM_GPU_OK;
 }
 
+// the walk itself: dPos holds BWT positions on entry, text positions on exit
+template <int LPQ, bool AMINO>
+static int launchWalk(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
+  int grid = 0;
+  if (c->locateVariant == 1) {  // group per hit with refill from a chunk dispenser
+    auto k = locateKernelRefill<LPQ, AMINO>;
+    if (int r = gridFor(c, k, 256, &grid)) return r;
+    const uint64_t need = (numHits * LPQ + 255) / 256;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, need);
+    CU(cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), st));
+    k<<<grid, 256, 0, st>>>(c->ix, numHits, dPos, c->dWorkCounter);
+    CU(cudaGetLastError());
+    return AWFM_GPU_OK;
+  }
+  auto k = locateKernel<LPQ, AMINO>;
+  if (int r = gridFor(c, k, 256, &grid)) return r;
+  const uint64_t need = (numHits * LPQ + 255) / 256;
+  grid = (int)std::min<uint64_t>((uint64_t)grid, need);
+  k<<<grid, 256, 0, st>>>(c->ix, numHits, dPos);
+  CU(cudaGetLastError());
+  return AWFM_GPU_OK;
+}
+
 template <int LPQ, bool AMINO>
 static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *dHitOffsets, uint64_t n,
                         uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
-  int grid = 0;
   {  // BWT start position of every hit of the window, written into the output buffer itself
     const uint64_t warps = (n + 31) / 32;
     const int g = (int)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->numSMs * 8);
     expandHits<<<std::max(g, 1), 256, 0, st>>>(dRanges, dHitOffsets, n, hb, he, dPos);
     CU(cudaGetLastError());
   }
-  if (c->locateVariant == 1) {  // group per hit with refill from a chunk dispenser
-    auto k = locateKernelRefill<LPQ, AMINO>;
-    if (int r = gridFor(c, k, 256, &grid)) return r;
-    const uint64_t need = ((he - hb) * LPQ + 255) / 256;
-    grid = (int)std::min<uint64_t>((uint64_t)grid, need);
-    CU(cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), st));
-    k<<<grid, 256, 0, st>>>(c->ix, he - hb, dPos, c->dWorkCounter);
-    CU(cudaGetLastError());
-    return AWFM_GPU_OK;
-  }
-  auto k = locateKernel<LPQ, AMINO>;
-  if (int r = gridFor(c, k, 256, &grid)) return r;
-  const uint64_t need = ((he - hb) * LPQ + 255) / 256;
-  grid = (int)std::min<uint64_t>((uint64_t)grid, need);
-  k<<<grid, 256, 0, st>>>(c->ix, he - hb, dPos);
-  CU(cudaGetLastError());
-  return AWFM_GPU_OK;
+  return launchWalk<LPQ, AMINO>(c, he - hb, dPos, st);
 }
 
 // nucleotide half-lines have 4 chunks (groups of 1, 2 or 4 lanes); amino quarter-lines 2 chunks (1 or 2 lanes);
@@ -393,6 +524,11 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
            : ((lpq) == 1   ? fn<1, false>(__VA_ARGS__)                     \
               : (lpq) == 2 ? fn<2, false>(__VA_ARGS__)                     \
                            : fn<4, false>(__VA_ARGS__)))
+
+static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
+  if (numHits == 0) return AWFM_GPU_OK;
+  return DISPATCH_LPQ(launchWalk, c->locateLpq, c->ix.amino != 0, c, numHits, dPos, st);
+}
 
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
                            uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
@@ -467,6 +603,150 @@ extern "C" int awfm_gpu_locate_device(awfm_gpu_ctx *c, const awfm_range *dRanges
   if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return fail(AWFM_GPU_ERR_ARG, "null argument");
   if (int r = setDevice(c)) return r;
   return locateDeviceImpl(c, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ derived structures
+static uint32_t ratioShiftOf(uint32_t ratio) {
+  if (ratio & (ratio - 1)) return 0xFFFFFFFFu;
+  uint32_t s = 0;
+  while ((1u << s) < ratio) s++;
+  return s;
+}
+
+template <bool AMINO>
+static int extendSeedLevels(awfm_gpu_ctx *c, uint32_t depth, bool wide) {
+  const uint64_t card = AMINO ? 20 : 4;
+  const uint64_t entryBytes = wide ? 16 : 8;
+  const void *src = c->dSeed;
+  bool srcWide = true;
+  uint64_t numSrc = c->ix.numSeeds;
+  void *prev = nullptr;  // intermediate level owned here
+  for (uint32_t level = c->ix.seedK; level < depth; level++) {
+    void *dst = nullptr;
+    cudaError_t e = cudaMalloc(&dst, numSrc * card * entryBytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(prev);
+      return fail(AWFM_GPU_ERR_ALLOC, "derived seed table does not fit in device memory", cudaGetErrorString(e));
+    }
+    const int grid = c->numSMs * 8;
+    if (srcWide && wide) extendSeedTable<AMINO, true, true><<<grid, 256>>>(c->ix, src, numSrc, dst);
+    else if (srcWide) extendSeedTable<AMINO, true, false><<<grid, 256>>>(c->ix, src, numSrc, dst);
+    else if (wide) extendSeedTable<AMINO, false, true><<<grid, 256>>>(c->ix, src, numSrc, dst);
+    else extendSeedTable<AMINO, false, false><<<grid, 256>>>(c->ix, src, numSrc, dst);
+    e = cudaDeviceSynchronize();
+    cudaFree(prev);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(dst);
+      return fail(AWFM_GPU_ERR_CUDA, "extendSeedTable", cudaGetErrorString(e));
+    }
+    prev = dst;
+    src = dst;
+    srcWide = wide;
+    numSrc *= card;
+  }
+  c->dDeepSeed = prev;
+  c->deepSeedBytes = numSrc * entryBytes;
+  return AWFM_GPU_OK;
+}
+
+extern "C" int awfm_gpu_ctx_extend_seed_table(awfm_gpu_ctx *c, uint32_t depth, double *buildMs) {
+  if (!c) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  CU(cudaDeviceSynchronize());
+  const double t0 = omp_get_wtime();
+  if (buildMs) *buildMs = 0;
+  // drop what is there
+  cudaFree(c->dDeepSeed);
+  c->dDeepSeed = nullptr;
+  c->deviceBytes -= c->deepSeedBytes;
+  c->deepSeedBytes = 0;
+  c->ix.deepSeedTable = nullptr;
+  c->ix.deepSeedK = 0;
+  c->deepSeedKBuilt = 0;
+  if (depth <= c->ix.seedK) return AWFM_GPU_OK;
+  const bool amino = c->ix.amino != 0;
+  if (depth > (amino ? 9u : 20u)) return fail(AWFM_GPU_ERR_ARG, "seed table depth too large (max 20 nucleotide, 9 amino)");
+  const bool wide = c->ix.bwtLength > (1ull << 32);
+  int rc = amino ? extendSeedLevels<true>(c, depth, wide) : extendSeedLevels<false>(c, depth, wide);
+  if (rc) return rc;
+  c->deviceBytes += c->deepSeedBytes;
+  c->ix.deepSeedTable = c->dDeepSeed;
+  c->ix.deepSeedK = depth;
+  c->deepSeedKBuilt = depth;
+  c->ix.deepSeedWide = wide;
+  if (buildMs) *buildMs = 1e3 * (omp_get_wtime() - t0);
+  return AWFM_GPU_OK;
+}
+
+static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st);
+
+extern "C" int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *c, uint32_t newRatio, double *buildMs) {
+  if (!c) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (int r = setDevice(c)) return r;
+  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  CU(cudaDeviceSynchronize());
+  const double t0 = omp_get_wtime();
+  if (buildMs) *buildMs = 0;
+  if (c->dDenseSa) {  // back to the index's own samples
+    cudaFree(c->dDenseSa);
+    c->dDenseSa = nullptr;
+    c->deviceBytes -= c->denseSaBytes;
+    c->denseSaBytes = 0;
+    c->ix.sa = (const uint64_t *)c->origSa;
+    c->ix.saBitWidth = c->origSaBitWidth;
+    c->ix.saRatio = c->origSaRatio;
+    c->ix.saRatioShift = c->origSaRatioShift;
+  }
+  if (newRatio == 0 || newRatio >= c->ix.saRatio) return AWFM_GPU_OK;
+  // samples at BWT positions j*newRatio, stored as aligned 32- or 64-bit fields (a packed SA of that width)
+  const uint64_t n = c->ix.bwtLength;
+  const uint64_t samples = (n + newRatio - 1) / newRatio;
+  const uint32_t width = c->ix.saBitWidth <= 32 ? 32 : 64;
+  const uint64_t bytes = ((samples * (width / 8) + 15) & ~15ull) + 16;
+  void *dense = nullptr;
+  uint64_t *work = nullptr;
+  const uint64_t slab = std::min<uint64_t>(samples, 1ull << 28);  // 2 GiB of walk state at a time
+  if (cudaMalloc(&dense, bytes) != cudaSuccess || cudaMalloc(&work, slab * 8) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(dense);
+    cudaFree(work);
+    return fail(AWFM_GPU_ERR_ALLOC, "dense suffix array does not fit in device memory");
+  }
+  cudaMemset(dense, 0, bytes);
+  cudaStream_t st = c->slots[0].stream;
+  int rc = AWFM_GPU_OK;
+  for (uint64_t first = 0; first < samples && rc == AWFM_GPU_OK; first += slab) {
+    const uint64_t count = std::min(slab, samples - first);
+    saIota<<<c->numSMs * 8, 256, 0, st>>>(work, first, count, newRatio);
+    rc = locateDeviceRaw(c, count, work, st);
+    if (rc == AWFM_GPU_OK) {
+      if (width == 32) saNarrow<uint32_t><<<c->numSMs * 8, 256, 0, st>>>(work, count, (uint32_t *)dense + first);
+      else saNarrow<uint64_t><<<c->numSMs * 8, 256, 0, st>>>(work, count, (uint64_t *)dense + first);
+      if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "densify suffix array", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  cudaFree(work);
+  if (rc) {
+    cudaFree(dense);
+    return rc;
+  }
+  c->origSa = c->dSa;
+  c->origSaBitWidth = c->ix.saBitWidth;
+  c->origSaRatio = c->ix.saRatio;
+  c->origSaRatioShift = c->ix.saRatioShift;
+  c->dDenseSa = dense;
+  c->denseSaBytes = bytes;
+  c->deviceBytes += bytes;
+  c->ix.sa = (const uint64_t *)dense;
+  c->ix.saBitWidth = width;
+  c->ix.saRatio = newRatio;
+  c->ix.saRatioShift = ratioShiftOf(newRatio);
+  if (buildMs) *buildMs = 1e3 * (omp_get_wtime() - t0);
+  return AWFM_GPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ contig mapping

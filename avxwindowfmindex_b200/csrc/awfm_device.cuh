@@ -44,6 +44,10 @@ struct DevIndex {
   const uint32_t *xRel;      // nucleotide only: relative count of the ambiguity letter per half-line
   const uint64_t *superC;    // [superblock][8 | 24] = C[c] + count of c before the superblock (c = 0..4 | 0..20)
   const uint4 *seedTable;    // {startLo, startHi, endLo, endHi}
+  const void *deepSeedTable; // derived at upload time (awfm_gpu_ctx_extend_seed_table), or nullptr: the range the
+                             // reference holds after the last deepSeedK letters; uint2 {start, end} when
+                             // bwtLength <= 2^32, else uint4 like seedTable
+  uint32_t deepSeedK, deepSeedWide;
   const uint64_t *sa;        // bit-packed sampled SA viewed as little-endian u64 words (+16 B zero padding)
   const uint64_t *sequenceEnds;  // cumulative end offset of every FASTA record (incl. its separator), or nullptr
   uint64_t numSequences;

@@ -119,8 +119,12 @@ static int contextFor(const struct AwFmIndex *index, awfm_gpu_ctx **out) {
     if ((e = getenv("AWFM_GPU_COUNT_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "count_variant", atoll(e));
     if ((e = getenv("AWFM_GPU_CHUNK_QUERIES"))) awfm_gpu_ctx_set_tuning(ctx, "chunk_queries", atoll(e));
     if ((e = getenv("AWFM_GPU_LOCATE_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "locate_variant", atoll(e));
+    /* opt-in derived structures (include/awfm_gpu.h): deeper seed table, denser SA samples */
+    if ((e = getenv("AWFM_GPU_SEED_DEPTH")) && atoi(e) > 0) rc = awfm_gpu_ctx_extend_seed_table(ctx, (uint32_t)atoi(e), NULL);
+    if (rc == AWFM_GPU_OK && view.saBytes && (e = getenv("AWFM_GPU_SA_RATIO")) && atoi(e) > 0)
+      rc = awfm_gpu_ctx_densify_suffix_array(ctx, (uint32_t)atoi(e), NULL);
     /* multi-sequence index: the record table rides along for awFmGpuGetLocalSequencePositions */
-    if (index->fastaVector && index->fastaVector->metadata.count)
+    if (rc == AWFM_GPU_OK && index->fastaVector && index->fastaVector->metadata.count)
       rc = awfm_gpu_ctx_set_sequences(ctx, index->fastaVector->metadata.data, index->fastaVector->metadata.count);
     if (rc != AWFM_GPU_OK) {
       awfm_gpu_ctx_destroy(ctx);

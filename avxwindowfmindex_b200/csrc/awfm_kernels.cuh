@@ -21,41 +21,60 @@ __device__ __forceinline__ void queryExtent(const QueryBatch &qb, uint64_t q, ui
   }
 }
 
+// Seed-table entry `index` of the original table (deep = false) or of the derived deeper one.
+__device__ __forceinline__ void loadSeedEntry(const DevIndex &ix, bool deep, uint64_t index, uint64_t &sp, uint64_t &ep) {
+  if (deep && !ix.deepSeedWide) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(ix.deepSeedTable) + index);
+    sp = r.x;
+    ep = r.y;
+  } else {
+    const uint4 r = __ldg((deep ? reinterpret_cast<const uint4 *>(ix.deepSeedTable) : ix.seedTable) + index);
+    sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
+    ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
+  }
+}
+
+// Table index of the last `k` letters (leftmost most significant, src/AwFmKmerTable.c:21-51); false when one of them is
+// not a searchable letter (src/AwFmKmerTable.c:4-19).  LETTERS are letter indices when TRANSLATED, else ASCII.
+template <bool AMINO, bool TRANSLATED>
+__device__ __forceinline__ bool seedIndexOf(const uint8_t *__restrict__ s, uint64_t len, uint32_t k, uint64_t &index) {
+  constexpr uint32_t CARD = AMINO ? 20u : 4u;
+  bool seedable = true;
+  uint64_t t = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    const uint32_t l = TRANSLATED ? (uint32_t)s[(len - k) + i] : letterIndex<AMINO>(__ldg(s + (len - k) + i));
+    seedable &= (l < CARD);
+    t = t * CARD + l;
+  }
+  index = t;
+  return seedable;
+}
+
 // Opens the range for one query (src/AwFmParallelSearch.c:222-271): seed-table entry when the last k letters are
 // all searchable letters (src/AwFmKmerTable.c:4-51), otherwise [C[c], C[c+1]-1] of the last letter
 // (src/AwFmSearch.c:485-501).  Returns the number of leading letters still to be stepped through; sets an
 // empty range (1,0) for inputs the reference leaves undefined (len == 0, '$' inside a query).
-template <bool AMINO>
+// With a derived deep table (awfm_gpu_ctx_extend_seed_table) a query whose last deepSeedK letters are all searchable
+// starts from the range the reference would hold after stepping through those letters — same result, fewer steps.
+template <bool AMINO, bool TRANSLATED = false>
 __device__ __forceinline__ uint64_t openRange(const DevIndex &ix, const uint8_t *__restrict__ s, uint64_t len,
                                               uint64_t &sp, uint64_t &ep) {
   constexpr uint32_t CARD = AMINO ? 20u : 4u;
   const uint32_t k = ix.seedK;
-  if (len == 0) {
-    sp = 1;
-    ep = 0;
-    return 0;
+  sp = 1;
+  ep = 0;
+  if (len == 0) return 0;
+  uint64_t tableIndex;
+  if (ix.deepSeedK && len >= ix.deepSeedK && seedIndexOf<AMINO, TRANSLATED>(s, len, ix.deepSeedK, tableIndex)) {
+    loadSeedEntry(ix, true, tableIndex, sp, ep);
+    return len - ix.deepSeedK;
   }
-  if (len >= k) {
-    uint64_t tableIndex = 0;
-    bool seedable = true;
-    for (uint32_t i = 0; i < k; i++) {
-      const uint32_t l = letterIndex<AMINO>(__ldg(s + (len - k) + i));
-      seedable &= (l < CARD);
-      tableIndex = tableIndex * CARD + l;
-    }
-    if (seedable) {
-      const uint4 r = __ldg(ix.seedTable + tableIndex);
-      sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
-      ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
-      return len - k;
-    }
+  if (len >= k && seedIndexOf<AMINO, TRANSLATED>(s, len, k, tableIndex)) {
+    loadSeedEntry(ix, false, tableIndex, sp, ep);
+    return len - k;
   }
-  const uint32_t last = letterIndex<AMINO>(__ldg(s + len - 1));
-  if (last > CARD) {
-    sp = 1;
-    ep = 0;
-    return 0;
-  }
+  const uint32_t last = TRANSLATED ? (uint32_t)s[len - 1] : letterIndex<AMINO>(__ldg(s + len - 1));
+  if (last > CARD) return 0;
   sp = ix.prefixSums[last];
   ep = ix.prefixSums[last + 1] - 1;
   return len - 1;
@@ -107,8 +126,8 @@ __global__ void __launch_bounds__(256)
 template <int TILE>
 struct TileSmem {
   uint64_t sp[TILE], ep[TILE];
+  uint64_t next[TILE];   // letters still to step through
   uint32_t start[TILE];  // offset of the query's first letter inside `letters`
-  uint32_t next[TILE];   // letters still to step through
   uint32_t counter;
   uint32_t lettersBase;  // 16-B aligned-down global byte offset of letters[0] (low bits)
 };
@@ -169,43 +188,12 @@ __global__ void __launch_bounds__(256)
     for (uint32_t t = threadIdx.x; t < nq; t += blockDim.x) {
       uint64_t off, len, sp, ep, next;
       queryExtent(qb, q0 + t, off, len);
-      if (staged) {
-        const uint8_t *s = letters + (off - aligned0);
-        const uint32_t k = ix.seedK;
-        next = 0;
-        sp = 1;
-        ep = 0;
-        if (len > 0) {
-          bool seedable = len >= k;
-          uint64_t tableIndex = 0;
-          if (seedable) {
-            for (uint32_t i = 0; i < k; i++) {
-              const uint32_t l = s[(len - k) + i];
-              seedable &= (l < CARD);
-              tableIndex = tableIndex * CARD + l;
-            }
-          }
-          if (seedable) {
-            const uint4 r = __ldg(ix.seedTable + tableIndex);
-            sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
-            ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
-            next = len - k;
-          } else {
-            const uint32_t last = s[len - 1];
-            if (last <= CARD) {
-              sp = ix.prefixSums[last];
-              ep = ix.prefixSums[last + 1] - 1;
-              next = len - 1;
-            }
-          }
-        }
-      } else {
-        next = openRange<AMINO>(ix, qb.letters + off, len, sp, ep);
-      }
+      if (staged) next = openRange<AMINO, true>(ix, letters + (off - aligned0), len, sp, ep);
+      else next = openRange<AMINO, false>(ix, qb.letters + off, len, sp, ep);
       sm.sp[t] = sp;
       sm.ep[t] = ep;
       sm.start[t] = (uint32_t)(off - aligned0);
-      sm.next[t] = (uint32_t)min(next, (uint64_t)0xFFFFFFFFu);
+      sm.next[t] = next;
     }
     __syncthreads();
 
@@ -218,11 +206,10 @@ __global__ void __launch_bounds__(256)
       uint64_t sp = sm.sp[t], ep = sm.ep[t];
       uint64_t next = sm.next[t];
       const uint32_t start = sm.start[t];
-      if (!staged || next == 0xFFFFFFFFu) {  // long queries: recompute extent from global
+      if (!staged) {  // tile too long for the staging window: letters straight from global memory
         uint64_t off, len;
         queryExtent(qb, q0 + t, off, len);
         const uint8_t *s = qb.letters + off;
-        if (next == 0xFFFFFFFFu) next = openRange<AMINO>(ix, s, len, sp, ep);
         while (next > 0 && sp <= ep) {
           const uint32_t letter = letterIndex<AMINO>(__ldg(s + next - 1));
           if (letter > CARD) {
@@ -380,6 +367,54 @@ __global__ void __launch_bounds__(256, 8)
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Derived structures that trade HBM for fewer dependent DRAM round trips (built once per context, on request).
+//
+// extendSeedTable: level j -> level j+1 of the seed table.  Entry x of level j holds the range the reference has
+// after the last j letters x of a query (src/AwFmParallelSearch.c:222-311: table entry for the last k letters, then
+// one LF step per further letter while the range is valid — an invalid range is kept as it is).  Prepending letter
+// c gives entry c*CARD^j + x of level j+1 = valid(entry) ? step(c, entry) : entry.  Exactly the reference's values,
+// including the stored invalid pairs.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool AMINO, bool SRC_WIDE, bool DST_WIDE>
+__global__ void __launch_bounds__(256)
+    extendSeedTable(const __grid_constant__ DevIndex ix, const void *__restrict__ src, uint64_t numSrc,
+                    void *__restrict__ dst) {
+  constexpr uint64_t CARD = AMINO ? 20 : 4;
+  const uint64_t total = numSrc * CARD;
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t x = o % numSrc;
+    const uint32_t c = (uint32_t)(o / numSrc);
+    uint64_t sp, ep;
+    if (SRC_WIDE) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4 *>(src) + x);
+      sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
+      ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
+    } else {
+      const uint2 r = __ldg(reinterpret_cast<const uint2 *>(src) + x);
+      sp = r.x;
+      ep = r.y;
+    }
+    if (sp <= ep) lfStep<1, AMINO>(ix, sp, ep, c, 0u, 0u);
+    if (DST_WIDE)
+      reinterpret_cast<uint4 *>(dst)[o] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
+    else
+      reinterpret_cast<uint2 *>(dst)[o] = make_uint2((uint32_t)sp, (uint32_t)ep);
+  }
+}
+
+// densify the sampled SA: out[j] = SA[j * newRatio] for j in [first, first + count), by the locate walk itself
+// (src/AwFmParallelSearch.c:333-361).  `work` holds j*newRatio on entry (iota kernel) and text positions on exit.
+__global__ void saIota(uint64_t *__restrict__ work, uint64_t first, uint64_t count, uint64_t newRatio) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    work[i] = (first + i) * newRatio;
+}
+template <typename T>
+__global__ void saNarrow(const uint64_t *__restrict__ work, uint64_t count, T *__restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = (T)work[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -52,6 +52,20 @@ class GpuIndex:
         capi.check(self.lib.awfm_gpu_ctx_create_from_device(C.byref(self._ctx), device, C.byref(view)))
         return self
 
+    @classmethod
+    def from_file(cls, path, device=0, want_suffix_array=True):
+        """Index loaded from an `.awfmi` file straight into HBM (awfm_gpu_ctx_create_from_file); `.info` holds the
+        header fields."""
+        self = cls.__new__(cls)
+        self.lib = capi.load()
+        self.arrays = None
+        self.device = device
+        self._ctx = C.c_void_p()
+        self.info = abi.awfm_file_info()
+        capi.check(self.lib.awfm_gpu_ctx_create_from_file(C.byref(self._ctx), device, str(path).encode(),
+                                                          int(want_suffix_array), C.byref(self.info)))
+        return self
+
     @property
     def ctx(self):
         return self._ctx
@@ -86,6 +100,18 @@ class GpuIndex:
     def map_positions_device(self, d_positions, n, d_sequence_index, d_local_position, stream=0):
         capi.check(self.lib.awfm_gpu_map_positions_device(self._ctx, d_positions, n, d_sequence_index, d_local_position,
                                                           stream or None))
+
+    def extend_seed_table(self, depth):
+        """Derive a deeper seed table on the device (0 or <= seed k drops it); returns the build time in ms."""
+        ms = C.c_double()
+        capi.check(self.lib.awfm_gpu_ctx_extend_seed_table(self._ctx, int(depth), C.byref(ms)))
+        return ms.value
+
+    def densify_suffix_array(self, new_ratio):
+        """Derive SA samples at every new_ratio-th BWT position (0 drops them); returns the build time in ms."""
+        ms = C.c_double()
+        capi.check(self.lib.awfm_gpu_ctx_densify_suffix_array(self._ctx, int(new_ratio), C.byref(ms)))
+        return ms.value
 
     def set_tuning(self, **kv):
         for k, v in kv.items():

@@ -30,19 +30,21 @@ def gather_counts(local_counts, num_queries, dst=0, group=None):
 
 
 def gather_hits(local_hit_offsets, local_positions, num_queries, dst=0, group=None):
-    """Per-rank CSR (hit_offsets[shard+1], positions[hits]) -> the global CSR on rank `dst`.
-    Hit totals are exchanged first (all_gather of one int64), then the variable-length segments are gathered padded."""
+    """Per-rank CSR (hit_offsets[shard+1], positions[hits] or payload[hits, k]) -> the global CSR on rank `dst`.
+    Hit totals are exchanged first (all_gather of one int64), then the variable-length segments are gathered padded.
+    A 2-D payload (e.g. position, contig, offset per hit) travels in ONE gather."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = local_positions.device
-    total = torch.tensor([local_positions.numel()], dtype=torch.int64, device=dev)
+    hits = local_positions.shape[0]
+    total = torch.tensor([hits], dtype=torch.int64, device=dev)
     totals = [torch.zeros_like(total) for _ in range(world)]
     dist.all_gather(totals, total, group=group)
-    totals = [int(t.item()) for t in totals]
+    totals = [int(t) for t in torch.cat(totals).tolist()]
     counts = (local_hit_offsets[1:] - local_hit_offsets[:-1]).to(torch.int64)
     all_counts = gather_counts(counts, num_queries, dst, group)
     width = max(max(totals), 1)
-    padded = torch.zeros(width, dtype=local_positions.dtype, device=dev)
-    padded[: local_positions.numel()] = local_positions
+    padded = torch.zeros((width,) + tuple(local_positions.shape[1:]), dtype=local_positions.dtype, device=dev)
+    padded[:hits] = local_positions
     bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
     dist.gather(padded, bufs, dst=dst, group=group)
     if rank != dst:

@@ -92,14 +92,43 @@ int awfm_gpu_device_count(void);
 int awfm_gpu_ctx_create(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view);
 /* Same, but every array pointer in `view` is a DEVICE pointer on `device` (index built or loaded on the GPU). */
 int awfm_gpu_ctx_create_from_device(awfm_gpu_ctx **ctx, int device, const awfm_index_view *view);
+/* Index straight from an unchanged `.awfmi` version-8 file (replaces awFmReadIndexFromFile,
+ * src/AwFmFile.c:195-449, + the upload): the file is mapped and its sections go from the page cache to the device,
+ * no host copy of the index is built.  wantSuffixArray = 0 gives a count-only context (the reference's
+ * keepSuffixArrayInMemory = false would pread per hit instead, src/AwFmFile.c:484-522).  A FastaVector record table
+ * in the file is installed for awfm_gpu_map_positions_*.  Format errors are AWFM_GPU_ERR_ARG and are detected before
+ * any CUDA call.  `info` (may be NULL) receives the header fields. */
+typedef struct awfm_file_info {
+  uint64_t bwtLength, numSequences, suffixArrayByteLength;
+  uint32_t versionNumber, featureFlags;
+  uint8_t suffixArrayCompressionRatio, kmerLengthInSeedTable, alphabetType, storeOriginalSequence;
+} awfm_file_info;
+int awfm_gpu_ctx_create_from_file(awfm_gpu_ctx **ctx, int device, const char *path, int wantSuffixArray,
+                                  awfm_file_info *info);
 void awfm_gpu_ctx_destroy(awfm_gpu_ctx *ctx);
 uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *ctx);
 int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
 /* Tuning knobs (kernel variant selection for measurement; defaults are the shipped configuration).
  * keys: "count_lpq" (lanes per query: 1,2,4,8; clamped to what the alphabet's line layout supports), "locate_lpq",
  * "count_variant" (0 group-per-query from global memory, 1 CTA tiles staged in shared memory), "locate_variant"
- * (0 group-per-hit, 1 lane-per-hit with refill), "chunk_queries", "blocks_per_sm". */
+ * (0 group-per-hit, 1 group-per-hit with refill), "chunk_queries", "blocks_per_sm", "use_deep_seed_table" (0/1: A/B
+ * switch for a table already derived with awfm_gpu_ctx_extend_seed_table). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
+
+/* ---- derived structures: spend HBM (180 GB per B200) to remove dependent DRAM round trips.  Both are computed on
+ *      the device from the unchanged index with the search kernels' own primitives, hold exactly the values the
+ *      reference would compute at query time, and are optional (default: absent). ----
+ * extend_seed_table: a deeper k-mer seed table.  Entry x of depth d = the range the reference holds after the last
+ *   d letters x of a query: kmerSeedTable entry of the last k letters (src/AwFmKmerTable.c:21-51) pushed through
+ *   d-k LF steps with the reference's stop-when-invalid rule (src/AwFmParallelSearch.c:279-311).  A query whose last
+ *   d letters are all searchable letters then opens with ONE table read instead of 1 + (d-k) step pairs; any other
+ *   query takes the normal path.  Size |alphabet|^d x 8 B (16 B when bwtLength > 2^32).  depth <= seedK drops it.
+ * densify_suffix_array: SA samples at every newRatio-th BWT position (newRatio < the index's ratio), obtained by
+ *   running the reference's own backtrace walk (src/AwFmParallelSearch.c:333-361) for each of them once.  Locate
+ *   then walks newRatio-1 steps per hit on average instead of ratio-1 (none at newRatio = 1).  Size
+ *   ceil(bwtLength/newRatio) x 4 B (8 B when bwtLength > 2^32).  newRatio = 0 or >= the index's ratio drops it. */
+int awfm_gpu_ctx_extend_seed_table(awfm_gpu_ctx *ctx, uint32_t depth, double *buildMs /* may be NULL */);
+int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *ctx, uint32_t newRatio, double *buildMs /* may be NULL */);
 
 /* ---- packed batch, HOST buffers (H2D, kernels, D2H inside the call) ---- */
 int awfm_gpu_count_host(awfm_gpu_ctx *ctx, const uint8_t *letters, const uint64_t *offsets, uint32_t fixedLen,

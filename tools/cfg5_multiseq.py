@@ -111,10 +111,8 @@ def main():
     def step_fn():
         search()
         if world > 1:  # rank 0 ends up with the global CSR of (position, contig, offset)
-            h, p = sharding.gather_hits(d_hit, d_pos, n * world)
-            _, s_ = sharding.gather_hits(d_hit, d_seq, n * world)
-            _, l_ = sharding.gather_hits(d_hit, d_loc, n * world)
-            gathered.update(hit=h, pos=p, seq=s_, loc=l_)
+            h, p = sharding.gather_hits(d_hit, torch.stack([d_pos, d_seq, d_loc], dim=1), n * world)
+            gathered.update(hit=h, payload=p)
 
     for _ in range(a.warmup):
         step_fn()
@@ -161,7 +159,7 @@ def main():
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if rank == 0:  # the gathered CSR equals rank 0's own shard at its head
-            same = torch.equal(gathered["pos"][:hits], d_pos) and torch.equal(gathered["seq"][:hits], d_seq)
+            same = torch.equal(gathered["payload"][:hits], torch.stack([d_pos, d_seq, d_loc], dim=1))
             ok[0] = min(int(ok.item()), int(same))
     total_hits = torch.tensor([hits], dtype=torch.int64, device=dev)
     if world > 1:

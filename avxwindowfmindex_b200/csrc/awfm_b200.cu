@@ -80,7 +80,7 @@ struct PipeSlot {  // one in-flight chunk of the search-list engine
 struct awfm_gpu_ctx {
   int device = 0, numSMs = 0;
   DevIndex ix{};
-  void *dLines = nullptr, *dXBase = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
+  void *dLines = nullptr, *dXRel16 = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
   uint64_t *dSequenceEnds = nullptr;
   void *dDeepSeed = nullptr, *dDenseSa = nullptr;  // derived structures (extend_seed_table / densify_suffix_array)
   uint64_t deepSeedBytes = 0, denseSaBytes = 0;
@@ -152,35 +152,37 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   if (fromDevice) CUB_(cudaMemcpy(prefix, v->prefixSums, numPrefix * 8, cudaMemcpyDeviceToHost));
   else memcpy(prefix, v->prefixSums, numPrefix * 8);
 
-  // blocks -> lines.  The raw copy is staged in slabs so peak extra memory stays small next to a 180 GB HBM.
-  const uint64_t lineBytes = amino ? 512u : 128u;  // per 256 positions: 4 amino quarter-lines / 2 nucleotide half-lines
+  // blocks -> sectors / quarter-lines.  The raw copy is staged in slabs so peak extra memory stays small.
+  const uint64_t lineBytes = amino ? 512u : 128u;  // per 256 positions: 4 amino quarter-lines / 4 nucleotide sectors
   CUB_(cudaMalloc(&c->dLines, v->numBlocks * lineBytes));
   c->deviceBytes += v->numBlocks * lineBytes;
-  uint64_t *dSuperCounts = nullptr;
-  if (!amino) {
-    CUB_(cudaMalloc(&c->dXBase, v->numBlocks * 2 * 4));
-    c->deviceBytes += v->numBlocks * 8;
-  }
-  {
-    // superblock tables: counts at the first block of every 2^31-position superblock (the searchable letters,
-    // row padded to 8 / 24 entries); superC folds the prefix sums C[c] in
-    const int numLetters = amino ? 21 : 5, stride = amino ? kAminoSuperStride : kNucSuperStride;
-    const uint32_t baseOffset = amino ? 160u : 96u;
+  uint64_t *dSuperCounts = nullptr, *dPrefix = nullptr;
+  if (amino) {
+    // counts at the first block of every 2^31-position superblock; superC folds the prefix sums C[c] in
     const uint64_t numSuper = ((v->bwtLength - 1) >> kSuperShift) + 1;
-    std::vector<uint64_t> superCounts(numSuper * stride, 0), superC(numSuper * stride, 0);
+    std::vector<uint64_t> superCounts(numSuper * kAminoSuperStride, 0), superC(numSuper * kAminoSuperStride, 0);
     for (uint64_t s = 0; s < numSuper; s++) {
-      const uint8_t *src = (const uint8_t *)v->blocks + ((s << kSuperShift) >> 8) * rawBlockBytes + baseOffset;
-      if (fromDevice) CUB_(cudaMemcpy(&superCounts[s * stride], src, numLetters * 8, cudaMemcpyDeviceToHost));
-      else memcpy(&superCounts[s * stride], src, numLetters * 8);
-      for (int l = 0; l < numLetters; l++) superC[s * stride + l] = prefix[l] + superCounts[s * stride + l];
+      const uint8_t *src = (const uint8_t *)v->blocks + ((s << kSuperShift) >> 8) * rawBlockBytes + 160;
+      if (fromDevice) CUB_(cudaMemcpy(&superCounts[s * kAminoSuperStride], src, 21 * 8, cudaMemcpyDeviceToHost));
+      else memcpy(&superCounts[s * kAminoSuperStride], src, 21 * 8);
+      for (int l = 0; l < 21; l++) superC[s * kAminoSuperStride + l] = prefix[l] + superCounts[s * kAminoSuperStride + l];
     }
-    CUB_(cudaMalloc(&dSuperCounts, numSuper * stride * 8));
-    CUB_(cudaMemcpy(dSuperCounts, superCounts.data(), numSuper * stride * 8, cudaMemcpyHostToDevice));
-    CUB_(cudaMalloc(&c->dSuperC, numSuper * stride * 8));
-    CUB_(cudaMemcpy(c->dSuperC, superC.data(), numSuper * stride * 8, cudaMemcpyHostToDevice));
+    CUB_(cudaMalloc(&dSuperCounts, numSuper * kAminoSuperStride * 8));
+    CUB_(cudaMemcpy(dSuperCounts, superCounts.data(), numSuper * kAminoSuperStride * 8, cudaMemcpyHostToDevice));
+    CUB_(cudaMalloc(&c->dSuperC, numSuper * kAminoSuperStride * 8));
+    CUB_(cudaMemcpy(c->dSuperC, superC.data(), numSuper * kAminoSuperStride * 8, cudaMemcpyHostToDevice));
+  } else {
+    // one row per 2^16 positions, filled on the device from the slab that holds the superblock's first block
+    const uint64_t numSuper = ((v->numBlocks * 256 - 1) >> kSectorSuperShift) + 1;
+    CUB_(cudaMalloc(&c->dXRel16, v->numBlocks * 4 * 2));
+    CUB_(cudaMalloc(&c->dSuperC, numSuper * kSectorSuperStride * 8));
+    CUB_(cudaMalloc(&dSuperCounts, numSuper * kSectorSuperStride * 8));
+    CUB_(cudaMalloc(&dPrefix, 8 * 8));
+    CUB_(cudaMemcpy(dPrefix, prefix, 6 * 8, cudaMemcpyHostToDevice));
+    c->deviceBytes += v->numBlocks * 8 + numSuper * kSectorSuperStride * 8;
   }
   {
-    const uint64_t slabBlocks = std::min<uint64_t>(v->numBlocks, 1u << 20);  // <= 352 MB staging
+    const uint64_t slabBlocks = std::min<uint64_t>(v->numBlocks, 1u << 20);  // <= 352 MB staging; multiple of 256
     uint8_t *dRaw = nullptr;
     CUB_(cudaMalloc(&dRaw, slabBlocks * rawBlockBytes));
     for (uint64_t b0 = 0; b0 < v->numBlocks; b0 += slabBlocks) {
@@ -188,18 +190,26 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
       cudaError_t e = cudaMemcpy(dRaw, (const uint8_t *)v->blocks + b0 * rawBlockBytes, nb * rawBlockBytes, kind);
       if (e == cudaSuccess) {
         const unsigned grid = (unsigned)((nb + 255) / 256);
-        if (amino) relayoutAmino<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines);
-        else relayoutNucleotide<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines, (uint32_t *)c->dXBase);
+        if (amino) {
+          relayoutAmino<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines);
+        } else {
+          const unsigned superGrid = (unsigned)(((nb + 255) / 256 + 255) / 256);
+          sectorSuperRows<<<superGrid, 256>>>(dRaw, nb, b0, dPrefix, dSuperCounts, (uint64_t *)c->dSuperC);
+          relayoutNucleotideSectors<<<grid, 256>>>(dRaw, nb, b0, dSuperCounts, (uint4 *)c->dLines,
+                                                   (uint16_t *)c->dXRel16);
+        }
         e = cudaDeviceSynchronize();
       }
       if (e != cudaSuccess) {
         cudaFree(dRaw);
         cudaFree(dSuperCounts);
+        cudaFree(dPrefix);
         CUB_(e);
       }
     }
     cudaFree(dRaw);
     cudaFree(dSuperCounts);
+    cudaFree(dPrefix);
   }
   // seed table
   const uint64_t numSeeds = numSeedsOf(v->alphabet, v->seedK);
@@ -217,7 +227,7 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   }
   DevIndex &ix = c->ix;
   ix.lines = (const uint4 *)c->dLines;
-  ix.xRel = (const uint32_t *)c->dXBase;
+  ix.xRel16 = (const uint16_t *)c->dXRel16;
   ix.superC = (const uint64_t *)c->dSuperC;
   ix.seedTable = (const uint4 *)c->dSeed;
   ix.sa = (const uint64_t *)c->dSa;
@@ -234,6 +244,10 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   }
   ix.seedK = v->seedK;
   ix.amino = amino;
+  // defaults measured on B200 (profiles/r01_locate_sweep*.jsonl): amino reads whole quarter-lines with 4-lane groups;
+  // nucleotide LF steps use 2-lane groups (one sector per lane), a nucleotide walk is always one thread
+  c->countLpq = amino ? 4 : 2;
+  c->locateLpq = amino ? 4 : 1;
   ix.deepSeedTable = nullptr;
   ix.deepSeedK = ix.deepSeedWide = 0;
   CUB_(cudaMalloc(&c->dWorkCounter, 64));
@@ -385,7 +399,7 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
     cudaEventDestroy(e.b);
   }
   cudaFree(c->dLines);
-  cudaFree(c->dXBase);
+  cudaFree(c->dXRel16);
   cudaFree(c->dSuperC);
   cudaFree(c->dSeed);
   cudaFree(c->dSa);
@@ -516,18 +530,23 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
   return launchWalk<LPQ, AMINO>(c, he - hb, dPos, st);
 }
 
-// nucleotide half-lines have 4 chunks (groups of 1, 2 or 4 lanes); amino quarter-lines 2 chunks (1 or 2 lanes);
-// larger requests are clamped
-#define DISPATCH_LPQ(fn, lpq, amino, ...)                                  \
+// lanes per query / per hit: amino quarter-lines are read by 1, 2 or 4 lanes; a nucleotide LF step by 1 or 2 lanes
+// (one sector each), a nucleotide walk by one thread.  Larger requests are clamped.
+#define DISPATCH_COUNT(fn, lpq, amino, ...)                                \
   ((amino) ? ((lpq) == 1   ? fn<1, true>(__VA_ARGS__)                      \
-                           : fn<2, true>(__VA_ARGS__))                     \
+              : (lpq) == 2 ? fn<2, true>(__VA_ARGS__)                      \
+                           : fn<4, true>(__VA_ARGS__))                     \
            : ((lpq) == 1   ? fn<1, false>(__VA_ARGS__)                     \
-              : (lpq) == 2 ? fn<2, false>(__VA_ARGS__)                     \
-                           : fn<4, false>(__VA_ARGS__)))
+                           : fn<2, false>(__VA_ARGS__)))
+#define DISPATCH_LOCATE(fn, lpq, amino, ...)                               \
+  ((amino) ? ((lpq) == 1   ? fn<1, true>(__VA_ARGS__)                      \
+              : (lpq) == 2 ? fn<2, true>(__VA_ARGS__)                      \
+                           : fn<4, true>(__VA_ARGS__))                     \
+           : fn<1, false>(__VA_ARGS__))
 
 static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
   if (numHits == 0) return AWFM_GPU_OK;
-  return DISPATCH_LPQ(launchWalk, c->locateLpq, c->ix.amino != 0, c, numHits, dPos, st);
+  return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, numHits, dPos, st);
 }
 
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
@@ -536,7 +555,7 @@ static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint6
   QueryBatch qb{dLetters, dOffsets, n, fixedLen};
   EventPair *ev = nextEvents(c);
   if (ev) CU(cudaEventRecord(ev->a, st));
-  int r = DISPATCH_LPQ(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
+  int r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
   if (ev) CU(cudaEventRecord(ev->b, st));
   c->stats.launches += 1;
   c->stats.queries += n;
@@ -590,7 +609,7 @@ static int locateDeviceImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, const ui
   if (he <= hb) return AWFM_GPU_OK;
   EventPair *ev = nextEvents(c);
   if (ev) CU(cudaEventRecord(ev->a, st));
-  int r = DISPATCH_LPQ(launchLocate, c->locateLpq, c->ix.amino != 0, c, (const uint4 *)dRanges, dHitOffsets, n, hb,
+  int r = DISPATCH_LOCATE(launchLocate, c->locateLpq, c->ix.amino != 0, c, (const uint4 *)dRanges, dHitOffsets, n, hb,
                        he, dPos, st);
   if (ev) CU(cudaEventRecord(ev->b, st));
   c->stats.launches += 2;

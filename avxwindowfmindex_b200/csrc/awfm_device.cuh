@@ -2,17 +2,19 @@
 //
 // HBM layout (built once at upload by relayout kernels in awfm_kernels.cuh from the unchanged reference blocks):
 //
-//  nucleotide "half-line" = 64 B, 64-B aligned, one per 128 BWT positions:
-//      4 chunks of 16 B; chunk j = { b0[j], b1[j], b2[j], rel[j] }   (32-bit words)
-//      b_i[j] = bits of letter bit-vector i for positions 128*h + 32*j .. +31 (bit t <-> position 32*j + t)
-//      rel[c] = occurrences of letter c (A,C,G,T) in BWT[0, 128*h) minus the count at the start of the enclosing
-//               2^31-position superblock (fits 32 bits); absolute 64-bit superblock counts, already summed with the
-//               prefix sum C[c], sit in a tiny table (superC) that stays in L1/L2.
-//      The ambiguity letter's relative count lives in a side array (xRel); the sentinel count is never needed.
-//    One rank = exactly ONE 64-B DRAM request: lane j of a 4-lane group issues one 128-bit load and owns all three
-//    code bits of 32 positions (no bit-gather shuffles).  Measured on B200 (profiles/r01_probe_*.json): random
-//    64-B reads sustain ~39 G requests/s, random 128-B lines only ~24 G/s, which is why the first layout of this
-//    path (128-B lines holding 256 positions + 64-bit counts) was replaced.
+//  nucleotide "sector" = 32 B, 32-B aligned, one per 64 BWT positions (0.5 B per position; a 128-B line = 256 positions):
+//      words 0-1 / 2-3 / 4-5 : bits 0 / 1 / 2 of the letter codes as 64-bit vectors (bit t <-> position 64*s + t)
+//      word 6 = count(A) | count(C) << 16,  word 7 = count(G) | count(T) << 16: occurrences in BWT[S * 2^16, 64*s)
+//               where S = s >> 10 is the enclosing 2^16-position superblock (so every count fits 16 bits);
+//      superC[S][c] = C[c] + occurrences of c before the superblock (64 B per 2^16 positions: 3 MB at 3.1 Gbp,
+//               L2-resident; the address does not depend on the sector, so the read overlaps the sector's miss);
+//      xRel16[s] = the ambiguity letter's 16-bit count (side array, touched only when a query or the BWT holds X).
+//    One rank = ONE 32-B sector read by ONE lane (two 128-bit loads of the same sector = one request), the letter
+//    selector is three 64-bit LOP3s, the count one shift/mask: no shuffles inside a rank.  A 2-lane group does an
+//    LF step (lane 0 ranks sp-1, lane 1 ranks ep, one exchange); a single thread owns a located hit's whole walk.
+//    History of this layout on B200 (profiles/): 128-B lines per 256 positions with 64-bit counts (3.9 G queries/s,
+//    instruction-bound) -> 64-B half-lines per 128 positions with 32-bit counts read by 2-4 lanes (5.6 G) -> sectors
+//    (6.4 G; locate 2.6 -> 4.6 G hits/s because a walk needs one lane, so 2048 walks are in flight per SM).
 //    Reference layout: struct AwFmNucleotideBlock, 160 B per 256 positions, 32-B aligned (src/AwFmIndex.h:61-65).
 //
 //  amino "quarter-line" = 128 B, 128-B aligned, one per 64 BWT positions (32 words):
@@ -32,17 +34,20 @@
 
 namespace awfm {
 
-constexpr int kNucHalfU4 = 4;     // uint4 per nucleotide half-line (128 positions)
 constexpr int kAminoLineU4 = 8;   // uint4 per amino quarter-line (64 positions)
 constexpr int kAminoRelWord = 11;  // first relative-count word of a quarter-line
-constexpr int kAminoSuperStride = 24, kNucSuperStride = 8;  // u64 per superblock row of superC
-constexpr int kSuperShift = 31;   // nucleotide superblock = 2^31 positions
+constexpr int kAminoSuperStride = 24;  // u64 per row of the amino superC
+constexpr int kSuperShift = 31;        // amino: superblock of the 32-bit relative counts = 2^31 positions
+constexpr int kSectorU4 = 2;           // uint4 per nucleotide sector (64 positions)
+constexpr int kSectorSuperShift = 16;  // nucleotide: superblock of the 16-bit sector counts = 2^16 positions
+constexpr int kSectorSuperStride = 8;  // u64 per row of the nucleotide superC
 constexpr uint32_t kNucSentinel = 5, kAminoSentinel = 21;
 
 struct DevIndex {
-  const uint4 *lines;        // nucleotide: half-lines; amino: quarter-lines
-  const uint32_t *xRel;      // nucleotide only: relative count of the ambiguity letter per half-line
-  const uint64_t *superC;    // [superblock][8 | 24] = C[c] + count of c before the superblock (c = 0..4 | 0..20)
+  const uint4 *lines;        // nucleotide: sectors; amino: quarter-lines
+  const uint16_t *xRel16;    // nucleotide only: ambiguity-letter count per sector
+  const uint64_t *superC;    // [superblock][8 | 24] = C[c] + count of c before the superblock (c = 0..4 | 0..20);
+                             // superblock = 2^16 positions (nucleotide) / 2^31 (amino)
   const uint4 *seedTable;    // {startLo, startHi, endLo, endHi}
   const void *deepSeedTable; // derived at upload time (awfm_gpu_ctx_extend_seed_table), or nullptr: the range the
                              // reference holds after the last deepSeedK letters; uint2 {start, end} when
@@ -164,40 +169,72 @@ __device__ __forceinline__ Selector makeSelector(uint32_t letter) {
 }
 
 // ================================================================================================ nucleotide
-// LPQ lanes (1, 2 or 4) cooperate on one half-line; lane `sub` holds chunks sub, sub+LPQ, ...
-template <int LPQ>
-struct NucLoad {
-  uint4 v[4 / LPQ];
+struct NucSector {
+  uint4 v0, v1;  // v0 = {b0.lo, b0.hi, b1.lo, b1.hi}, v1 = {b2.lo, b2.hi, A|C<<16, G|T<<16}
 };
-template <int LPQ>
-__device__ __forceinline__ NucLoad<LPQ> nucIssue(const DevIndex &ix, uint64_t half, unsigned sub) {
-  NucLoad<LPQ> l;
-  const uint4 *line = ix.lines + half * kNucHalfU4;
-#pragma unroll
-  for (int i = 0; i < 4 / LPQ; i++) l.v[i] = __ldg(line + sub + LPQ * i);
-  return l;
+__device__ __forceinline__ NucSector sectorIssue(const DevIndex &ix, uint64_t p) {
+  const uint4 *s = ix.lines + (p >> 6) * kSectorU4;
+  NucSector x;
+  x.v0 = __ldg(s);
+  x.v1 = __ldg(s + 1);
+  return x;
 }
-// this lane's share of popcount(select(letter) & positions 0..local)
-template <int LPQ>
-__device__ __forceinline__ uint32_t nucPop(const NucLoad<LPQ> &l, const Selector &s, uint32_t local, unsigned sub) {
-  uint32_t acc = 0;
-#pragma unroll
-  for (int i = 0; i < 4 / LPQ; i++) {
-    const uint4 v = l.v[i];
-    const uint32_t sel = ((v.x ^ s.flip[0]) | s.dontcare[0]) & ((v.y ^ s.flip[1]) | s.dontcare[1]) &
-                         ((v.z ^ s.flip[2]) | s.dontcare[2]);
-    acc += __popc(sel & inclusiveMask(local, sub + LPQ * i));
-  }
-  return acc;
+// popcount(select(letter) & positions 0..local inclusive), local in [0, 64)
+__device__ __forceinline__ uint32_t sectorPop(const NucSector &x, uint32_t letter, uint32_t local) {
+  const uint32_t cc = nucCodeCare(letter), code = cc & 0xFu, care = cc >> 4;
+  const uint64_t b0 = (uint64_t)x.v0.x | ((uint64_t)x.v0.y << 32), b1 = (uint64_t)x.v0.z | ((uint64_t)x.v0.w << 32),
+                 b2 = (uint64_t)x.v1.x | ((uint64_t)x.v1.y << 32);
+  const uint64_t f0 = (uint64_t)((code >> 0) & 1u) - 1ull, f1 = (uint64_t)((code >> 1) & 1u) - 1ull,
+                 f2 = (uint64_t)((code >> 2) & 1u) - 1ull;
+  const uint64_t d0 = (uint64_t)((care >> 0) & 1u) - 1ull, d1 = (uint64_t)((care >> 1) & 1u) - 1ull,
+                 d2 = (uint64_t)((care >> 2) & 1u) - 1ull;
+  const uint64_t sel = ((b0 ^ f0) | d0) & ((b1 ^ f1) | d1) & ((b2 ^ f2) | d2);
+  const uint64_t mask = (2ull << local) - 1ull;  // local == 63 -> all ones
+  return (uint32_t)__popcll(sel & mask);
 }
-// relative count word of `letter` (0..3): chunk `letter` of the half-line, fetched from the lane that loaded it
-template <int LPQ>
-__device__ __forceinline__ uint32_t nucRel(const NucLoad<LPQ> &l, uint32_t letter, unsigned sub, unsigned mask) {
-  uint32_t w = 0;
-#pragma unroll
-  for (int i = 0; i < 4 / LPQ; i++) w = (sub + LPQ * i == letter) ? l.v[i].w : w;
-  if (LPQ > 1) w = __shfl_sync(mask, w, groupBaseLane<LPQ>() + (letter % LPQ));
-  return w;
+// 16-bit count of letter 0..3 at the sector start, relative to its 2^16-position superblock
+__device__ __forceinline__ uint32_t sectorCount(const NucSector &x, uint32_t letter) {
+  return (((letter & 2u) ? x.v1.w : x.v1.z) >> ((letter & 1u) * 16u)) & 0xFFFFu;
+}
+// Occ(letter, p) + C[letter] for letter 0..4
+__device__ __forceinline__ uint64_t sectorRank(const DevIndex &ix, const NucSector &x, uint64_t super, uint32_t letter,
+                                               uint64_t p) {
+  const uint32_t rel = (letter == 4u) ? (uint32_t)__ldg(ix.xRel16 + (p >> 6)) : sectorCount(x, letter);
+  return super + rel + sectorPop(x, letter, (uint32_t)p & 63u);
+}
+// one LF step owned by one thread (src/AwFmSearch.c:42-103)
+__device__ __forceinline__ void lfStepSector(const DevIndex &ix, uint64_t &sp, uint64_t &ep, uint32_t letter) {
+  const uint64_t pa = sp - 1, pb = ep;
+  const NucSector a = sectorIssue(ix, pa), b = sectorIssue(ix, pb);
+  const uint64_t ca = __ldg(ix.superC + (pa >> kSectorSuperShift) * kSectorSuperStride + letter);
+  const uint64_t cb = __ldg(ix.superC + (pb >> kSectorSuperShift) * kSectorSuperStride + letter);
+  sp = sectorRank(ix, a, ca, letter, pa);
+  ep = sectorRank(ix, b, cb, letter, pb) - 1;
+}
+// one LF step by a 2-lane group: lane 0 ranks sp-1, lane 1 ranks ep, one exchange
+__device__ __forceinline__ void lfStepSectorPair(const DevIndex &ix, uint64_t &sp, uint64_t &ep, uint32_t letter,
+                                                 unsigned sub, unsigned mask) {
+  const uint64_t p = sub == 0 ? sp - 1 : ep;
+  const NucSector x = sectorIssue(ix, p);
+  const uint64_t c = __ldg(ix.superC + (p >> kSectorSuperShift) * kSectorSuperStride + letter);
+  const uint64_t mine = sectorRank(ix, x, c, letter, p);
+  const uint64_t other = __shfl_xor_sync(mask, mine, 1);
+  sp = sub == 0 ? mine : other;
+  ep = (sub == 0 ? other : mine) - 1;
+}
+// one backtrace step owned by one thread (src/AwFmSearch.c:369-397)
+__device__ __forceinline__ uint64_t backtraceStepSector(const DevIndex &ix, uint64_t p) {
+  const uint64_t *row = ix.superC + (p >> kSectorSuperShift) * kSectorSuperStride;
+  const NucSector x = sectorIssue(ix, p);
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(row));      // the row entry depends on the letter being read:
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 4));  // have both of its sectors on the way meanwhile
+  const uint32_t local = (uint32_t)p & 63u, bit = local & 31u;
+  const bool hi = local >= 32u;
+  const uint32_t w0 = hi ? x.v0.y : x.v0.x, w1 = hi ? x.v0.w : x.v0.z, w2 = hi ? x.v1.y : x.v1.x;
+  const uint32_t code = ((w0 >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
+  const uint32_t letter = nucCodeToLetter(code);
+  if (letter == kNucSentinel) return 0;
+  return sectorRank(ix, x, __ldg(row + letter), letter, p) - 1;
 }
 
 // ================================================================================================ amino
@@ -235,18 +272,68 @@ __device__ __forceinline__ uint32_t aminoPop(const AminoLoad<LPQ> &l, const Sele
   return acc;
 }
 
+// ---- 4-lane amino groups: the whole quarter-line in ONE pair of instructions (lane j holds uint4 j and j+4; each
+// instruction covers two adjacent sectors of 8 lines per warp, the request shape that sustains the full random-line
+// rate in profiles/r01_gather_shapes_ncu.txt).  Lanes 0/1 own the low/high 32 positions, lane 2 also holds b4 and
+// count 0, lanes 3,0,1,2,3 (second load) the other counts.
+struct AminoLine4 {
+  uint4 a, b;
+};
+__device__ __forceinline__ AminoLine4 aminoIssue4(const uint4 *line, unsigned sub) {
+  AminoLine4 l;
+  l.a = __ldg(line + sub);
+  l.b = __ldg(line + sub + 4);
+  return l;
+}
+// b4 word of this lane's 32 positions (meaningful in lanes 0 and 1 of the group)
+__device__ __forceinline__ uint32_t aminoB4Of(const AminoLine4 &l, unsigned sub, unsigned mask) {
+  const unsigned src = groupBaseLane<4>() + 2;
+  const uint32_t lo = __shfl_sync(mask, l.a.x, src), hi = __shfl_sync(mask, l.a.y, src);
+  return sub == 0 ? lo : hi;
+}
+__device__ __forceinline__ uint32_t aminoPop4(const AminoLine4 &l, uint32_t b4, const Selector &s, uint32_t local,
+                                              unsigned sub) {
+  const uint4 v = l.a;
+  const uint32_t sel = ((v.x ^ s.flip[0]) | s.dontcare[0]) & ((v.y ^ s.flip[1]) | s.dontcare[1]) &
+                       ((v.z ^ s.flip[2]) | s.dontcare[2]) & ((v.w ^ s.flip[3]) | s.dontcare[3]) &
+                       ((b4 ^ s.flip[4]) | s.dontcare[4]);
+  return sub < 2 ? __popc(sel & inclusiveMask(local, sub)) : 0u;
+}
+// relative count word of `letter`: word 11 + letter of the line = uint4 (w >> 2), component (w & 3)
+__device__ __forceinline__ uint32_t aminoRel4(const AminoLine4 &l, uint32_t letter, unsigned mask) {
+  const uint32_t w = kAminoRelWord + letter, u = w >> 2, comp = w & 3u;
+  const uint4 v = (u >> 2) ? l.b : l.a;
+  const uint32_t mine = comp == 0 ? v.x : comp == 1 ? v.y : comp == 2 ? v.z : v.w;
+  return __shfl_sync(mask, mine, groupBaseLane<4>() + (u & 3u));
+}
+
 // ================================================================================================ LF step
 // One LF-mapping step (src/AwFmSearch.c:42-159): sp' = C[c] + Occ(c, sp-1), ep' = C[c] + Occ(c, ep) - 1.
 // Both blocks are requested before either is consumed (two independent misses in flight per group); the two
 // partial popcounts travel through the group reduction packed in one 32-bit register.
-// Nucleotide groups are 1, 2 or 4 lanes (half-line = 4 chunks); amino groups 1 or 2 lanes (quarter-line = 2 chunks).
+// Nucleotide: one thread (both ranks) or a 2-lane group (one sector per lane); amino groups are 1 or 2 lanes
+// (quarter-line = 2 chunks of 32 positions) or 4 lanes (whole line in registers, see AminoLine4).
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_t &ep, uint32_t letter,
                                        unsigned sub, unsigned mask) {
-  const uint64_t pa = sp - 1, pb = ep;
-  const Selector s = makeSelector<AMINO>(letter);
-  if constexpr (AMINO) {
-    static_assert(!AMINO || LPQ <= 2, "amino quarter-lines have 2 chunks");
+  [[maybe_unused]] const uint64_t pa = sp - 1, pb = ep;
+  [[maybe_unused]] Selector s;
+  if constexpr (AMINO) s = makeSelector<true>(letter);
+  if constexpr (AMINO && LPQ == 4) {
+    const uint4 *lineA = ix.lines + (pa >> 6) * kAminoLineU4, *lineB = ix.lines + (pb >> 6) * kAminoLineU4;
+    const AminoLine4 la = aminoIssue4(lineA, sub);
+    const AminoLine4 lb = aminoIssue4(lineB, sub);
+    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * kAminoSuperStride + letter);
+    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * kAminoSuperStride + letter);
+    const uint32_t ra = aminoRel4(la, letter, mask), rb = aminoRel4(lb, letter, mask);
+    const uint32_t b4a = aminoB4Of(la, sub, mask), b4b = aminoB4Of(lb, sub, mask);
+    const uint32_t packed = groupSum32<4>(aminoPop4(la, b4a, s, (uint32_t)pa & 63u, sub) |
+                                              (aminoPop4(lb, b4b, s, (uint32_t)pb & 63u, sub) << 16),
+                                          mask);
+    sp = ca + ra + (packed & 0xFFFFu);
+    ep = cb + rb + (packed >> 16) - 1;
+  } else if constexpr (AMINO) {
+    static_assert(!AMINO || LPQ <= 2, "2-chunk amino groups are 1 or 2 lanes");
     const uint4 *lineA = ix.lines + (pa >> 6) * kAminoLineU4, *lineB = ix.lines + (pb >> 6) * kAminoLineU4;
     const AminoLoad<LPQ> la = aminoIssue<LPQ>(lineA, sub);
     const AminoLoad<LPQ> lb = aminoIssue<LPQ>(lineB, sub);
@@ -259,25 +346,9 @@ __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_
     sp = ca + ra + (packed & 0xFFFFu);
     ep = cb + rb + (packed >> 16) - 1;
   } else {
-    static_assert(AMINO || LPQ <= 4, "nucleotide half-lines have 4 chunks");
-    const uint64_t ha = pa >> 7, hb = pb >> 7;
-    const NucLoad<LPQ> la = nucIssue<LPQ>(ix, ha, sub);
-    const NucLoad<LPQ> lb = nucIssue<LPQ>(ix, hb, sub);
-    const uint64_t ca = __ldg(ix.superC + (pa >> kSuperShift) * kNucSuperStride + letter);
-    const uint64_t cb = __ldg(ix.superC + (pb >> kSuperShift) * kNucSuperStride + letter);
-    uint32_t ra, rb;
-    if (letter == 4u) {  // ambiguity letter: relative count from the side array
-      ra = __ldg(ix.xRel + ha);
-      rb = __ldg(ix.xRel + hb);
-    } else {
-      ra = nucRel<LPQ>(la, letter, sub, mask);
-      rb = nucRel<LPQ>(lb, letter, sub, mask);
-    }
-    const uint32_t packed = groupSum32<LPQ>(nucPop<LPQ>(la, s, (uint32_t)pa & 127u, sub) |
-                                                (nucPop<LPQ>(lb, s, (uint32_t)pb & 127u, sub) << 16),
-                                            mask);
-    sp = ca + ra + (packed & 0xFFFFu);
-    ep = cb + rb + (packed >> 16) - 1;
+    static_assert(AMINO || LPQ <= 2, "nucleotide LF steps are done by one thread or by a 2-lane group");
+    if constexpr (LPQ == 1) lfStepSector(ix, sp, ep, letter);
+    else lfStepSectorPair(ix, sp, ep, letter, sub, mask);
   }
 }
 
@@ -285,7 +356,21 @@ __device__ __forceinline__ void lfStep(const DevIndex &ix, uint64_t &sp, uint64_
 // The letter and the rank come from the SAME block load.
 template <int LPQ, bool AMINO>
 __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p, unsigned sub, unsigned mask) {
-  if constexpr (AMINO) {
+  if constexpr (AMINO && LPQ == 4) {
+    const uint32_t local = (uint32_t)p & 63u, ownerChunk = local >> 5, bit = local & 31u;
+    const uint4 *line = ix.lines + (p >> 6) * kAminoLineU4;
+    const AminoLine4 l = aminoIssue4(line, sub);
+    const uint32_t b4 = aminoB4Of(l, sub, mask);
+    const uint32_t c = ((l.a.x >> bit) & 1u) | (((l.a.y >> bit) & 1u) << 1) | (((l.a.z >> bit) & 1u) << 2) |
+                       (((l.a.w >> bit) & 1u) << 3) | (((b4 >> bit) & 1u) << 4);
+    const uint32_t code = __shfl_sync(mask, c, groupBaseLane<4>() + ownerChunk);
+    const uint32_t letter = kAminoCodeToLetter[code];
+    if (letter == kAminoSentinel) return 0;
+    const uint32_t rel = aminoRel4(l, letter, mask);
+    const Selector s = makeSelector<true>(letter);
+    const uint32_t pop = groupSum32<4>(aminoPop4(l, b4, s, local, sub), mask);
+    return __ldg(ix.superC + (p >> kSuperShift) * kAminoSuperStride + letter) + rel + pop - 1;
+  } else if constexpr (AMINO) {
     const uint32_t local = (uint32_t)p & 63u, ownerChunk = local >> 5, bit = local & 31u;
     const uint4 *line = ix.lines + (p >> 6) * kAminoLineU4;
     const AminoLoad<LPQ> l = aminoIssue<LPQ>(line, sub);
@@ -309,23 +394,8 @@ __device__ __forceinline__ uint64_t backtraceStep(const DevIndex &ix, uint64_t p
     const uint32_t pop = groupSum32<LPQ>(aminoPop<LPQ>(l, s, local, sub), mask);
     return __ldg(ix.superC + (p >> kSuperShift) * kAminoSuperStride + letter) + rel + pop - 1;
   } else {
-    const uint64_t half = p >> 7;
-    const uint32_t local = (uint32_t)p & 127u, ownerChunk = local >> 5, bit = local & 31u;
-    const NucLoad<LPQ> l = nucIssue<LPQ>(ix, half, sub);
-    uint32_t code = 0;
-#pragma unroll
-    for (int i = 0; i < 4 / LPQ; i++) {
-      const uint4 v = l.v[i];
-      const uint32_t c = ((v.x >> bit) & 1u) | (((v.y >> bit) & 1u) << 1) | (((v.z >> bit) & 1u) << 2);
-      code = (sub + LPQ * i == ownerChunk) ? c : code;
-    }
-    if (LPQ > 1) code = __shfl_sync(mask, code, groupBaseLane<LPQ>() + (ownerChunk % LPQ));
-    const uint32_t letter = nucCodeToLetter(code);
-    if (letter == kNucSentinel) return 0;
-    const Selector s = makeSelector<false>(letter);
-    const uint32_t rel = (letter == 4u) ? __ldg(ix.xRel + half) : nucRel<LPQ>(l, letter, sub, mask);
-    const uint32_t pop = groupSum32<LPQ>(nucPop<LPQ>(l, s, local, sub), mask);
-    return __ldg(ix.superC + (p >> kSuperShift) * kNucSuperStride + letter) + rel + pop - 1;
+    static_assert(AMINO || LPQ == 1, "a nucleotide walk is owned by one thread");
+    return backtraceStepSector(ix, p);
   }
 }
 

@@ -267,14 +267,20 @@ __global__ void __launch_bounds__(256)
       sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
     }
     const bool live = b > a && b > hitBegin && a < hitEnd;
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+    const uint64_t lo = max(a, hitBegin), hi = min(b, hitEnd);
+    // short ranges (the common case on sparse hits): the lane writes its own few positions, neighbours in a warp
+    // write neighbouring slots; long ranges are spread over the whole warp below
+    const bool small = live && hi - lo <= 8;
+    if (small)
+      for (uint64_t h = lo; h < hi; h++) positions[h - hitBegin] = sp + (h - a);
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, live && !small);
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const uint64_t qa = __shfl_sync(0xFFFFFFFFu, a, src), qb = __shfl_sync(0xFFFFFFFFu, b, src);
+      const uint64_t qa = __shfl_sync(0xFFFFFFFFu, a, src);
+      const uint64_t qlo = __shfl_sync(0xFFFFFFFFu, lo, src), qhi = __shfl_sync(0xFFFFFFFFu, hi, src);
       const uint64_t qsp = __shfl_sync(0xFFFFFFFFu, sp, src);
-      const uint64_t lo = max(qa, hitBegin), hi = min(qb, hitEnd);
-      for (uint64_t h = lo + lane; h < hi; h += 32) positions[h - hitBegin] = qsp + (h - qa);
+      for (uint64_t h = qlo + lane; h < qhi; h += 32) positions[h - hitBegin] = qsp + (h - qa);
     }
   }
 }
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(256)
 // that reaches a sampled position finishes its hit (sampled-SA read, add, mod, store) and takes the next hit in the
 // same round: every group keeps one independent DRAM request in flight.  Hits are handed out in 64-hit chunks from
 // a global counter (one atomic per chunk per warp), so the tail of the launch is one chunk, not the slowest thread.
-// All lanes of a group carry the same (h, p, offset).
+// All lanes of a group carry the same (h, p, offset); a nucleotide walk is owned by a single thread (LPQ = 1).
 constexpr uint32_t kLocateChunk = 64;
 template <int LPQ, bool AMINO>
 __global__ void __launch_bounds__(256, 8)
@@ -467,46 +473,57 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------
 // upload-time relayout: reference blocks -> lines (one thread per block)
 // ---------------------------------------------------------------------------------------------------------------
-// One thread per reference block (256 positions) -> two half-lines.  `superCounts[s][c]` = baseOccurrences[c] of the
-// block that starts superblock s (read from the raw blocks by the host before this kernel runs); `firstBlock` is the
-// global index of raw[0] (blocks are relaid in slabs).  Counts at the middle of the block = base + popcount of the
-// letter's selector over its first 128 positions.
-__global__ void relayoutNucleotide(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
-                                   const uint64_t *__restrict__ superCounts /* [numSuper][8] */,
-                                   uint4 *__restrict__ halves, uint32_t *__restrict__ xRel) {
+// Nucleotide: first the superblock rows (one thread per 2^16-position superblock = 256 reference blocks), then one
+// thread per reference block (256 positions) -> four 32-B sectors with 16-bit counts relative to the superblock row.
+__global__ void sectorSuperRows(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+                                const uint64_t *__restrict__ prefixSums /* device copy, 6 entries */,
+                                uint64_t *__restrict__ superCounts, uint64_t *__restrict__ superC) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // superblock inside this slab
+  const uint64_t i = j * 256;                                          // its first block inside the slab
+  if (i >= numBlocks) return;
+  const uint64_t row = (firstBlock + i) >> 8;
+  const uint64_t *base = reinterpret_cast<const uint64_t *>(raw + i * 160 + 96);
+  for (int c = 0; c < 8; c++) {
+    const uint64_t v = c < 5 ? base[c] : 0;
+    superCounts[row * kSectorSuperStride + c] = v;
+    superC[row * kSectorSuperStride + c] = c < 5 ? v + prefixSums[c] : 0;
+  }
+}
+__global__ void relayoutNucleotideSectors(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+                                          const uint64_t *__restrict__ superCounts, uint4 *__restrict__ sectors,
+                                          uint16_t *__restrict__ xRel16) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= numBlocks) return;
   const uint64_t b = firstBlock + i;
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + i * 160);  // 160 B blocks are 32-B aligned
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + i * 160);
   const uint64_t *base = reinterpret_cast<const uint64_t *>(raw + i * 160 + 96);
-  const uint64_t *super = superCounts + ((b * 256) >> kSuperShift) * 8;
+  const uint64_t *super = superCounts + (b >> 8) * kSectorSuperStride;
   uint32_t w[3][8];
 #pragma unroll
   for (int v = 0; v < 3; v++)
 #pragma unroll
     for (int j = 0; j < 8; j++) w[v][j] = src[8 * v + j];
-  uint32_t rel[2][5];
+  uint32_t rel[5];
 #pragma unroll
-  for (int c = 0; c < 5; c++) {
-    const uint32_t cc = nucCodeCare(c), code = cc & 0xFu, care = cc >> 4;
-    uint32_t firstHalf = 0;
+  for (int c = 0; c < 5; c++) rel[c] = (uint32_t)(base[c] - super[c]);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t sel = 0xFFFFFFFFu;
+  for (int q = 0; q < 4; q++) {
+    sectors[(4 * b + q) * kSectorU4] = make_uint4(w[0][2 * q], w[0][2 * q + 1], w[1][2 * q], w[1][2 * q + 1]);
+    sectors[(4 * b + q) * kSectorU4 + 1] =
+        make_uint4(w[2][2 * q], w[2][2 * q + 1], rel[0] | (rel[1] << 16), rel[2] | (rel[3] << 16));
+    xRel16[4 * b + q] = (uint16_t)rel[4];
 #pragma unroll
-      for (int v = 0; v < 3; v++)
-        if ((care >> v) & 1u) sel &= ((code >> v) & 1u) ? w[v][j] : ~w[v][j];
-      firstHalf += __popc(sel);
+    for (int c = 0; c < 5; c++) {
+      const uint32_t cc = nucCodeCare(c), code = cc & 0xFu, care = cc >> 4;
+#pragma unroll
+      for (int j = 2 * q; j < 2 * q + 2; j++) {
+        uint32_t sel = 0xFFFFFFFFu;
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          if ((care >> v) & 1u) sel &= ((code >> v) & 1u) ? w[v][j] : ~w[v][j];
+        rel[c] += __popc(sel);
+      }
     }
-    rel[0][c] = (uint32_t)(base[c] - super[c]);
-    rel[1][c] = rel[0][c] + firstHalf;
-  }
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      halves[(2 * b + h) * kNucHalfU4 + j] = make_uint4(w[0][4 * h + j], w[1][4 * h + j], w[2][4 * h + j], rel[h][j]);
-    xRel[2 * b + h] = rel[h][4];
   }
 }
 

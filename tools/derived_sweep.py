@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--depths", default="0,13,14,15,16")
     ap.add_argument("--ratios", default="0,4,2,1")
     ap.add_argument("--sample", type=int, default=500_000)
+    ap.add_argument("--count-variants", default="1")
+    ap.add_argument("--count-lpqs", default="2")
     a = ap.parse_args()
     lib = capi.load()
     dev = torch.device("cuda:0")
@@ -72,16 +74,19 @@ def main():
     o_counts, o_ranges, work = oracle.count(hs, fixed_len=L, threads=os.cpu_count())
     for depth in [int(x) for x in a.depths.split(",")]:
         build_ms = gpu.extend_seed_table(depth)
-        ms = timed(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream))
-        gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream)
-        torch.cuda.synchronize()
-        ok = (np.array_equal(d_counts[:ns].cpu().numpy().astype(np.uint32), o_counts)
-              and np.array_equal(d_ranges[:ns].cpu().numpy().astype(np.uint64), o_ranges))
-        row = {"depth": depth or a.seed_k, "derived": bool(depth), "build_ms": round(build_ms, 1),
-               "device_bytes": gpu.device_bytes(), "ms": round(ms, 3), "Gq_per_s": round(n / ms / 1e6, 3),
-               "ranges_and_counts_bit_exact_on_sample": bool(ok)}
-        out["count"].append(row)
-        print(json.dumps(row), flush=True)
+        for variant in [int(x) for x in a.count_variants.split(",")]:
+            for lpq in [int(x) for x in a.count_lpqs.split(",")]:
+                gpu.set_tuning(count_variant=variant, count_lpq=lpq)
+                ms = timed(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream))
+                gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream)
+                torch.cuda.synchronize()
+                ok = (np.array_equal(d_counts[:ns].cpu().numpy().astype(np.uint32), o_counts)
+                      and np.array_equal(d_ranges[:ns].cpu().numpy().astype(np.uint64), o_ranges))
+                row = {"depth": depth or a.seed_k, "derived": bool(depth), "count_variant": variant, "count_lpq": lpq,
+                       "build_ms": round(build_ms, 1), "device_bytes": gpu.device_bytes(), "ms": round(ms, 3),
+                       "Gq_per_s": round(n / ms / 1e6, 3), "ranges_and_counts_bit_exact_on_sample": bool(ok)}
+                out["count"].append(row)
+                print(json.dumps(row), flush=True)
     gpu.extend_seed_table(0)
     del d_q, d_counts, d_ranges
     torch.cuda.empty_cache()

@@ -33,6 +33,24 @@ def sweep(name, amino, bp, seed_k, ratio, nq, L, reps=5):
     d_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
     d_ranges = torch.zeros((nq, 2), dtype=torch.int64, device=dev)
     d_hit = torch.zeros(nq + 1, dtype=torch.int64, device=dev)
+    count_rows = []
+    first_counts = None
+    for variant in (0, 1):
+        for lpq in (1, 2, 4):
+            gpu.set_tuning(count_variant=variant, count_lpq=lpq)
+            best = 1e30
+            for _ in range(reps + 1):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                gpu.count_device(d_q.data_ptr(), None, L, nq, d_counts.data_ptr(), None, stream)
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            if first_counts is None:
+                first_counts = d_counts.clone()
+            count_rows.append({"variant": variant, "lpq": lpq, "ms": round(best, 4), "Gq_per_s": round(nq / best / 1e6, 3),
+                               "same_as_first": bool(torch.equal(d_counts, first_counts))})
+    gpu.set_tuning(count_variant=1, count_lpq=2)
     gpu.count_device(d_q.data_ptr(), None, L, nq, d_counts.data_ptr(), d_ranges.data_ptr(), stream)
     gpu.scan_ranges_device(d_ranges.data_ptr(), nq, d_hit.data_ptr(), stream)
     total = int(d_hit[-1].item())
@@ -55,7 +73,7 @@ def sweep(name, amino, bp, seed_k, ratio, nq, L, reps=5):
                 first = got
             rows.append({"variant": variant, "lpq": lpq, "ms": round(best, 4), "Ghits_per_s": round(total / best / 1e6, 3),
                          "same_as_first": bool(torch.equal(got, first))})
-    out = {"config": name, "hits": total, "queries": nq, "ratio": ratio, "rows": rows}
+    out = {"config": name, "hits": total, "queries": nq, "ratio": ratio, "count_rows": count_rows, "rows": rows}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "locate_sweep.jsonl"), "a") as f:
         f.write(json.dumps(out) + "\n")
@@ -75,6 +93,8 @@ def main():
         sweep("3.1 Gbp, 10 M 16-mers, ratio 16", False, 3_100_000_000, 12, 16, 10_000_000, 16)
     if "dense" in a.which:
         sweep("3.1 Gbp, 40 M 14-mers, ratio 8", False, 3_100_000_000, 12, 8, 40_000_000, 14)
+    if "count20" in a.which:
+        sweep("3.1 Gbp, 100 M 20-mers, ratio 8", False, 3_100_000_000, 12, 8, 100_000_000, 20)
     if "amino" in a.which:
         sweep("1 G residues, 50 M 8-mers, ratio 8", True, 1_000_000_000, 5, 8, 50_000_000, 8)
 

@@ -168,6 +168,19 @@ __device__ __forceinline__ Selector makeSelector(uint32_t letter) {
   return s;
 }
 
+// 128-bit read-only load that asks L2 to fetch only the 64-B half of the line it misses on (PTX prefetch-size hint
+// .L2::64B).  By default a missing sector brings its whole 128-B line from DRAM (profiles/r01_granularity_probe*:
+// 125 B per random read, 63 B with the hint); on this path the other half is rarely wanted.
+__device__ __forceinline__ uint4 ldgHalfLine(const uint4 *p) {
+  uint4 v;
+#ifdef AWFM_NO_L2_64B_HINT
+  v = __ldg(p);
+#else
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
+  return v;
+}
+
 // ================================================================================================ nucleotide
 struct NucSector {
   uint4 v0, v1;  // v0 = {b0.lo, b0.hi, b1.lo, b1.hi}, v1 = {b2.lo, b2.hi, A|C<<16, G|T<<16}
@@ -175,8 +188,8 @@ struct NucSector {
 __device__ __forceinline__ NucSector sectorIssue(const DevIndex &ix, uint64_t p) {
   const uint4 *s = ix.lines + (p >> 6) * kSectorU4;
   NucSector x;
-  x.v0 = __ldg(s);
-  x.v1 = __ldg(s + 1);
+  x.v0 = ldgHalfLine(s);
+  x.v1 = ldgHalfLine(s + 1);
   return x;
 }
 // popcount(select(letter) & positions 0..local inclusive), local in [0, 64)

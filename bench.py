@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — batched exact-match k-mer COUNT throughput (BASELINE.json configs[1]):
+"""bench.py — batched exact-match k-mer COUNT throughput (BASELINE.json configs[1]), plus a located-hits/s leg
+(configs[2] shape) and an opt-in derived-structures leg reported as extra objects on the same JSON line:
 3.1 Gbp synthetic nucleotide index (seed k=12, SA ratio 8), 100 M random 20-mers per GPU, query-sharded.
 
     python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU; torchrun for N>1)
@@ -48,6 +49,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="queries per CPU-baseline pass")
     ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--locate-queries", type=int, default=10_000_000, help="cfg 3 leg: random 16-mers located per GPU")
+    ap.add_argument("--locate-kmer", type=int, default=16)
+    ap.add_argument("--derived-seed-depth", type=int, default=16, help="0 = skip the derived-structures leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -312,8 +316,95 @@ def run_ours(args):
         kernel_ms.append(ka.elapsed_time(kb))
     kernel_avg = sum(kernel_ms) / len(kernel_ms)
 
-    # ---- parity on a sample + exact algorithmic bytes from the oracle (checker, not the product) ----
+    # ---- second half of BASELINE's metric: located hits/s (configs[2] shape: random 16-mers, this index's SA ratio),
+    #      device-resident, ranges -> scan -> expand -> backtrace walk -> positions; outside the timed count steps ----
     result = {}
+    nl, Ll = args.locate_queries, args.locate_kmer
+    if nl > 0:
+        d_lq = torch.empty(nl * Ll + 64, dtype=torch.uint8, device=dev)
+        capi.check(lib.awfm_gpu_synth_letters(local, d_lq.data_ptr(), nl * Ll, synth.QUERY_SEED + 3, rank * nl * Ll, 0))
+        d_lc = torch.zeros(nl, dtype=torch.int32, device=dev)
+        d_lr = torch.zeros((nl, 2), dtype=torch.int64, device=dev)
+        d_lh = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
+        gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream.cuda_stream)
+        gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream.cuda_stream)
+        hits = int(d_lh[-1].item())
+        d_lp = torch.zeros(max(hits, 1), dtype=torch.int64, device=dev)
+
+        def locate_all():
+            gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream.cuda_stream)
+            gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream.cuda_stream)
+            gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(), stream.cuda_stream)
+
+        def best_ms(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                ka.record(stream)
+                fn()
+                kb.record(stream)
+                torch.cuda.synchronize()
+                best = min(best, ka.elapsed_time(kb))
+            return best
+
+        ms_all = best_ms(locate_all)
+        ms_walk = best_ms(lambda: gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(),
+                                                    stream.cuda_stream))
+        loc = {"workload": f"{nl} random {Ll}-mers per GPU on the same index (SA ratio {args.sa_ratio}), BASELINE.json configs[2] shape",
+               "hits": hits, "locate_ms": ms_all, "located_hits_per_s": hits / ms_all * 1e3,
+               "locate_queries_per_s": nl / ms_all * 1e3, "walk_ms": ms_walk, "walk_hits_per_s": hits / ms_walk * 1e3}
+        if arrays is not None:
+            ls = min(nl, 200_000)
+            o_hit, o_pos, lwork = harness.Oracle(arrays).locate(d_lq[: ls * Ll].cpu().numpy(), fixed_len=Ll,
+                                                                 threads=os.cpu_count())
+            nh = int(o_hit[-1])
+            same = (np.array_equal(d_lh[: ls + 1].cpu().numpy().astype(np.uint64), o_hit)
+                    and np.array_equal(d_lp[:nh].cpu().numpy().astype(np.uint64), o_pos))
+            loc["parity_sample"] = {"queries": ls, "hits": nh, "bit_exact_vs_oracle": bool(same)}
+            if nh:
+                loc["backtrace_steps_per_hit"] = lwork["backtraceSteps"] / nh
+                loc["algorithmic_bytes_per_hit"] = lwork["locateBytes"] / nh
+                loc["walk_algorithmic_GBps"] = lwork["locateBytes"] / nh * hits / ms_walk / 1e6
+            if not same:
+                raise SystemExit("PARITY FAILURE: CUDA positions differ from the oracle on the bench's locate leg")
+        result["locate"] = loc
+
+        # ---- derived structures (opt-in: HBM for fewer dependent DRAM round trips), same queries, same checks ----
+        if args.derived_seed_depth > args.seed_k:
+            try:
+                derived = {}
+                build_seed_ms = gpu.extend_seed_table(args.derived_seed_depth)
+                dms = best_ms(lambda: gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None,
+                                                       stream.cuda_stream), reps=3)
+                derived["seed_table"] = {"depth": args.derived_seed_depth, "build_ms": build_seed_ms,
+                                         "count_ms": dms, "count_queries_per_s": n / dms * 1e3}
+                build_sa_ms = gpu.densify_suffix_array(1)
+                wms = best_ms(lambda: gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(),
+                                                        stream.cuda_stream))
+                derived["suffix_array"] = {"sa_ratio": 1, "build_ms": build_sa_ms, "walk_ms": wms,
+                                           "walk_hits_per_s": hits / wms * 1e3}
+                derived["device_bytes_with_both"] = gpu.device_bytes()
+                if arrays is not None:
+                    derived["suffix_array"]["bit_exact_vs_oracle"] = bool(
+                        np.array_equal(d_lp[:nh].cpu().numpy().astype(np.uint64), o_pos))
+                    derived_counts = d_counts[:1_000_000].cpu().numpy().astype(np.uint32)
+                gpu.extend_seed_table(0)
+                gpu.densify_suffix_array(0)
+                # d_counts again from the plain path (what the parity sample below checks)
+                gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
+                torch.cuda.synchronize()
+                result["derived_structures"] = derived
+            except capi.AwfmGpuError as e:  # e.g. not enough free HBM for the depth asked for
+                result["derived_structures"] = {"error": str(e)}
+                derived_counts = None
+        else:
+            derived_counts = None
+        del d_lq, d_lc, d_lr, d_lh, d_lp
+    else:
+        derived_counts = None
+
+    # ---- parity on a sample + exact algorithmic bytes from the oracle (checker, not the product) ----
     sample = min(n, 1_000_000)
     h_counts_sample = d_counts[:sample].cpu().numpy().astype(np.uint32)
     h_letters_sample = d_letters[: sample * L].cpu().numpy()
@@ -327,6 +418,11 @@ def run_ours(args):
                                    "algorithmic_bytes_per_query": bytes_per_query}
         if not parity:
             raise SystemExit("PARITY FAILURE: CUDA counts differ from the oracle on the bench workload")
+        if derived_counts is not None:
+            ok = bool(np.array_equal(derived_counts[:sample], o_counts[: len(derived_counts[:sample])]))
+            result["derived_structures"]["seed_table"]["bit_exact_vs_oracle"] = ok
+            if not ok:
+                raise SystemExit("PARITY FAILURE: counts through the derived seed table differ from the oracle")
     else:
         bytes_per_query = None
 

@@ -64,6 +64,14 @@ struct EventPair {
   cudaEvent_t a, b;
 };
 
+struct LocateScratch {  // per-stream scratch of scan + walk (two streams may not share one)
+  void *scanTemp = nullptr;
+  size_t scanTempBytes = 0;
+  uint64_t *dLengths = nullptr;
+  uint64_t lengthsCap = 0;
+  unsigned long long *dWorkCounter = nullptr;  // locateKernelRefill's chunk dispenser
+};
+
 struct PipeSlot {  // one in-flight chunk of the search-list engine
   uint8_t *hLetters = nullptr, *dLetters = nullptr;
   uint64_t lettersCap = 0, dLettersCap = 0;
@@ -75,6 +83,13 @@ struct PipeSlot {  // one in-flight chunk of the search-list engine
   cudaEvent_t done = nullptr;
   uint64_t first = 0, n = 0;
   bool busy = false;
+  // locate pipeline: hit offsets and positions of the chunk, both sides of the bus
+  LocateScratch sc;
+  uint64_t *hHit = nullptr, *dHit = nullptr, hitCap = 0;
+  uint64_t *hPos = nullptr, *dPos = nullptr, posCap = 0;
+  cudaEvent_t offsetsDone = nullptr;
+  uint64_t total = 0;
+  bool shipped = false, walked = false, big = false;
 };
 
 struct awfm_gpu_ctx {
@@ -92,16 +107,16 @@ struct awfm_gpu_ctx {
   // tuning
   int countLpq = 2, locateLpq = 2, countVariant = 1, locateVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
   int64_t chunkQueries = 1 << 18;
-  // scratch
-  void *scanTemp = nullptr;
-  size_t scanTempBytes = 0;
-  uint64_t *dLengths = nullptr;
-  uint64_t lengthsCap = 0;
-  unsigned long long *dWorkCounter = nullptr;  // locateKernelRefill's chunk dispenser
+  int64_t locateChunkQueries = 1 << 18;
+  int64_t locateInlineHits = 1 << 22;  // a chunk with more hits than this is finished through windows of ...
+  int64_t locateWindowHits = 1 << 26;  // ... this many flat hit indices
+  LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
+  uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
   awfm_gpu_stats stats{};
-  PipeSlot slots[3];
+  static constexpr int kSlots = 6;
+  PipeSlot slots[kSlots];
   std::mutex mu;
 };
 
@@ -250,10 +265,12 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   c->locateLpq = amino ? 4 : 1;
   ix.deepSeedTable = nullptr;
   ix.deepSeedK = ix.deepSeedWide = 0;
-  CUB_(cudaMalloc(&c->dWorkCounter, 64));
+  CUB_(cudaMalloc(&c->sc.dWorkCounter, 64));
   for (auto &s : c->slots) {
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&s.offsetsDone, cudaEventDisableTiming));
+    CUB_(cudaMalloc(&s.sc.dWorkCounter, 64));
   }
 #undef CUB_
   *out = c;
@@ -376,7 +393,20 @@ extern "C" int awfm_gpu_ctx_create_from_file(awfm_gpu_ctx **ctx, int device, con
   return rc;
 }
 
+static void freeScratch(LocateScratch &sc) {
+  cudaFree(sc.scanTemp);
+  cudaFree(sc.dLengths);
+  cudaFree(sc.dWorkCounter);
+  sc = LocateScratch();
+}
+
 static void freeSlot(PipeSlot &s) {
+  freeScratch(s.sc);
+  if (s.hHit) cudaFreeHost(s.hHit);
+  if (s.hPos) cudaFreeHost(s.hPos);
+  cudaFree(s.dHit);
+  cudaFree(s.dPos);
+  if (s.offsetsDone) cudaEventDestroy(s.offsetsDone);
   if (s.hLetters) cudaFreeHost(s.hLetters);
   if (s.hOffsets) cudaFreeHost(s.hOffsets);
   if (s.hCounts) cudaFreeHost(s.hCounts);
@@ -406,9 +436,9 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dSequenceEnds);
   cudaFree(c->dDeepSeed);
   cudaFree(c->dDenseSa);
-  cudaFree(c->scanTemp);
-  cudaFree(c->dLengths);
-  cudaFree(c->dWorkCounter);
+  freeScratch(c->sc);
+  if (c->hBigPos) cudaFreeHost(c->hBigPos);
+  cudaFree(c->dBigPos);
   cudaGetLastError();
   delete c;
 }
@@ -423,6 +453,11 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "locate_lpq" && lpqOk(value)) c->locateLpq = (int)value;
   else if (k == "count_variant" && (value == 0 || value == 1)) c->countVariant = (int)value;
   else if (k == "locate_variant" && (value == 0 || value == 1)) c->locateVariant = (int)value;
+  else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
+  else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
+  else if (k == "locate_chunk_queries" && value >= 64 && value <= (1ll << 30)) c->locateChunkQueries = value;
+  else if (k == "locate_inline_hits" && value >= 0 && value <= (1ll << 32)) c->locateInlineHits = value;
+  else if (k == "locate_window_hits" && value >= 1 && value <= (1ll << 32)) c->locateWindowHits = value;
   else if (k == "use_deep_seed_table" && (value == 0 || value == 1)) {  // A/B switch for a table already derived
     const bool on = value && c->dDeepSeed;
     c->ix.deepSeedTable = on ? c->dDeepSeed : nullptr;
@@ -497,15 +532,15 @@ static int launchCount(awfm_gpu_ctx *c, const QueryBatch &qb, uint32_t *dCounts,
 
 // the walk itself: dPos holds BWT positions on entry, text positions on exit
 template <int LPQ, bool AMINO>
-static int launchWalk(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
+static int launchWalk(awfm_gpu_ctx *c, LocateScratch &sc, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
   int grid = 0;
   if (c->locateVariant == 1) {  // group per hit with refill from a chunk dispenser
     auto k = locateKernelRefill<LPQ, AMINO>;
     if (int r = gridFor(c, k, 256, &grid)) return r;
     const uint64_t need = (numHits * LPQ + 255) / 256;
     grid = (int)std::min<uint64_t>((uint64_t)grid, need);
-    CU(cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), st));
-    k<<<grid, 256, 0, st>>>(c->ix, numHits, dPos, c->dWorkCounter);
+    CU(cudaMemsetAsync(sc.dWorkCounter, 0, sizeof(unsigned long long), st));
+    k<<<grid, 256, 0, st>>>(c->ix, numHits, dPos, sc.dWorkCounter);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   }
@@ -519,15 +554,15 @@ static int launchWalk(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStr
 }
 
 template <int LPQ, bool AMINO>
-static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *dHitOffsets, uint64_t n,
-                        uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
+static int launchLocate(awfm_gpu_ctx *c, LocateScratch &sc, const uint4 *dRanges, const uint64_t *dHitOffsets,
+                        uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
   {  // BWT start position of every hit of the window, written into the output buffer itself
     const uint64_t warps = (n + 31) / 32;
     const int g = (int)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->numSMs * 8);
     expandHits<<<std::max(g, 1), 256, 0, st>>>(dRanges, dHitOffsets, n, hb, he, dPos);
     CU(cudaGetLastError());
   }
-  return launchWalk<LPQ, AMINO>(c, he - hb, dPos, st);
+  return launchWalk<LPQ, AMINO>(c, sc, he - hb, dPos, st);
 }
 
 // lanes per query / per hit: amino quarter-lines are read by 1, 2 or 4 lanes; a nucleotide LF step by 1 or 2 lanes
@@ -546,7 +581,7 @@ static int launchLocate(awfm_gpu_ctx *c, const uint4 *dRanges, const uint64_t *d
 
 static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
   if (numHits == 0) return AWFM_GPU_OK;
-  return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, numHits, dPos, st);
+  return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, c->sc, numHits, dPos, st);
 }
 
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
@@ -571,27 +606,28 @@ extern "C" int awfm_gpu_count_device(awfm_gpu_ctx *c, const uint8_t *dLetters, c
   return countDeviceImpl(c, dLetters, dOffsets, fixedLen, n, dCounts, dRanges, (cudaStream_t)stream);
 }
 
-static int scanImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, uint64_t n, uint64_t *dHitOffsets, cudaStream_t st) {
-  if (c->lengthsCap < n + 1) {
-    cudaFree(c->dLengths);
-    c->dLengths = nullptr;
-    c->lengthsCap = 0;
-    CU(cudaMalloc(&c->dLengths, (n + 1) * 8));
-    c->lengthsCap = n + 1;
+static int scanImpl(awfm_gpu_ctx *c, LocateScratch &sc, const awfm_range *dRanges, uint64_t n, uint64_t *dHitOffsets,
+                    cudaStream_t st) {
+  if (sc.lengthsCap < n + 1) {
+    cudaFree(sc.dLengths);
+    sc.dLengths = nullptr;
+    sc.lengthsCap = 0;
+    CU(cudaMalloc(&sc.dLengths, (n + 1) * 8));
+    sc.lengthsCap = n + 1;
   }
   size_t need = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, need, c->dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
-  if (need > c->scanTempBytes) {
-    cudaFree(c->scanTemp);
-    c->scanTemp = nullptr;
-    c->scanTempBytes = 0;
-    CU(cudaMalloc(&c->scanTemp, need));
-    c->scanTempBytes = need;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, need, sc.dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
+  if (need > sc.scanTempBytes) {
+    cudaFree(sc.scanTemp);
+    sc.scanTemp = nullptr;
+    sc.scanTempBytes = 0;
+    CU(cudaMalloc(&sc.scanTemp, need));
+    sc.scanTempBytes = need;
   }
-  CU(cudaMemsetAsync(c->dLengths + n, 0, 8, st));
-  if (n) rangeLengths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)dRanges, n, c->dLengths);
+  CU(cudaMemsetAsync(sc.dLengths + n, 0, 8, st));
+  if (n) rangeLengths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)dRanges, n, sc.dLengths);
   CU(cudaGetLastError());
-  CU(cub::DeviceScan::ExclusiveSum(c->scanTemp, need, c->dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
+  CU(cub::DeviceScan::ExclusiveSum(sc.scanTemp, need, sc.dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
   c->stats.launches += 3;
   return AWFM_GPU_OK;
 }
@@ -600,17 +636,17 @@ extern "C" int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *c, const awfm_range *dR
                                            uint64_t *dHitOffsets, void *stream) {
   if (!c || !dHitOffsets || (n && !dRanges)) return fail(AWFM_GPU_ERR_ARG, "null argument");
   if (int r = setDevice(c)) return r;
-  return scanImpl(c, dRanges, n, dHitOffsets, (cudaStream_t)stream);
+  return scanImpl(c, c->sc, dRanges, n, dHitOffsets, (cudaStream_t)stream);
 }
 
-static int locateDeviceImpl(awfm_gpu_ctx *c, const awfm_range *dRanges, const uint64_t *dHitOffsets, uint64_t n,
-                            uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
+static int locateDeviceImpl(awfm_gpu_ctx *c, LocateScratch &sc, const awfm_range *dRanges, const uint64_t *dHitOffsets,
+                            uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
   if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
   if (he <= hb) return AWFM_GPU_OK;
   EventPair *ev = nextEvents(c);
   if (ev) CU(cudaEventRecord(ev->a, st));
-  int r = DISPATCH_LOCATE(launchLocate, c->locateLpq, c->ix.amino != 0, c, (const uint4 *)dRanges, dHitOffsets, n, hb,
-                       he, dPos, st);
+  int r = DISPATCH_LOCATE(launchLocate, c->locateLpq, c->ix.amino != 0, c, sc, (const uint4 *)dRanges, dHitOffsets, n,
+                          hb, he, dPos, st);
   if (ev) CU(cudaEventRecord(ev->b, st));
   c->stats.launches += 2;
   c->stats.hits += he - hb;
@@ -621,7 +657,7 @@ extern "C" int awfm_gpu_locate_device(awfm_gpu_ctx *c, const awfm_range *dRanges
                                       uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, void *stream) {
   if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return fail(AWFM_GPU_ERR_ARG, "null argument");
   if (int r = setDevice(c)) return r;
-  return locateDeviceImpl(c, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
+  return locateDeviceImpl(c, c->sc, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ derived structures
@@ -909,7 +945,7 @@ extern "C" int awfm_gpu_locate_host(awfm_gpu_ctx *c, const uint8_t *letters, con
   if (int r = countDeviceImpl(c, (const uint8_t *)dL.p, offsets ? (const uint64_t *)dO.p : nullptr, fixedLen, n,
                               (uint32_t *)dC.p, (awfm_range *)dR.p, st))
     return r;
-  if (int r = scanImpl(c, (const awfm_range *)dR.p, n, (uint64_t *)dH.p, st)) return r;
+  if (int r = scanImpl(c, c->sc, (const awfm_range *)dR.p, n, (uint64_t *)dH.p, st)) return r;
   CU(cudaMemcpyAsync(hitOffsets, dH.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (ranges) CU(cudaMemcpyAsync(ranges, dR.p, n * 16, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -923,7 +959,7 @@ extern "C" int awfm_gpu_locate_host(awfm_gpu_ctx *c, const uint8_t *letters, con
   CU(dP.alloc(batch * 8));
   for (uint64_t hb = 0; hb < total; hb += batch) {
     const uint64_t he = std::min(total, hb + batch);
-    if (int r = locateDeviceImpl(c, (const awfm_range *)dR.p, (const uint64_t *)dH.p, n, hb, he, (uint64_t *)dP.p, st))
+    if (int r = locateDeviceImpl(c, c->sc, (const awfm_range *)dR.p, (const uint64_t *)dH.p, n, hb, he, (uint64_t *)dP.p, st))
       return r;
     CU(cudaMemcpyAsync(positions + hb, dP.p, (he - hb) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1008,83 +1044,126 @@ static bool isPinnedHost(const void *p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Packs queries [first, first+n) for shipping.  Fast path (one pass over the 32-B entries): all lengths equal; if the
-// strings are also laid out back to back in page-locked memory the copy is skipped and the DMA reads the caller's
-// buffer directly.  General path: two passes (lengths -> offsets, then copy).
-static int packChunk(PipeSlot &s, const awfm_kmer_search_data *data, uint64_t first, uint64_t n, int threads,
-                     bool wantRanges, bool sourcePinned, Packed *out) {
-  threads = std::max(1, std::min<int>(threads, (int)std::max<uint64_t>(1, n / 2048)));
-  const awfm_kmer_search_data *d0 = data + first;
-  const uint64_t len0 = d0[0].kmerLength;
-  if (len0 >= 1 && len0 <= 65536) {
-    const uint8_t *base = (const uint8_t *)d0[0].kmerString;
-    // cheap probe before committing to the copy-free variant
-    bool direct = sourcePinned && (const uint8_t *)d0[n - 1].kmerString == base + (n - 1) * len0 &&
-                  (const uint8_t *)d0[n / 2].kmerString == base + (n / 2) * len0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-      if (int r = ensureSlot(s, n, direct ? 16 : n * len0 + 16, wantRanges)) return r;
-      uint8_t *dst = s.hLetters;
-      int uniform = 1, contiguous = 1;
-#pragma omp parallel num_threads(threads) reduction(&& : uniform, contiguous)
+// ---- packing one chunk of the list by the engine's OpenMP team ----
+// Shared by the whole team; written by the master thread only, and only between barriers.
+// Fast path (one pass over the 32-B entries): all lengths equal; if the strings are also laid out back to back in
+// page-locked memory the copy is skipped and the DMA reads the caller's buffer directly.  General path: two passes
+// (lengths -> offsets, then copy).
+struct TeamPack {
+  const awfm_kmer_search_data *d0 = nullptr;
+  uint64_t n = 0, len0 = 0;
+  bool optimistic = false, direct = false, fallback = false, wantRanges = false;
+  uint8_t *staging = nullptr;
+  const uint8_t *base = nullptr;
+  int uniformAll = 1, contiguousAll = 1;
+  std::vector<uint64_t> partSum;
+  int rc = AWFM_GPU_OK;
+};
+
+// master thread, before the barrier that precedes teamPack()
+static void teamPackPrepare(TeamPack &tp, PipeSlot &s, const awfm_kmer_search_data *d0, uint64_t n, bool sourcePinned,
+                            bool wantRanges) {
+  tp.d0 = d0, tp.n = n, tp.wantRanges = wantRanges, tp.rc = AWFM_GPU_OK;
+  tp.len0 = d0[0].kmerLength;
+  tp.optimistic = tp.len0 >= 1 && tp.len0 <= 65536;
+  tp.base = (const uint8_t *)d0[0].kmerString;
+  // cheap probe before committing to the copy-free variant
+  tp.direct = tp.optimistic && sourcePinned &&
+              (const uint8_t *)d0[n - 1].kmerString == tp.base + (n - 1) * tp.len0 &&
+              (const uint8_t *)d0[n / 2].kmerString == tp.base + (n / 2) * tp.len0;
+  if (tp.optimistic) {
+    tp.rc = ensureSlot(s, n, tp.direct ? 16 : n * tp.len0 + 16, wantRanges);
+    tp.staging = s.hLetters;
+  }
+  tp.uniformAll = tp.contiguousAll = 1;
+  tp.fallback = !tp.optimistic;
+}
+
+// every thread of the team (t of T); contains barriers, so all threads must call it under the same conditions
+static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
+  const awfm_kmer_search_data *d0 = tp.d0;
+  const uint64_t n = tp.n, len0 = tp.len0;
+  const uint64_t a = n * t / T, b = n * (t + 1) / T;
+  if (n && tp.rc == AWFM_GPU_OK && tp.optimistic) {
+    bool uni = true, con = true;
+    if (tp.direct) {
+      const uint8_t *base = tp.base;
+      for (uint64_t i = a; i < b; i++) {
+        uni &= d0[i].kmerLength == len0;
+        con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+      }
+    } else {
+      uint8_t *staging = tp.staging;
+      for (uint64_t i = a; i < b && uni; i++) {
+        uni = d0[i].kmerLength == len0;
+        if (uni) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+      }
+    }
+    if (!uni) {
+#pragma omp atomic write
+      tp.uniformAll = 0;
+    }
+    if (!con) {
+#pragma omp atomic write
+      tp.contiguousAll = 0;
+    }
+  }
+#pragma omp barrier
+  if (n && tp.rc == AWFM_GPU_OK) {
+    // a direct (copy-free) attempt that found a gap, or mixed lengths: redo this chunk on the general path
+    if (tp.optimistic && tp.uniformAll && tp.direct && !tp.contiguousAll) {
+#pragma omp barrier
+#pragma omp master
       {
-        const int t = omp_get_thread_num();
-        const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
-        bool uni = true, con = true;
-        if (direct) {
-          for (uint64_t i = a; i < b; i++) {
-            uni &= d0[i].kmerLength == len0;
-            con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
-          }
-        } else {
-          for (uint64_t i = a; i < b && uni; i++) {
-            uni = d0[i].kmerLength == len0;
-            if (uni) copyLetters(dst + i * len0, (const uint8_t *)d0[i].kmerString, len0);
-          }
+        tp.direct = false;
+        tp.rc = ensureSlot(s, n, n * len0 + 16, tp.wantRanges);
+        tp.staging = s.hLetters;
+      }
+#pragma omp barrier
+      if (tp.rc == AWFM_GPU_OK) {
+        uint8_t *staging = tp.staging;
+        for (uint64_t i = a; i < b; i++) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+      }
+#pragma omp barrier
+    } else if (!tp.optimistic || !tp.uniformAll) {
+      uint64_t sum = 0;
+      for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
+      tp.partSum[t + 1] = sum;
+#pragma omp barrier
+#pragma omp master
+      {
+        tp.partSum[0] = 0;
+        for (int k = 0; k < T; k++) tp.partSum[k + 1] += tp.partSum[k];
+        tp.rc = ensureSlot(s, n, tp.partSum[T] + 16, tp.wantRanges);
+        tp.staging = s.hLetters;
+        tp.fallback = true;
+      }
+#pragma omp barrier
+      if (tp.rc == AWFM_GPU_OK) {
+        uint64_t o = tp.partSum[t];
+        uint64_t *offs = s.hOffsets;
+        uint8_t *staging = tp.staging;
+        for (uint64_t i = a; i < b; i++) {
+          offs[i] = o;
+          memcpy(staging + o, d0[i].kmerString, d0[i].kmerLength);
+          o += d0[i].kmerLength;
         }
-        uniform = uni;
-        contiguous = con;
       }
-      if (!uniform) break;  // general path below
-      if (direct && !contiguous) {
-        direct = false;  // the probe was too optimistic: pack with the copy
-        continue;
-      }
-      out->uniformLen = (uint32_t)len0;
-      out->letterBytes = n * len0;
-      out->source = direct ? base : s.hLetters;
-      return AWFM_GPU_OK;
+#pragma omp barrier
     }
   }
-  std::vector<uint64_t> partSum(threads + 1, 0);
-#pragma omp parallel num_threads(threads)
-  {
-    const int t = omp_get_thread_num();
-    const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
-    uint64_t sum = 0;
-    for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
-    partSum[t + 1] = sum;
+}
+
+// master thread, after teamPack() and a barrier: what to ship
+static Packed teamPackResult(TeamPack &tp, PipeSlot &s, int T) {
+  Packed pk;
+  if (tp.fallback) {
+    s.hOffsets[tp.n] = tp.partSum[T];
+    pk.uniformLen = 0, pk.letterBytes = tp.partSum[T], pk.source = s.hLetters;
+  } else {
+    pk.uniformLen = (uint32_t)tp.len0, pk.letterBytes = tp.n * tp.len0, pk.source = tp.direct ? tp.base : s.hLetters;
   }
-  for (int t = 0; t < threads; t++) partSum[t + 1] += partSum[t];
-  const uint64_t total = partSum[threads];
-  if (int r = ensureSlot(s, n, total + 16, wantRanges)) return r;
-  uint8_t *dst = s.hLetters;
-  uint64_t *offs = s.hOffsets;
-#pragma omp parallel num_threads(threads)
-  {
-    const int t = omp_get_thread_num();
-    const uint64_t a = n * t / threads, b = n * (t + 1) / threads;
-    uint64_t o = partSum[t];
-    for (uint64_t i = a; i < b; i++) {
-      offs[i] = o;
-      memcpy(dst + o, d0[i].kmerString, d0[i].kmerLength);
-      o += d0[i].kmerLength;
-    }
-  }
-  offs[n] = total;
-  out->uniformLen = 0;
-  out->letterBytes = total;
-  out->source = s.hLetters;
-  return AWFM_GPU_OK;
+  return pk;
 }
 
 static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, const Packed &pk, bool wantRanges) {
@@ -1097,6 +1176,10 @@ static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, const Packed &pk, bool want
     return r;
   c->stats.h2dBytes += pk.letterBytes + (fixed ? 0 : (s.n + 1) * 8);
   return AWFM_GPU_OK;
+}
+
+static int teamSize(uint32_t numThreads, uint64_t n, uint64_t chunk) {
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(1, numThreads), std::min(n, chunk) / 64));
 }
 
 // awFmParallelSearchCount over the reference's list layout.  One persistent OpenMP region runs the whole call: per
@@ -1113,7 +1196,7 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
   if (n == 0) return AWFM_GPU_OK;
   const uint64_t chunk = (uint64_t)c->chunkQueries;
   const uint64_t numChunks = (n + chunk - 1) / chunk;
-  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(1, numThreads), std::min(n, chunk) / 1024 + 1));
+  const int T = teamSize(numThreads, n, chunk);
   constexpr int NS = 3;
   const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
   const double tStart = omp_get_wtime();
@@ -1123,13 +1206,9 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
   int rc = AWFM_GPU_OK;
   uint64_t oldFirst = 0, oldN = 0;  // chunk whose counts are scattered this round
   const uint32_t *oldCounts = nullptr;
-  uint64_t newFirst = 0, newN = 0, len0 = 0;  // chunk packed this round
-  bool direct = false, optimistic = false, fallback = false;
-  uint8_t *staging = nullptr;
-  const uint8_t *base = nullptr;
-  int uniformAll = 1, contiguousAll = 1;
-  std::vector<uint64_t> partSum(T + 1, 0);
-  Packed pk;
+  uint64_t newFirst = 0;            // chunk packed this round
+  TeamPack tp;
+  tp.partSum.assign(T + 1, 0);
 
 #pragma omp parallel num_threads(T)
   {
@@ -1147,22 +1226,11 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
           if (rc == AWFM_GPU_OK) oldFirst = s.first, oldN = s.n, oldCounts = s.hCounts;
           s.busy = false;
         }
-        newN = 0;
+        tp.n = 0;
         if (ci < numChunks && rc == AWFM_GPU_OK) {
           newFirst = ci * chunk;
-          newN = std::min(chunk, n - newFirst);
-          const awfm_kmer_search_data *d0 = data + newFirst;
-          len0 = d0[0].kmerLength;
-          optimistic = len0 >= 1 && len0 <= 65536;
-          base = (const uint8_t *)d0[0].kmerString;
-          direct = optimistic && sourcePinned && (const uint8_t *)d0[newN - 1].kmerString == base + (newN - 1) * len0 &&
-                   (const uint8_t *)d0[newN / 2].kmerString == base + (newN / 2) * len0;
-          if (optimistic) {
-            rc = ensureSlot(s, newN, direct ? 16 : newN * len0 + 16, false);
-            staging = s.hLetters;
-          }
-          uniformAll = contiguousAll = 1;
-          fallback = !optimistic;
+          teamPackPrepare(tp, s, data + newFirst, std::min(chunk, n - newFirst), sourcePinned, false);
+          if (tp.rc != AWFM_GPU_OK) rc = tp.rc;
         }
         tWait += omp_get_wtime() - t0;
       }
@@ -1173,88 +1241,15 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
         const uint64_t a = oldN * t / T, b = oldN * (t + 1) / T;
         for (uint64_t i = a; i < b; i++) dst[i].count = oldCounts[i];
       }
-      if (newN && rc == AWFM_GPU_OK && optimistic) {
-        const awfm_kmer_search_data *d0 = data + newFirst;
-        const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
-        bool uni = true, con = true;
-        if (direct) {
-          for (uint64_t i = a; i < b; i++) {
-            uni &= d0[i].kmerLength == len0;
-            con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
-          }
-        } else {
-          for (uint64_t i = a; i < b && uni; i++) {
-            uni = d0[i].kmerLength == len0;
-            if (uni) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
-          }
-        }
-        if (!uni) {
-#pragma omp atomic write
-          uniformAll = 0;
-        }
-        if (!con) {
-#pragma omp atomic write
-          contiguousAll = 0;
-        }
-      }
-#pragma omp barrier
-      if (newN && rc == AWFM_GPU_OK) {
-        // a direct (copy-free) attempt that found a gap, or mixed lengths: redo this chunk on the general path
-        if (optimistic && uniformAll && direct && !contiguousAll) {
-#pragma omp barrier
-#pragma omp master
-          {
-            direct = false;
-            rc = ensureSlot(s, newN, newN * len0 + 16, false);
-            staging = s.hLetters;
-          }
-#pragma omp barrier
-          if (rc == AWFM_GPU_OK) {
-            const awfm_kmer_search_data *d0 = data + newFirst;
-            const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
-            for (uint64_t i = a; i < b; i++) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
-          }
-#pragma omp barrier
-        } else if (!optimistic || !uniformAll) {
-          const awfm_kmer_search_data *d0 = data + newFirst;
-          const uint64_t a = newN * t / T, b = newN * (t + 1) / T;
-          uint64_t sum = 0;
-          for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
-          partSum[t + 1] = sum;
-#pragma omp barrier
-#pragma omp master
-          {
-            partSum[0] = 0;
-            for (int k = 0; k < T; k++) partSum[k + 1] += partSum[k];
-            rc = ensureSlot(s, newN, partSum[T] + 16, false);
-            staging = s.hLetters;
-            fallback = true;
-          }
-#pragma omp barrier
-          if (rc == AWFM_GPU_OK) {
-            uint64_t o = partSum[t];
-            uint64_t *offs = s.hOffsets;
-            for (uint64_t i = a; i < b; i++) {
-              offs[i] = o;
-              memcpy(staging + o, d0[i].kmerString, d0[i].kmerLength);
-              o += d0[i].kmerLength;
-            }
-          }
-#pragma omp barrier
-        }
-      }
+      teamPack(tp, s, t, T);
       const double w1 = omp_get_wtime();
 #pragma omp master
       {
         tWork += w1 - w0;
-        if (newN && rc == AWFM_GPU_OK) {
-          if (fallback) {
-            s.hOffsets[newN] = partSum[T];
-            pk.uniformLen = 0, pk.letterBytes = partSum[T], pk.source = s.hLetters;
-          } else {
-            pk.uniformLen = (uint32_t)len0, pk.letterBytes = newN * len0, pk.source = direct ? base : s.hLetters;
-          }
-          s.first = newFirst, s.n = newN;
+        if (tp.n && tp.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = tp.rc;
+        if (tp.n && rc == AWFM_GPU_OK) {
+          const Packed pk = teamPackResult(tp, s, T);
+          s.first = newFirst, s.n = tp.n;
           rc = submitCount(c, s, pk, false);
           if (rc == AWFM_GPU_OK) {
             cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
@@ -1273,7 +1268,7 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
   }
   for (auto &s : c->slots)  // only reachable with rc != OK: never leave a DMA in flight
     if (s.busy) {
-      cudaEventSynchronize(s.done);
+      cudaStreamSynchronize(s.stream);
       s.busy = false;
     }
   if (getenv("AWFM_GPU_VERBOSE"))
@@ -1283,6 +1278,41 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
   return rc;
 }
 
+// ---- awFmParallelSearchLocate over the reference's list layout ----
+static int ensureHitBuffers(PipeSlot &s, uint64_t queries) {
+  if (s.hitCap < queries + 1) {
+    if (s.hHit) cudaFreeHost(s.hHit);
+    cudaFree(s.dHit);
+    s.hHit = nullptr, s.dHit = nullptr, s.hitCap = 0;
+    CU(cudaHostAlloc(&s.hHit, (queries + 1) * 8, cudaHostAllocDefault));
+    CU(cudaMalloc(&s.dHit, (queries + 1) * 8));
+    s.hitCap = queries + 1;
+  }
+  return AWFM_GPU_OK;
+}
+
+static int ensurePositionBuffers(uint64_t **hPos, uint64_t **dPos, uint64_t *cap, uint64_t hits, uint64_t floorHits) {
+  if (*cap < hits) {
+    if (*hPos) cudaFreeHost(*hPos);
+    cudaFree(*dPos);
+    *hPos = nullptr, *dPos = nullptr, *cap = 0;
+    const uint64_t want = std::max(hits + hits / 4, floorHits);
+    CU(cudaHostAlloc(hPos, want * 8, cudaHostAllocDefault));
+    CU(cudaMalloc(dPos, want * 8));
+    *cap = want;
+  }
+  return AWFM_GPU_OK;
+}
+
+// A chunk goes through four stations, one round apart or more, so neither side of the bus waits for the other:
+//   pack   (team)    round r                     letters of the chunk into staging (or nothing when copy-free)
+//   ship   (master)  round r+1                   H2D, search with ranges, scan of the range lengths, hit offsets D2H
+//   walk   (master)  round r+1+kWalkLag          the hit total is on the host: expand + backtrace walk, positions D2H
+//   finish (team)    round r+1+kWalkLag+kFinLag  count / capacity semantics of src/AwFmParallelSearch.c:367-387
+//                                                (realloc to exactly `count` when the list is too small) and the
+//                                                positions of SA[sp..ep] in that order into each positionList
+// A chunk with more hits than kInlineHits (a very short or very repetitive query) is finished through a window of
+// flat hit indices instead, by the same team, with the pipeline behind it waiting.
 extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
                                            uint32_t numThreads) {
   if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
@@ -1290,106 +1320,216 @@ extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_dat
   if (int r = setDevice(c)) return r;
   if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
   beginCall(c);
-  const int threads = (int)std::max<uint32_t>(1, numThreads);
-  const uint64_t chunk = (uint64_t)c->chunkQueries;
-  PipeSlot &s = c->slots[0];
-  const bool sourcePinned = n > 0 && data[0].kmerString && isPinnedHost(data[0].kmerString);
-  uint64_t *hHit = nullptr, *hPos = nullptr, *dHit = nullptr, *dPos = nullptr;
-  uint64_t hitCap = 0, posCap = 0;
+  if (n == 0) return AWFM_GPU_OK;
+  constexpr int64_t kWalkLag = 2, kFinLag = 2, NS = awfm_gpu_ctx::kSlots;
+  static_assert(NS >= 2 + kWalkLag + kFinLag, "a slot is reused only after its chunk is finished");
+  const uint64_t kInlineHits = (uint64_t)c->locateInlineHits, kWindowHits = (uint64_t)c->locateWindowHits;
+  const uint64_t chunk = (uint64_t)c->locateChunkQueries;
+  const int64_t numChunks = (int64_t)((n + chunk - 1) / chunk);
+  const int T = teamSize(numThreads, n, chunk);
+  const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
+  const double tStart = omp_get_wtime();
+  double tShip = 0, tWalkWait = 0, tWalk = 0, tFinWait = 0, tTeam = 0, tWindows = 0;
+
+  // state shared by the team (written by the calling thread between barriers)
   int rc = AWFM_GPU_OK;
-  bool allocFailed = false;
-  auto cleanup = [&]() {
-    if (hHit) cudaFreeHost(hHit);
-    if (hPos) cudaFreeHost(hPos);
-    cudaFree(dHit);
-    cudaFree(dPos);
+  int allocFailed = 0;
+  TeamPack tp;
+  tp.partSum.assign(T + 1, 0);
+  bool packed = false;  // tp holds the chunk packed in the previous round
+  struct {
+    awfm_kmer_search_data *dst = nullptr;
+    uint64_t n = 0, total = 0;
+    const uint64_t *hit = nullptr, *pos = nullptr;
+    bool big = false;
+    PipeSlot *slot = nullptr;
+  } fin;
+  struct {
+    uint64_t hb = 0, he = 0, q0 = 0, q1 = 0, cursor = 0;
+    bool ok = false;
+  } win;
+
+  auto cudaFailed = [&](cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return false;
+    cudaGetLastError();
+    if (rc == AWFM_GPU_OK)
+      rc = fail(e == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, what, cudaGetErrorString(e));
+    return true;
   };
-#define CUL(call)                                                         \
-  do {                                                                    \
-    cudaError_t e_ = (call);                                              \
-    if (e_ != cudaSuccess) {                                              \
-      cudaGetLastError();                                                 \
-      cleanup();                                                          \
-      return fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, #call, cudaGetErrorString(e_)); \
-    }                                                                     \
-  } while (0)
-  for (uint64_t first = 0; first < n; first += chunk) {
-    s.first = first;
-    s.n = std::min(chunk, n - first);
-    Packed pk;
-    if ((rc = packChunk(s, data, first, s.n, threads, true, sourcePinned, &pk))) break;
-    if ((rc = submitCount(c, s, pk, true))) break;
-    if (hitCap < s.n + 1) {
-      if (hHit) cudaFreeHost(hHit);
-      cudaFree(dHit);
-      hHit = nullptr, dHit = nullptr;
-      CUL(cudaHostAlloc(&hHit, (s.n + 1) * 8, cudaHostAllocDefault));
-      CUL(cudaMalloc(&dHit, (s.n + 1) * 8));
-      hitCap = s.n + 1;
-    }
-    if ((rc = scanImpl(c, (const awfm_range *)s.dRanges, s.n, dHit, s.stream))) break;
-    CUL(cudaMemcpyAsync(hHit, dHit, (s.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
-    CUL(cudaStreamSynchronize(s.stream));
-    c->stats.d2hBytes += (s.n + 1) * 8;
-    const uint64_t total = hHit[s.n];
-    // positions are produced in bounded batches of flat hit indices
-    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(total, 1ull << 28));
-    if (posCap < batch) {
-      if (hPos) cudaFreeHost(hPos);
-      cudaFree(dPos);
-      hPos = nullptr, dPos = nullptr;
-      CUL(cudaHostAlloc(&hPos, batch * 8, cudaHostAllocDefault));
-      CUL(cudaMalloc(&dPos, batch * 8));
-      posCap = batch;
-    }
-    // counts + capacity semantics first (src/AwFmParallelSearch.c:367-387): grow to exactly `count` when too small
-    {
-      awfm_kmer_search_data *dst = data + first;
-      const int64_t cnt = (int64_t)s.n;
-      bool failed = false;
-#pragma omp parallel for num_threads(threads) schedule(static) reduction(|| : failed)
-      for (int64_t i = 0; i < cnt; i++) {
-        const uint32_t count = (uint32_t)(hHit[i + 1] - hHit[i]);
-        if (dst[i].capacity >= count) {
-          dst[i].count = count;
-        } else {
-          void *p = realloc(dst[i].positionList, (size_t)count * sizeof(uint64_t));
-          if (!p) {
-            fprintf(stderr, "Critical memory failure: could not allocate memory for position list.\n");
-            dst[i].count = 0;  // never write past the old allocation
-            failed = true;
-          } else {
-            dst[i].positionList = (uint64_t *)p;
-            dst[i].capacity = count;
-            dst[i].count = count;
+
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    for (int64_t r = 0; r <= numChunks + kWalkLag + kFinLag; r++) {
+#pragma omp master
+      {
+        double t0 = omp_get_wtime();
+        // ---- ship the chunk packed in the previous round ----
+        if (packed && tp.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = tp.rc;
+        if (packed && rc == AWFM_GPU_OK) {
+          PipeSlot &s = c->slots[(r - 1) % NS];
+          const Packed pk = teamPackResult(tp, s, T);
+          s.first = (uint64_t)(r - 1) * chunk, s.n = tp.n;
+          s.total = 0, s.walked = s.big = false;
+          if (rc == AWFM_GPU_OK) rc = ensureHitBuffers(s, s.n);
+          if (rc == AWFM_GPU_OK) rc = submitCount(c, s, pk, true);
+          if (rc == AWFM_GPU_OK) rc = scanImpl(c, s.sc, (const awfm_range *)s.dRanges, s.n, s.dHit, s.stream);
+          if (rc == AWFM_GPU_OK &&
+              !cudaFailed(cudaMemcpyAsync(s.hHit, s.dHit, (s.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream), "hit offsets D2H") &&
+              !cudaFailed(cudaEventRecord(s.offsetsDone, s.stream), "event record")) {
+            c->stats.d2hBytes += (s.n + 1) * 8;
+            s.busy = true;
           }
         }
+        packed = false;
+        double t1 = omp_get_wtime();
+        tShip += t1 - t0;
+        // ---- the chunk shipped kWalkLag rounds ago: its hit total is on the host, walk it ----
+        const int64_t w = r - 1 - kWalkLag;
+        if (w >= 0 && w < numChunks && c->slots[w % NS].busy && rc == AWFM_GPU_OK) {
+          PipeSlot &s = c->slots[w % NS];
+          if (!cudaFailed(cudaEventSynchronize(s.offsetsDone), "hit offsets")) {
+            const double t2 = omp_get_wtime();
+            tWalkWait += t2 - t1;
+            s.total = s.hHit[s.n];
+            if (s.total > kInlineHits) s.big = true;
+            else if (s.total) {
+              rc = ensurePositionBuffers(&s.hPos, &s.dPos, &s.posCap, s.total, std::max<uint64_t>(chunk, 1 << 16));
+              if (rc == AWFM_GPU_OK)
+                rc = locateDeviceImpl(c, s.sc, (const awfm_range *)s.dRanges, s.dHit, s.n, 0, s.total, s.dPos, s.stream);
+              if (rc == AWFM_GPU_OK &&
+                  !cudaFailed(cudaMemcpyAsync(s.hPos, s.dPos, s.total * 8, cudaMemcpyDeviceToHost, s.stream), "positions D2H") &&
+                  !cudaFailed(cudaEventRecord(s.done, s.stream), "event record")) {
+                c->stats.d2hBytes += s.total * 8;
+                s.walked = true;
+              }
+            }
+            tWalk += omp_get_wtime() - t2;
+          }
+        }
+        t1 = omp_get_wtime();
+        // ---- the chunk walked kFinLag rounds ago: its positions are on the host, the team finishes it ----
+        fin.n = 0;
+        const int64_t f = w - kFinLag;
+        if (f >= 0 && f < numChunks && c->slots[f % NS].busy) {
+          PipeSlot &s = c->slots[f % NS];
+          if (s.walked) cudaFailed(cudaEventSynchronize(s.done), "positions");
+          if (rc == AWFM_GPU_OK) {
+            fin.dst = data + s.first, fin.n = s.n, fin.total = s.total, fin.hit = s.hHit, fin.pos = s.hPos;
+            fin.big = s.big, fin.slot = &s;
+            if (s.big) {
+              rc = ensurePositionBuffers(&c->hBigPos, &c->dBigPos, &c->bigPosCap, std::min(s.total, kWindowHits), 0);
+              if (rc != AWFM_GPU_OK) fin.n = 0;
+              win.cursor = 0;
+            }
+          }
+          if (!s.walked || rc != AWFM_GPU_OK) cudaStreamSynchronize(s.stream);
+          s.busy = false;
+        }
+        tFinWait += omp_get_wtime() - t1;
+        // ---- the chunk the team packs this round ----
+        tp.n = 0;
+        if (r < numChunks && rc == AWFM_GPU_OK) {
+          const uint64_t first = (uint64_t)r * chunk;
+          teamPackPrepare(tp, c->slots[r % NS], data + first, std::min(chunk, n - first), sourcePinned, true);
+          if (tp.rc != AWFM_GPU_OK) rc = tp.rc;
+          else packed = true;
+        }
       }
-      allocFailed |= failed;
-    }
-    uint64_t qCursor = 0;  // first query whose hits may intersect the current batch
-    for (uint64_t hb = 0; hb < total; hb += batch) {
-      const uint64_t he = std::min(total, hb + batch);
-      if ((rc = locateDeviceImpl(c, (const awfm_range *)s.dRanges, dHit, s.n, hb, he, dPos, s.stream))) break;
-      CUL(cudaMemcpyAsync(hPos, dPos, (he - hb) * 8, cudaMemcpyDeviceToHost, s.stream));
-      CUL(cudaStreamSynchronize(s.stream));
-      c->stats.d2hBytes += (he - hb) * 8;
-      while (qCursor < s.n && hHit[qCursor + 1] <= hb) qCursor++;
-      uint64_t qEnd = qCursor;
-      while (qEnd < s.n && hHit[qEnd] < he) qEnd++;
-      awfm_kmer_search_data *dst = data + first;
-      const int64_t q0 = (int64_t)qCursor, q1 = (int64_t)qEnd;
-#pragma omp parallel for num_threads(threads) schedule(static)
-      for (int64_t i = q0; i < q1; i++) {
-        if (dst[i].count == 0) continue;
-        const uint64_t a = std::max(hHit[i], hb), b = std::min(hHit[i + 1], he);
-        if (a < b) memcpy(dst[i].positionList + (a - hHit[i]), hPos + (a - hb), (b - a) * 8);
+#pragma omp barrier
+      const double w0 = omp_get_wtime();
+      // read now: the master rewrites `fin` in the next round's block, which it may reach before this thread is done
+      const bool windowed = fin.n && fin.big;
+      const uint64_t windowTotal = fin.total, windowHits = c->bigPosCap;
+      if (fin.n) {
+        awfm_kmer_search_data *dst = fin.dst;
+        const uint64_t *hit = fin.hit, *pos = fin.pos;
+        const bool copyNow = !fin.big;
+        const uint64_t a = fin.n * t / T, b = fin.n * (t + 1) / T;
+        bool failed = false;
+        for (uint64_t i = a; i < b; i++) {
+          const uint64_t h0 = hit[i];
+          const uint32_t count = (uint32_t)(hit[i + 1] - h0);
+          if (dst[i].capacity < count) {
+            void *p = realloc(dst[i].positionList, (size_t)count * sizeof(uint64_t));
+            if (!p) {
+              fprintf(stderr, "Critical memory failure: could not allocate memory for position list.\n");
+              dst[i].count = 0;  // never write past the old allocation
+              failed = true;
+              continue;
+            }
+            dst[i].positionList = (uint64_t *)p;
+            dst[i].capacity = count;
+          }
+          dst[i].count = count;
+          if (copyNow) {
+            if (count == 1) dst[i].positionList[0] = pos[h0];
+            else if (count) memcpy(dst[i].positionList, pos + h0, (size_t)count * 8);
+          }
+        }
+        if (failed) {
+#pragma omp atomic write
+          allocFailed = 1;
+        }
+      }
+      teamPack(tp, c->slots[r % NS], t, T);
+#pragma omp barrier
+      const double w1 = omp_get_wtime();
+      if (windowed) {  // positions in windows of flat hit indices [hb, he)
+        for (uint64_t hb = 0; hb < windowTotal; hb += windowHits) {
+#pragma omp master
+          {
+            PipeSlot &s = *fin.slot;
+            win.hb = hb, win.he = std::min(fin.total, hb + c->bigPosCap), win.ok = false;
+            if (rc == AWFM_GPU_OK)
+              rc = locateDeviceImpl(c, s.sc, (const awfm_range *)s.dRanges, s.dHit, s.n, win.hb, win.he, c->dBigPos, s.stream);
+            if (rc == AWFM_GPU_OK &&
+                !cudaFailed(cudaMemcpyAsync(c->hBigPos, c->dBigPos, (win.he - win.hb) * 8, cudaMemcpyDeviceToHost, s.stream), "positions D2H") &&
+                !cudaFailed(cudaStreamSynchronize(s.stream), "positions")) {
+              c->stats.d2hBytes += (win.he - win.hb) * 8;
+              while (win.cursor < fin.n && fin.hit[win.cursor + 1] <= win.hb) win.cursor++;
+              win.q0 = win.q1 = win.cursor;
+              while (win.q1 < fin.n && fin.hit[win.q1] < win.he) win.q1++;
+              win.ok = true;
+            }
+          }
+#pragma omp barrier
+          if (win.ok) {
+            awfm_kmer_search_data *dst = fin.dst;
+            const uint64_t *hit = fin.hit, *pos = c->hBigPos;
+            const uint64_t span = win.q1 - win.q0;
+            const uint64_t q0 = win.q0 + span * t / T, q1 = win.q0 + span * (t + 1) / T;
+            for (uint64_t i = q0; i < q1; i++) {
+              if (dst[i].count == 0) continue;
+              const uint64_t lo = std::max(hit[i], win.hb), hi = std::min(hit[i] + dst[i].count, win.he);
+              if (lo < hi) memcpy(dst[i].positionList + (lo - hit[i]), pos + (lo - win.hb), (hi - lo) * 8);
+            }
+          }
+#pragma omp barrier
+        }
+      }
+#pragma omp master
+      {
+        tTeam += w1 - w0;
+        tWindows += omp_get_wtime() - w1;
       }
     }
-    if (rc) break;
   }
-#undef CUL
-  cleanup();
+  for (auto &s : c->slots)  // only reachable with rc != OK: never leave a DMA in flight
+    if (s.busy) {
+      cudaStreamSynchronize(s.stream);
+      s.busy = false;
+    }
+  if (c->bigPosCap) {  // the window is not worth keeping between calls
+    cudaFreeHost(c->hBigPos);
+    cudaFree(c->dBigPos);
+    c->hBigPos = c->dBigPos = nullptr, c->bigPosCap = 0;
+  }
+  if (getenv("AWFM_GPU_VERBOSE"))
+    fprintf(stderr, "[awfm_gpu] locate list: %llu queries, %lld chunks, %d threads, pinned=%d, %llu hits: total %.1f ms = ship %.1f + "
+            "wait(offsets) %.1f + walk submit %.1f + wait(positions) %.1f + team pack/finish %.1f + windows %.1f\n",
+            (unsigned long long)n, (long long)numChunks, T, (int)sourcePinned, (unsigned long long)c->stats.hits,
+            1e3 * (omp_get_wtime() - tStart), 1e3 * tShip, 1e3 * tWalkWait, 1e3 * tWalk, 1e3 * tFinWait, 1e3 * tTeam, 1e3 * tWindows);
   if (rc == AWFM_GPU_OK && allocFailed) return fail(AWFM_GPU_ERR_ALLOC, "realloc of a position list failed");
   return rc;
 }

@@ -118,6 +118,9 @@ static int contextFor(const struct AwFmIndex *index, awfm_gpu_ctx **out) {
     if ((e = getenv("AWFM_GPU_LOCATE_LPQ"))) awfm_gpu_ctx_set_tuning(ctx, "locate_lpq", atoll(e));
     if ((e = getenv("AWFM_GPU_COUNT_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "count_variant", atoll(e));
     if ((e = getenv("AWFM_GPU_CHUNK_QUERIES"))) awfm_gpu_ctx_set_tuning(ctx, "chunk_queries", atoll(e));
+    if ((e = getenv("AWFM_GPU_LOCATE_CHUNK_QUERIES"))) awfm_gpu_ctx_set_tuning(ctx, "locate_chunk_queries", atoll(e));
+    if ((e = getenv("AWFM_GPU_LOCATE_INLINE_HITS"))) awfm_gpu_ctx_set_tuning(ctx, "locate_inline_hits", atoll(e));
+    if ((e = getenv("AWFM_GPU_LOCATE_WINDOW_HITS"))) awfm_gpu_ctx_set_tuning(ctx, "locate_window_hits", atoll(e));
     if ((e = getenv("AWFM_GPU_LOCATE_VARIANT"))) awfm_gpu_ctx_set_tuning(ctx, "locate_variant", atoll(e));
     /* opt-in derived structures (include/awfm_gpu.h): deeper seed table, denser SA samples */
     if ((e = getenv("AWFM_GPU_SEED_DEPTH")) && atoi(e) > 0) rc = awfm_gpu_ctx_extend_seed_table(ctx, (uint32_t)atoi(e), NULL);

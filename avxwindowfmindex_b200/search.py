@@ -231,6 +231,20 @@ class KmerSearchList:
                 out.append(np.frombuffer(buf, dtype=np.uint64).copy())
         return out
 
+    def positions_flat(self, limit=None):
+        """positions of the first `limit` queries, concatenated in query order (CSR values)."""
+        e = self.entries()
+        n = self.count if limit is None else min(limit, self.count)
+        counts = e["count"][:n]
+        lists = e["positionList"][:n]
+        out = np.zeros(int(counts.sum(dtype=np.uint64)), np.uint64)
+        o = 0
+        for i in np.flatnonzero(counts):
+            c = int(counts[i])
+            out[o:o + c] = np.frombuffer((C.c_uint64 * c).from_address(int(lists[i])), dtype=np.uint64)
+            o += c
+        return out
+
     def close(self):
         if self.ptr:
             self.lib.awFmDeallocKmerSearchList(self.ptr)

@@ -369,6 +369,11 @@ def run_ours(args):
             if not same:
                 raise SystemExit("PARITY FAILURE: CUDA positions differ from the oracle on the bench's locate leg")
         result["locate"] = loc
+        h_lq_cpu = d_lq[: min(nl, 1_000_000) * Ll].cpu().numpy()
+        h_lq = None
+        if not args.no_e2e:
+            h_lq = torch.empty(nl * Ll, dtype=torch.uint8).pin_memory()
+            h_lq.copy_(d_lq[: nl * Ll])
 
         # ---- derived structures (opt-in: HBM for fewer dependent DRAM round trips), same queries, same checks ----
         if args.derived_seed_depth > args.seed_k:
@@ -403,6 +408,7 @@ def run_ours(args):
         del d_lq, d_lc, d_lr, d_lh, d_lp
     else:
         derived_counts = None
+        h_lq = h_lq_cpu = None
 
     # ---- parity on a sample + exact algorithmic bytes from the oracle (checker, not the product) ----
     sample = min(n, 1_000_000)
@@ -430,13 +436,22 @@ def run_ours(args):
     e2e = None
     threads = max(1, (os.cpu_count() or 1) // world)
     if not args.no_e2e:
-        h_letters = torch.empty(n * L, dtype=torch.uint8).pin_memory()
-        h_letters.copy_(d_letters[: n * L])
+        # host memory of one rank's list: 32-B entry + one malloc'd 32-B position list (48 B with its header) + letters
+        ne = n
+        try:
+            import psutil
+            room = psutil.virtual_memory().available // max(world, 1) // 2
+            if ne * (80 + L) > room:
+                ne = max(1_000_000, int(room // (80 + L)))
+        except Exception:
+            pass
+        h_letters = torch.empty(ne * L, dtype=torch.uint8).pin_memory()
+        h_letters.copy_(d_letters[: ne * L])
         hl = h_letters.numpy()
         ix = host_index_struct(arrays)
         ip = C.addressof(ix)
         t0 = time.time()
-        sl = KmerSearchList(lib, n).fill(hl, fixed_len=L)  # awFmCreateKmerSearchList: n position lists, as the reference
+        sl = KmerSearchList(lib, ne).fill(hl, fixed_len=L)  # awFmCreateKmerSearchList: one position list per query, as the reference
         list_s = time.time() - t0
         assert lib.awFmGpuPrepareIndex(ip) == abi.AwFmSuccess  # one-time upload, reported separately
         lib.awFmParallelSearchCount(ip, sl.ptr, threads)
@@ -448,20 +463,57 @@ def run_ours(args):
             lib.awFmParallelSearchCount(ip, sl.ptr, threads)
             times.append(time.perf_counter() - t1)
         assert lib.awFmGpuLastCountStatus() == abi.AwFmSuccess
-        e2e_counts = sl.entries()["count"][:sample]
-        if not np.array_equal(e2e_counts, h_counts_sample):
+        e2e_counts = sl.entries()["count"][: min(sample, ne)]
+        if not np.array_equal(e2e_counts, h_counts_sample[: len(e2e_counts)]):
             raise SystemExit("PARITY FAILURE: drop-in counts differ from the device-resident path")
         t_step = sum(times) / len(times)
         if world > 1:
             t = torch.tensor([t_step], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_step = float(t.item())
-        e2e = {"value": world * n / t_step, "unit": UNIT, "h2d_bytes_per_step": n * L, "d2h_bytes_per_step": n * 4,
+        e2e = {"value": world * ne / t_step, "unit": UNIT, "h2d_bytes_per_step": ne * L, "d2h_bytes_per_step": ne * 4,
                "call": "awFmParallelSearchCount(index, searchList, numThreads) drop-in, host AwFmKmerSearchList",
-               "host_threads": threads, "ms_per_step": 1e3 * t_step, "search_list_setup_s": round(list_s, 2)}
+               "host_threads": threads, "ms_per_step": 1e3 * t_step, "search_list_setup_s": round(list_s, 2),
+               "queries_per_gpu": ne}
+        if ne != n:
+            e2e["note"] = f"host memory bounds the list to {ne} of the {n} queries per rank"
         sl.close()
-        lib.awFmGpuReleaseIndex(ip)
         del h_letters
+        # the other half of the metric through the same door: awFmParallelSearchLocate on a host list
+        if h_lq is not None:
+            sl = KmerSearchList(lib, nl).fill(h_lq.numpy(), fixed_len=Ll)
+            rc = lib.awFmParallelSearchLocate(ip, sl.ptr, threads)  # warm-up: grows the position lists that need it
+            if world > 1:
+                dist.barrier()
+            times = []
+            for _ in range(args.e2e_steps):
+                t1 = time.perf_counter()
+                rc = lib.awFmParallelSearchLocate(ip, sl.ptr, threads)
+                times.append(time.perf_counter() - t1)
+            if rc != abi.AwFmSuccess:
+                raise SystemExit(f"drop-in awFmParallelSearchLocate returned {rc}")
+            l_counts = sl.entries()["count"][:nl]
+            l_hits = int(l_counts.sum(dtype=np.uint64))
+            if arrays is not None and "locate" in result and "parity_sample" in result["locate"]:
+                ls = result["locate"]["parity_sample"]["queries"]
+                mine = sl.positions_flat(ls)
+                same = bool(np.array_equal(l_counts[:ls].astype(np.uint64), np.diff(o_hit)) and np.array_equal(mine, o_pos))
+                if not same:
+                    raise SystemExit("PARITY FAILURE: drop-in positions differ from the oracle")
+            else:
+                same = None
+            t_step = sum(times) / len(times)
+            if world > 1:
+                t = torch.tensor([t_step], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_step = float(t.item())
+            e2e["locate"] = {"call": "awFmParallelSearchLocate(index, searchList, numThreads) drop-in, host AwFmKmerSearchList",
+                             "queries_per_gpu": nl, "hits_per_gpu": l_hits, "ms_per_step": 1e3 * t_step,
+                             "located_hits_per_s": world * l_hits / t_step, "queries_per_s": world * nl / t_step,
+                             "h2d_bytes_per_step": nl * Ll, "d2h_bytes_per_step": (nl + 1) * 8 + l_hits * 8,
+                             "bit_exact_vs_oracle_sample": same}
+            sl.close()
+        lib.awFmGpuReleaseIndex(ip)
 
     # ---- cpu baseline (rank 0, N=1): the unmodified reference on the host cores, bounded sample ----
     cpu = None
@@ -478,6 +530,20 @@ def run_ours(args):
                    "sample": f"first {ns} of the {n} queries, 1 warm-up + best of 3 passes of the reference's "
                              f"awFmParallelSearchCount (oracle/_ref), numThreads={cores}",
                    "bit_exact_vs_cuda": ok}
+            if h_lq_cpu is not None:  # located hits/s of the reference on the locate leg's queries (bounded sample)
+                nq = len(h_lq_cpu) // Ll
+                rsl = KmerSearchList(ref.lib, nq).fill(h_lq_cpu, fixed_len=Ll)
+                ref.lib.awFmParallelSearchLocate(C.addressof(ix), rsl.ptr, cores)
+                best_t = 1e30
+                for _ in range(3):
+                    t1 = time.perf_counter()
+                    ref.lib.awFmParallelSearchLocate(C.addressof(ix), rsl.ptr, cores)
+                    best_t = min(best_t, time.perf_counter() - t1)
+                r_hits = int(rsl.entries()["count"][:nq].sum(dtype=np.uint64))
+                rsl.close()
+                cpu["locate"] = {"located_hits_per_s": r_hits / best_t, "queries_per_s": nq / best_t, "queries": nq,
+                                 "hits": r_hits, "sample": f"first {nq} of the locate leg's {nl} {Ll}-mers, 1 warm-up + best "
+                                                           f"of 3 passes of the reference's awFmParallelSearchLocate"}
         else:
             t1 = time.perf_counter()
             harness.Oracle(arrays).count(hs[: 1_000_000 * L], fixed_len=L, threads=cores)

@@ -111,8 +111,10 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
 /* Tuning knobs (kernel variant selection for measurement; defaults are the shipped configuration).
  * keys: "count_lpq" (lanes per query: 1,2,4,8; clamped to what the alphabet's line layout supports), "locate_lpq",
  * "count_variant" (0 group-per-query from global memory, 1 CTA tiles staged in shared memory), "locate_variant"
- * (0 group-per-hit, 1 group-per-hit with refill), "chunk_queries", "blocks_per_sm", "use_deep_seed_table" (0/1: A/B
- * switch for a table already derived with awfm_gpu_ctx_extend_seed_table). */
+ * (0 group-per-hit, 1 group-per-hit with refill), "blocks_per_sm" (0 = occupancy query), "use_deep_seed_table" (0/1:
+ * A/B switch for a table already derived with awfm_gpu_ctx_extend_seed_table); of the search-list engine:
+ * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
+ * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 
 /* ---- derived structures: spend HBM (180 GB per B200) to remove dependent DRAM round trips.  Both are computed on
@@ -174,7 +176,8 @@ int awfm_gpu_map_positions_host(awfm_gpu_ctx *ctx, const uint64_t *positions, ui
 int awfm_gpu_search_list_count(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
                                uint32_t numThreads);
 /* Fills count + positionList with the reference's capacity semantics (realloc to exactly count when
- * count > capacity, src/AwFmParallelSearch.c:367-387).  Returns AWFM_GPU_ERR_ALLOC if a realloc failed. */
+ * count > capacity, src/AwFmParallelSearch.c:367-387).  Returns AWFM_GPU_ERR_ALLOC if a realloc failed.
+ * Chunks of the list are pipelined: pack (host team) -> H2D + search + scan -> walk + D2H -> scatter (host team). */
 int awfm_gpu_search_list_locate(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
                                 uint32_t numThreads);
 

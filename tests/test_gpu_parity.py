@@ -226,12 +226,14 @@ def test_medium_index_many_queries(reference, tmp_path):
     sl = KmerSearchList(lib, n).fill(letters, fixed_len=length)
     import os
     os.environ["AWFM_GPU_CHUNK_QUERIES"] = "30000"  # force several pipeline chunks
+    os.environ["AWFM_GPU_LOCATE_CHUNK_QUERIES"] = "17000"
     try:
         parallel_search_count(lib, C.addressof(ix), sl, 8)
         assert np.array_equal(sl.counts(), r_counts)
         assert parallel_search_locate(lib, C.addressof(ix), sl, 8) == abi.AwFmSuccess
     finally:
         del os.environ["AWFM_GPU_CHUNK_QUERIES"]
+        del os.environ["AWFM_GPU_LOCATE_CHUNK_QUERIES"]
     o_hit, o_pos, _ = oracle.locate(letters, fixed_len=length, threads=8)
     mine = sl.positions()
     flat = np.concatenate(mine)

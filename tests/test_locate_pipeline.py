@@ -1,0 +1,168 @@
+"""The drop-in awFmParallelSearchLocate is a four-station pipeline over chunks of the list (pack -> ship -> walk ->
+finish, csrc/awfm_b200.cu).  These tests push many small chunks, every packing path (mixed lengths, equal lengths
+copied, equal lengths read in place from page-locked memory, a list that only looks contiguous) and the windowed
+path of chunks with very many hits through it, with 1..8 host threads, and compare element-wise with the compiled
+reference (src/AwFmParallelSearch.c:95-157, 315-387).  Run with -m gpu on a B200."""
+import contextlib
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from avxwindowfmindex_b200 import KmerSearchList, abi, capi, parallel_search_count, parallel_search_locate
+from avxwindowfmindex_b200.search import pack_queries
+from conftest import make_queries
+
+pytestmark = pytest.mark.gpu
+
+
+@contextlib.contextmanager
+def engine_env(**kv):
+    """The shim reads its tuning from the environment when it uploads an index (awfm_dropin.c)."""
+    old = {k: os.environ.get(k) for k in kv}
+    os.environ.update({k: str(v) for k, v in kv.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def check_against_reference(sl, r_counts, r_pos):
+    assert np.array_equal(sl.counts(), r_counts)
+    mine = sl.positions()
+    for i, p in enumerate(r_pos):
+        assert np.array_equal(p, mine[i]), i
+    e = sl.entries()
+    n = sl.count
+    # capacity = max(old capacity, count), grown by realloc to exactly count (src/AwFmParallelSearch.c:367-387)
+    assert np.array_equal(e["capacity"][:n], np.maximum(4, e["count"][:n]))
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r16", "amino_r8"])
+def test_many_small_chunks_mixed_lengths(small_indexes, reference, name):
+    b = small_indexes[name]
+    lib = capi.load()
+    k = b.arrays.seed_k
+    queries = make_queries(b.text, b.amino, seed=77, num=3000, min_len=1, max_len=k + 9, seed_k=k)
+    letters, offsets = pack_queries(queries)
+    rc, r_counts, r_pos = reference.locate(b.ptr, letters, offsets, threads=4)
+    ix = b.arrays.as_awfm_index()
+    ip = C.addressof(ix)
+    for chunk, threads in ((64, 1), (64, 8), (200, 3), (1 << 18, 5)):
+        with engine_env(AWFM_GPU_LOCATE_CHUNK_QUERIES=chunk, AWFM_GPU_CHUNK_QUERIES=chunk):
+            sl = KmerSearchList(lib, len(queries)).fill(letters, offsets)
+            assert parallel_search_locate(lib, ip, sl, threads) == rc == abi.AwFmSuccess
+            check_against_reference(sl, r_counts, r_pos)
+            # the list is reusable (src/AwFmIndex.h:344-345): count, then locate again with the grown capacities
+            parallel_search_count(lib, ip, sl, threads)
+            assert lib.awFmGpuLastCountStatus() == abi.AwFmSuccess
+            assert np.array_equal(sl.counts(), r_counts)
+            assert parallel_search_locate(lib, ip, sl, threads) == abi.AwFmSuccess
+            check_against_reference(sl, r_counts, r_pos)
+            sl.close()
+            lib.awFmGpuReleaseIndex(ip)
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "amino_r2"])
+def test_windowed_path_for_chunks_with_many_hits(small_indexes, reference, name):
+    """Short queries have thousands of hits each; with the inline limit at 0 every chunk that has hits is finished
+    through windows of 37 flat hit indices, so position lists straddle many windows."""
+    b = small_indexes[name]
+    lib = capi.load()
+    k = b.arrays.seed_k
+    queries = make_queries(b.text, b.amino, seed=5, num=400, min_len=1, max_len=k + 2, seed_k=k)
+    letters, offsets = pack_queries(queries)
+    rc, r_counts, r_pos = reference.locate(b.ptr, letters, offsets, threads=4)
+    assert int(r_counts.max()) > 100
+    ix = b.arrays.as_awfm_index()
+    ip = C.addressof(ix)
+    for threads in (1, 6):
+        with engine_env(AWFM_GPU_LOCATE_CHUNK_QUERIES=96, AWFM_GPU_LOCATE_INLINE_HITS=0,
+                        AWFM_GPU_LOCATE_WINDOW_HITS=37):
+            sl = KmerSearchList(lib, len(queries)).fill(letters, offsets)
+            assert parallel_search_locate(lib, ip, sl, threads) == rc
+            check_against_reference(sl, r_counts, r_pos)
+            sl.close()
+            lib.awFmGpuReleaseIndex(ip)
+    # mixed: only the chunks above 2000 hits take the windows
+    with engine_env(AWFM_GPU_LOCATE_CHUNK_QUERIES=64, AWFM_GPU_LOCATE_INLINE_HITS=2000,
+                    AWFM_GPU_LOCATE_WINDOW_HITS=1000):
+        sl = KmerSearchList(lib, len(queries)).fill(letters, offsets)
+        assert parallel_search_locate(lib, ip, sl, 4) == rc
+        check_against_reference(sl, r_counts, r_pos)
+        sl.close()
+        lib.awFmGpuReleaseIndex(ip)
+
+
+def test_equal_length_queries_every_packing_path(small_indexes, reference):
+    """Equal lengths: copied from pageable memory, read in place from page-locked memory, and a page-locked list
+    whose probe entries (first / middle / last of a chunk) look contiguous while others are not."""
+    import torch
+    b = small_indexes["nuc_r16"]
+    lib = capi.load()
+    n, length = 5000, 11
+    rng = np.random.default_rng(3)
+    starts = rng.integers(0, len(b.text) - length, n)
+    letters = b.text[starts[:, None] + np.arange(length)[None, :]].reshape(-1).copy()
+    letters.reshape(n, length)[rng.integers(0, n, n // 3), rng.integers(0, length, n // 3)] = ord("G")
+    rc, r_counts, r_pos = reference.locate(b.ptr, letters, fixed_len=length, threads=4)
+    ix = b.arrays.as_awfm_index()
+    ip = C.addressof(ix)
+    pinned = torch.from_numpy(letters.copy()).pin_memory()
+    with engine_env(AWFM_GPU_LOCATE_CHUNK_QUERIES=512, AWFM_GPU_CHUNK_QUERIES=512):
+        for source in ("pageable", "pinned", "pinned_shuffled"):
+            buf = letters if source == "pageable" else pinned.numpy()
+            sl = KmerSearchList(lib, n).fill(buf, fixed_len=length)
+            expect_counts, expect_pos = r_counts, r_pos
+            if source == "pinned_shuffled":
+                # swap two interior entries of every chunk: same strings, the list is no longer back to back
+                e = sl.entries()
+                perm = np.arange(n)
+                for first in range(0, n - 512, 512):
+                    perm[first + 10], perm[first + 20] = perm[first + 20], perm[first + 10]
+                e["kmerString"][:n] = e["kmerString"][:n][perm]
+                expect_counts = r_counts[perm]
+                expect_pos = [r_pos[i] for i in perm]
+            for threads in (1, 7):
+                assert parallel_search_locate(lib, ip, sl, threads) == rc
+                check_against_reference(sl, expect_counts, expect_pos)
+                parallel_search_count(lib, ip, sl, threads)
+                assert np.array_equal(sl.counts(), expect_counts)
+            sl.close()
+    lib.awFmGpuReleaseIndex(ip)
+
+
+def test_caller_capacity_is_kept_and_grown_exactly(small_indexes, reference):
+    """A caller may hand over lists with larger position lists; they are kept, smaller ones are grown to exactly
+    `count` (src/AwFmParallelSearch.c:367-387)."""
+    b = small_indexes["nuc_r8"]
+    lib = capi.load()
+    libc = C.CDLL(None)
+    libc.realloc.restype = C.c_void_p
+    libc.realloc.argtypes = [C.c_void_p, C.c_size_t]
+    queries = make_queries(b.text, False, seed=9, num=300, min_len=2, max_len=9, seed_k=b.arrays.seed_k)
+    letters, offsets = pack_queries(queries)
+    rc, r_counts, r_pos = reference.locate(b.ptr, letters, offsets, threads=2)
+    ix = b.arrays.as_awfm_index()
+    ip = C.addressof(ix)
+    sl = KmerSearchList(lib, len(queries)).fill(letters, offsets)
+    e = sl.entries()
+    roomy = np.arange(0, len(queries), 3)
+    for i in roomy:  # 5000 slots: more than any of these queries' hit counts
+        e["positionList"][i] = libc.realloc(int(e["positionList"][i]), 5000 * 8)
+        e["capacity"][i] = 5000
+    with engine_env(AWFM_GPU_LOCATE_CHUNK_QUERIES=64):
+        assert parallel_search_locate(lib, ip, sl, 4) == rc
+    assert np.array_equal(sl.counts(), r_counts)
+    mine = sl.positions()
+    assert all(np.array_equal(p, q) for p, q in zip(r_pos, mine))
+    expected_capacity = np.maximum(4, r_counts)
+    expected_capacity[roomy] = np.maximum(5000, r_counts[roomy])
+    assert np.array_equal(sl.entries()["capacity"][: len(queries)], expected_capacity)
+    sl.close()
+    lib.awFmGpuReleaseIndex(ip)

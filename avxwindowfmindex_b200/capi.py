@@ -69,6 +69,7 @@ def load():
     lib.awfm_gpu_ctx_device_bytes.restype = u64
     lib.awfm_gpu_ctx_get_stats.argtypes = [vp, C.POINTER(abi.awfm_gpu_stats)]
     lib.awfm_gpu_ctx_set_tuning.argtypes = [vp, C.c_char_p, i64]
+    lib.awfm_gpu_ctx_sweep_stage_ms.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.awfm_gpu_count_host.argtypes = [vp, vp, vp, u32, u64, vp, vp]
     lib.awfm_gpu_locate_host.argtypes = [vp, vp, vp, u32, u64, vp, vp, u64, vp]
     lib.awfm_gpu_count_device.argtypes = [vp, vp, vp, u32, u64, vp, vp, vp]

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <string>
@@ -22,6 +23,7 @@
 
 #include "../../include/awfm_gpu.h"
 #include "awfm_kernels.cuh"
+#include "awfm_sweep.cuh"
 
 using namespace awfm;
 
@@ -72,6 +74,21 @@ struct LocateScratch {  // per-stream scratch of scan + walk (two streams may no
   unsigned long long *dWorkCounter = nullptr;  // locateKernelRefill's chunk dispenser
 };
 
+struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grown on demand, one call at a time
+  uint64_t cap = 0;                       // queries the buffers hold
+  uint32_t *keys[2] = {nullptr, nullptr};  // seed-table index per query, radix-sort double buffer
+  uint64_t *vals[2] = {nullptr, nullptr};  // (remaining letters << 32) | query id
+  uint4 *recs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // two generations x two double-ended arrays
+  uint32_t *ctrl = nullptr;               // [kSweepMaxPasses][4] bucket counters, then the irregular-query counter
+  uint32_t *irregularIds = nullptr;
+  void *sortTemp = nullptr;
+  size_t sortTempBytes = 0;
+  cudaEvent_t done = nullptr;             // end of the last sweep: the next one (possibly on another stream) waits
+  cudaEvent_t stage[kSweepMaxPasses + 4];  // stage boundaries of the most recent call ("sweep_profile")
+  int numStages = 0, stagesRecorded = 0;
+  uint64_t bytes = 0;
+};
+
 struct PipeSlot {  // one in-flight chunk of the search-list engine
   uint8_t *hLetters = nullptr, *dLetters = nullptr;
   uint64_t lettersCap = 0, dLettersCap = 0;
@@ -111,6 +128,9 @@ struct awfm_gpu_ctx {
   int64_t locateInlineHits = 1 << 22;  // a chunk with more hits than this is finished through windows of ...
   int64_t locateWindowHits = 1 << 26;  // ... this many flat hit indices
   LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
+  SweepScratch sweep;
+  int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
+  int sweepSortBits = 16, sweepProfile = 0;
   uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
@@ -400,6 +420,21 @@ static void freeScratch(LocateScratch &sc) {
   sc = LocateScratch();
 }
 
+static void freeSweep(SweepScratch &w) {
+  for (int i = 0; i < 2; i++) {
+    cudaFree(w.keys[i]);
+    cudaFree(w.vals[i]);
+    cudaFree(w.recs[i][0]);
+    cudaFree(w.recs[i][1]);
+  }
+  cudaFree(w.ctrl);
+  cudaFree(w.irregularIds);
+  cudaFree(w.sortTemp);
+  if (w.done) cudaEventDestroy(w.done);
+  for (int i = 0; i < w.numStages; i++) cudaEventDestroy(w.stage[i]);
+  w = SweepScratch();
+}
+
 static void freeSlot(PipeSlot &s) {
   freeScratch(s.sc);
   if (s.hHit) cudaFreeHost(s.hHit);
@@ -437,6 +472,7 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dDeepSeed);
   cudaFree(c->dDenseSa);
   freeScratch(c->sc);
+  freeSweep(c->sweep);
   if (c->hBigPos) cudaFreeHost(c->hBigPos);
   cudaFree(c->dBigPos);
   cudaGetLastError();
@@ -454,6 +490,9 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "count_variant" && (value == 0 || value == 1)) c->countVariant = (int)value;
   else if (k == "locate_variant" && (value == 0 || value == 1)) c->locateVariant = (int)value;
   else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
+  else if (k == "sweep_min_queries") c->sweepMinQueries = value;
+  else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
+  else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
   else if (k == "locate_chunk_queries" && value >= 64 && value <= (1ll << 30)) c->locateChunkQueries = value;
   else if (k == "locate_inline_hits" && value >= 0 && value <= (1ll << 32)) c->locateInlineHits = value;
@@ -584,17 +623,171 @@ static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cu
   return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, c->sc, numHits, dPos, st);
 }
 
+// ---- sweep count path (awfm_sweep.cuh): large fixed-length nucleotide batches, counts only ----
+static uint32_t sweepSeedK(const awfm_gpu_ctx *c, uint32_t len) {
+  return (c->ix.deepSeedK && len >= c->ix.deepSeedK) ? c->ix.deepSeedK : c->ix.seedK;
+}
+static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t len,
+                          uint64_t n, const awfm_range *dRanges) {
+  if (c->sweepMinQueries < 0 || c->countVariant != 1 || c->ix.amino || dOffsets || dRanges) return false;
+  if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
+  if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0xFFFFFFF0ull) return false;
+  const uint32_t k = sweepSeedK(c, len);
+  if (k == 0 || k > 16 || len < k || len - k > 16) return false;
+  // pays off once the batch puts about one query on every 128-B line of the index
+  const uint64_t floorQueries = c->sweepMinQueries > 0 ? (uint64_t)c->sweepMinQueries
+                                                       : std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> 8);
+  return n >= floorQueries;
+}
+
+static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
+  SweepScratch &w = c->sweep;
+  if (!w.done) CU(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+  while (w.numStages < kSweepMaxPasses + 4) {
+    CU(cudaEventCreate(&w.stage[w.numStages]));
+    w.numStages++;
+  }
+  if (!w.ctrl) CU(cudaMalloc(&w.ctrl, (kSweepMaxPasses * 4 + 4) * sizeof(uint32_t)));
+  if (w.cap >= n) return AWFM_GPU_OK;
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < 2; i++) {
+    cudaFree(w.keys[i]);
+    cudaFree(w.vals[i]);
+    cudaFree(w.recs[i][0]);
+    cudaFree(w.recs[i][1]);
+    w.keys[i] = nullptr, w.vals[i] = nullptr, w.recs[i][0] = w.recs[i][1] = nullptr;
+  }
+  cudaFree(w.irregularIds);
+  w.irregularIds = nullptr;
+  c->deviceBytes -= w.bytes;
+  w.bytes = 0;
+  w.cap = 0;
+  const uint64_t cap = n + (n >> 4) + 1024;
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMalloc(&w.keys[i], cap * 4));
+    CU(cudaMalloc(&w.vals[i], cap * 8));
+    CU(cudaMalloc(&w.recs[i][0], cap * 16));
+    CU(cudaMalloc(&w.recs[i][1], cap * 16));
+  }
+  CU(cudaMalloc(&w.irregularIds, cap * 4));
+  w.cap = cap;
+  w.bytes = cap * (2 * (4 + 8 + 32) + 4);
+  c->deviceBytes += w.bytes;
+  return AWFM_GPU_OK;
+}
+
+static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
+                      cudaStream_t st) {
+  if (int r = ensureSweep(c, n)) return r;
+  SweepScratch &w = c->sweep;
+  const uint32_t k = sweepSeedK(c, len), steps = len - k;
+  const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
+  int stage = 0;
+  auto mark = [&]() {
+    if (c->sweepProfile && stage < w.numStages) cudaEventRecord(w.stage[stage++], st);
+  };
+  CU(cudaStreamWaitEvent(st, w.done, 0));
+  mark();
+  CU(cudaMemsetAsync(dCounts, 0, n * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(w.ctrl, 0, (kSweepMaxPasses * 4 + 4) * sizeof(uint32_t), st));
+  uint32_t *irregularCount = w.ctrl + kSweepMaxPasses * 4;
+  {
+    const uint64_t tiles = (n + 255) / 256;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
+    if (len % 4 == 0) {
+      sweepPackWords<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(dLetters), n, len / 4, k, w.keys[0],
+                                           w.vals[0], w.irregularIds, irregularCount);
+    } else {
+      const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
+      sweepPack<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount);
+    }
+    CU(cudaGetLastError());
+  }
+  mark();
+  int cur = 0;
+  const int endBit = 2 * (int)k, beginBit = std::max(0, endBit - c->sweepSortBits);
+  if (endBit > beginBit) {
+    cub::DoubleBuffer<uint32_t> dk(w.keys[0], w.keys[1]);
+    cub::DoubleBuffer<uint64_t> dv(w.vals[0], w.vals[1]);
+    size_t need = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int64_t)n, beginBit, endBit, st));
+    if (need > w.sortTempBytes) {
+      CU(cudaStreamSynchronize(st));
+      cudaFree(w.sortTemp);
+      w.sortTemp = nullptr;
+      w.sortTempBytes = 0;
+      CU(cudaMalloc(&w.sortTemp, need));
+      w.sortTempBytes = need;
+    }
+    size_t have = w.sortTempBytes;
+    CU(cub::DeviceRadixSort::SortPairs(w.sortTemp, have, dk, dv, (int64_t)n, beginBit, endBit, st));
+    cur = dk.selector;
+  }
+  mark();
+  int grid = 0;
+  {
+    auto kf = sweepStep<true>;
+    if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
+  }
+  grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSweepTile - 1) / kSweepTile);
+  auto gen = [&](int g, int pass) {
+    SweepRecs r;
+    r.arr[0] = w.recs[g][0];
+    r.arr[1] = w.recs[g][1];
+    r.count = w.ctrl + 4 * pass;
+    r.cap = w.cap;
+    return r;
+  };
+  sweepStep<true><<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1),
+                                                    gen(0, 0), steps, dCounts);
+  CU(cudaGetLastError());
+  mark();
+  for (uint32_t pass = 1; pass < steps; pass++) {  // pass p does LF step p+1 of the queries still alive
+    sweepStep<false><<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
+                                                       gen(pass & 1, pass), steps - pass, dCounts);
+    CU(cudaGetLastError());
+    mark();
+  }
+  sweepIrregular<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts);
+  CU(cudaGetLastError());
+  mark();
+  CU(cudaEventRecord(w.done, st));
+  w.stagesRecorded = stage;
+  c->stats.launches += 3 + (steps > 1 ? steps - 1 : 0) + (endBit > beginBit ? 3 : 0);
+  return AWFM_GPU_OK;
+}
+
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
                            uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
   if (n == 0) return AWFM_GPU_OK;
   QueryBatch qb{dLetters, dOffsets, n, fixedLen};
   EventPair *ev = nextEvents(c);
   if (ev) CU(cudaEventRecord(ev->a, st));
-  int r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
+  int r;
+  if (sweepEligible(c, dLetters, dOffsets, fixedLen, n, dRanges)) {
+    r = sweepCount(c, dLetters, fixedLen, n, dCounts, st);
+  } else {
+    r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
+    c->stats.launches += 1;
+  }
   if (ev) CU(cudaEventRecord(ev->b, st));
-  c->stats.launches += 1;
   c->stats.queries += n;
   return r;
+}
+
+extern "C" int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *c, double *ms, int capacity) {
+  if (!c || !ms) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = setDevice(c)) return r;
+  SweepScratch &w = c->sweep;
+  int n = 0;
+  for (int i = 0; i + 1 < w.stagesRecorded && n < capacity; i++, n++) {
+    if (cudaEventSynchronize(w.stage[i + 1]) != cudaSuccess) break;
+    float f = 0;
+    if (cudaEventElapsedTime(&f, w.stage[i], w.stage[i + 1]) != cudaSuccess) break;
+    ms[n] = f;
+  }
+  cudaGetLastError();
+  return n;
 }
 
 extern "C" int awfm_gpu_count_device(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets,

@@ -117,6 +117,12 @@ class GpuIndex:
         for k, v in kv.items():
             capi.check(self.lib.awfm_gpu_ctx_set_tuning(self._ctx, k.encode(), int(v)))
 
+    def sweep_stage_ms(self):
+        """Device time (ms) of every stage of the most recent sweep count call made under sweep_profile=1."""
+        ms = (C.c_double * 32)()
+        n = self.lib.awfm_gpu_ctx_sweep_stage_ms(self._ctx, ms, 32)
+        return [ms[i] for i in range(max(n, 0))]
+
     def device_bytes(self):
         return int(self.lib.awfm_gpu_ctx_device_bytes(self._ctx))
 

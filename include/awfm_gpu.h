@@ -114,8 +114,16 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * (0 group-per-hit, 1 group-per-hit with refill), "blocks_per_sm" (0 = occupancy query), "use_deep_seed_table" (0/1:
  * A/B switch for a table already derived with awfm_gpu_ctx_extend_seed_table); of the search-list engine:
  * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
- * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window). */
+ * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
+ * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length nucleotide batches, counts only): "sweep_min_queries"
+ * (0 = automatic: batches of at least max(2^22, bwtLength/256) queries; n > 0 = batches of at least n; -1 = never),
+ * "sweep_sort_bits" (top bits of the seed index the initial radix sort orders, default 16), "sweep_profile" (0/1:
+ * record an event after every stage of the next calls). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
+/* Device time of every stage of the most recent sweep count call made with "sweep_profile" = 1, in launch order:
+ * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.
+ * Returns the number of entries written (<= capacity), 0 when the last count call did not take the sweep path. */
+int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *ctx, double *ms, int capacity);
 
 /* ---- derived structures: spend HBM (180 GB per B200) to remove dependent DRAM round trips.  Both are computed on
  *      the device from the unchanged index with the search kernels' own primitives, hold exactly the values the

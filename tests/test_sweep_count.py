@@ -1,0 +1,108 @@
+"""Sweep count path (csrc/awfm_sweep.cuh): pack -> radix sort on the seed index -> one pass per LF step over records
+bucketed by the next letter.  Forced here on small reference-built indexes (sweep_min_queries=1) and compared bit for
+bit with the oracle and with the tile kernels: counts only depend on the query, not on the order it is processed in."""
+import numpy as np
+import pytest
+
+from avxwindowfmindex_b200 import GpuIndex
+from oracle import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def fixed_batch(b, length, num, seed, irregular=True):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    text = b.text
+    rows = np.empty((num, length), dtype=np.uint8)
+    for i in range(num):
+        if rng.random() < 0.6:
+            s = int(rng.integers(0, len(text) - length))
+            rows[i] = text[s:s + length]
+        else:
+            rows[i] = alphabet[rng.integers(0, 4, length)]
+    if irregular and num >= 40:
+        pick = rng.choice(num, num // 20, replace=False)
+        for j, i in enumerate(pick):
+            col = int(rng.integers(0, length))
+            rows[i, col] = (ord("N"), ord("n"), ord("$"), ord("x"), ord("-"))[j % 5]
+        lower = rng.choice(num, num // 10, replace=False)
+        rows[lower] |= 0x20
+        rows[rng.choice(num, num // 25, replace=False)] = np.frombuffer(b"U", dtype=np.uint8)[0]
+    return rows.reshape(-1)
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r3", "nuc_r16", "nuc_r1"])
+def test_sweep_matches_oracle(small_indexes, name):
+    b = small_indexes[name]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 5, 255), (k + 8, 5000), (k + 16, 1031), (k + 3, 20000)):
+        letters = fixed_batch(b, length, num, seed=length * 31 + num)
+        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        for bits in (16, 0, 3):
+            gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_profile=1)
+            counts = gpu.count(letters, fixed_len=length)
+            assert np.array_equal(counts, o_counts), (name, length, num, bits)
+            assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
+        gpu.set_tuning(sweep_min_queries=-1)
+        assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
+    gpu.close()
+
+
+def test_sweep_falls_back_outside_its_domain(small_indexes):
+    """Too many letters left of the seed, ranges wanted, variable lengths: the tile kernels answer, same results."""
+    b = small_indexes["nuc_r8"]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    gpu.set_tuning(sweep_min_queries=1)
+    letters = fixed_batch(b, k + 17, 300, seed=5)
+    o_counts, o_ranges, _ = oracle.count(letters, fixed_len=k + 17)
+    assert np.array_equal(gpu.count(letters, fixed_len=k + 17), o_counts)
+    letters = fixed_batch(b, k + 4, 300, seed=6)
+    o_counts, o_ranges, _ = oracle.count(letters, fixed_len=k + 4)
+    counts, ranges = gpu.count(letters, fixed_len=k + 4, want_ranges=True)
+    assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges)
+    offsets = np.arange(0, len(letters) + 1, k + 4, dtype=np.uint64)
+    assert np.array_equal(gpu.count(letters, offsets), o_counts)
+    gpu.close()
+
+
+def test_sweep_with_derived_seed_table(small_indexes):
+    b = small_indexes["nuc_r16"]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    gpu.set_tuning(sweep_min_queries=1)
+    gpu.extend_seed_table(k + 3)
+    for length in (k + 1, k + 3, k + 4, k + 11):
+        letters = fixed_batch(b, length, 3000, seed=length)
+        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts), length
+    gpu.close()
+
+
+def test_sweep_repeated_calls_and_streams(small_indexes):
+    """Scratch is reused across calls, grown when a larger batch arrives, and serialised across streams."""
+    import torch
+    b = small_indexes["nuc_r8"]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    gpu.set_tuning(sweep_min_queries=1)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i, num in enumerate((4000, 100, 9000, 9000)):
+        letters = fixed_batch(b, k + 6, num, seed=100 + i)
+        d_letters = torch.from_numpy(letters).cuda()
+        d_counts = torch.full((num,), 7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        gpu.count_device(d_letters.data_ptr(), None, k + 6, num, d_counts.data_ptr(), None, streams[i % 2].cuda_stream)
+        outs.append((letters, d_letters, d_counts))
+    torch.cuda.synchronize()
+    for letters, _, d_counts in outs:
+        o_counts, _, _ = oracle.count(letters, fixed_len=k + 6)
+        assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), o_counts)
+    gpu.close()

@@ -1,0 +1,95 @@
+"""Development probe (run under gpurun): sweep count path vs the tile kernel on the bench workload — total time,
+per-stage device time, sort-bits and batch-size sweeps; every variant's counts compared with the tile kernel's over
+the whole batch.  Writes gpurun_out/sweep_probe.jsonl.  Not part of the product."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from avxwindowfmindex_b200 import DeviceBuiltIndex, abi, capi, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bp", type=int, default=3_100_000_000)
+    ap.add_argument("--queries", type=int, default=100_000_000)
+    ap.add_argument("--kmer", type=int, default=20)
+    ap.add_argument("--seed-k", type=int, default=12)
+    ap.add_argument("--bits", type=str, default="16,24,8,12,20")
+    ap.add_argument("--sizes", type=str, default="50000000,25000000,12500000,4194304")
+    ap.add_argument("--deep", type=int, default=0)
+    args = ap.parse_args()
+    lib = capi.load()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    out = open(os.path.join(ROOT, "gpurun_out", "sweep_probe.jsonl"), "a")
+
+    def emit(row):
+        print(json.dumps(row), flush=True)
+        out.write(json.dumps(row) + "\n")
+        out.flush()
+
+    d_text = torch.empty(args.bp, dtype=torch.uint8, device="cuda")
+    capi.check(lib.awfm_gpu_synth_letters(0, d_text.data_ptr(), args.bp, synth.TEXT_SEED + 2, 0, 0))
+    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), args.bp, abi.AwFmAlphabetDna, args.seed_k, 8)
+    del d_text
+    gpu = built.gpu_index()
+    built.close()
+    torch.cuda.empty_cache()
+    n, L = args.queries, args.kmer
+    d_letters = torch.empty(n * L + 64, dtype=torch.uint8, device="cuda")
+    capi.check(lib.awfm_gpu_synth_letters(0, d_letters.data_ptr(), n * L, synth.QUERY_SEED + 2, 0, 0))
+    d_ref = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(nq, dst, reps=4):
+        best = 1e30
+        for _ in range(reps + 1):
+            a.record(stream)
+            gpu.count_device(d_letters.data_ptr(), None, L, nq, dst.data_ptr(), None, stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    gpu.set_tuning(sweep_min_queries=-1)
+    ms = timed(n, d_ref)
+    emit({"variant": "tile", "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6, "hits": int(d_ref.sum(dtype=torch.int64))})
+    gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
+    for bits in [int(x) for x in args.bits.split(",") if x]:
+        gpu.set_tuning(sweep_sort_bits=bits)
+        d_counts.fill_(-1)
+        ms = timed(n, d_counts)
+        emit({"variant": "sweep", "sort_bits": bits, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
+              "equal_to_tile": bool(torch.equal(d_counts, d_ref)), "device_bytes": gpu.device_bytes()})
+    gpu.set_tuning(sweep_sort_bits=16)
+    for nq in [int(x) for x in args.sizes.split(",") if x]:
+        gpu.set_tuning(sweep_min_queries=-1)
+        t_tile = timed(nq, d_ref, reps=2)
+        gpu.set_tuning(sweep_min_queries=1)
+        d_counts.fill_(-1)
+        t_sweep = timed(nq, d_counts, reps=2)
+        emit({"variant": "size", "queries": nq, "tile_ms": t_tile, "sweep_ms": t_sweep,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
+              "equal_to_tile": bool(torch.equal(d_counts[:nq], d_ref[:nq]))})
+    if args.deep:
+        gpu.extend_seed_table(args.deep)
+        gpu.set_tuning(sweep_min_queries=-1)
+        t_tile = timed(n, d_ref, reps=2)
+        gpu.set_tuning(sweep_min_queries=1)
+        d_counts.fill_(-1)
+        t_sweep = timed(n, d_counts, reps=2)
+        emit({"variant": "deep", "depth": args.deep, "queries": n, "tile_ms": t_tile, "sweep_ms": t_sweep,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()], "equal_to_tile": bool(torch.equal(d_counts, d_ref))})
+    gpu.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@
 #include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/awfm_gpu.h"
@@ -130,7 +131,7 @@ struct awfm_gpu_ctx {
   LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
   SweepScratch sweep;
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
-  int sweepSortBits = 16, sweepProfile = 0;
+  int sweepSortBits = 32, sweepProfile = 0, sweepItems = 4;
   uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
@@ -493,6 +494,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_min_queries") c->sweepMinQueries = value;
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
+  else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
   else if (k == "locate_chunk_queries" && value >= 64 && value <= (1ll << 30)) c->locateChunkQueries = value;
   else if (k == "locate_inline_hits" && value >= 0 && value <= (1ll << 32)) c->locateInlineHits = value;
@@ -631,13 +633,15 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
                           uint64_t n, const awfm_range *dRanges) {
   if (c->sweepMinQueries < 0 || c->countVariant != 1 || c->ix.amino || dOffsets || dRanges) return false;
   if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
-  if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0xFFFFFFF0ull) return false;
+  if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0x70000000ull) return false;  // 32-bit positions and record indices
   const uint32_t k = sweepSeedK(c, len);
   if (k == 0 || k > 16 || len < k || len - k > 16) return false;
-  // pays off once the batch puts about one query on every 128-B line of the index
-  const uint64_t floorQueries = c->sweepMinQueries > 0 ? (uint64_t)c->sweepMinQueries
-                                                       : std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> 8);
-  return n >= floorQueries;
+  if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
+  // automatic: pays off once the batch puts about one query on every 128-B line of the index (measured break-even
+  // at 3.1 Gbp: 12 M queries, profiles/r01_sweep_probe.jsonl).  With a derived deep seed table most of the LF steps
+  // the sweep would stream for are gone already and the tile kernel is the faster of the two.
+  if (c->ix.deepSeedK && len >= c->ix.deepSeedK) return false;
+  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> 8);
 }
 
 static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
@@ -695,8 +699,17 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
     if (len % 4 == 0) {
-      sweepPackWords<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(dLetters), n, len / 4, k, w.keys[0],
-                                           w.vals[0], w.irregularIds, irregularCount);
+      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
+      switch (len / 4) {
+#define AWFM_PACK_CASE(W)                                                                                         \
+  case W:                                                                                                         \
+    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); \
+    break;
+        AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
+        AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
+#undef AWFM_PACK_CASE
+        default: return fail(AWFM_GPU_ERR_ARG, "sweep: query length out of range");
+      }
     } else {
       const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
       sweepPack<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount);
@@ -724,12 +737,6 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
     cur = dk.selector;
   }
   mark();
-  int grid = 0;
-  {
-    auto kf = sweepStep<true>;
-    if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
-  }
-  grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSweepTile - 1) / kSweepTile);
   auto gen = [&](int g, int pass) {
     SweepRecs r;
     r.arr[0] = w.recs[g][0];
@@ -738,14 +745,35 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
     r.cap = w.cap;
     return r;
   };
-  sweepStep<true><<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1),
-                                                    gen(0, 0), steps, dCounts);
-  CU(cudaGetLastError());
-  mark();
-  for (uint32_t pass = 1; pass < steps; pass++) {  // pass p does LF step p+1 of the queries still alive
-    sweepStep<false><<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
-                                                       gen(pass & 1, pass), steps - pass, dCounts);
+  auto launchPass = [&](auto first, auto items, uint32_t pass) -> int {
+    constexpr bool FIRST = decltype(first)::value;
+    constexpr int ITEMS = decltype(items)::value;
+    auto kf = sweepStep<FIRST, ITEMS>;
+    int grid = 0;
+    if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
+    const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
+    if (FIRST)
+      kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
+                                         steps, dCounts);
+    else  // pass p does LF step p+1 of the queries still alive
+      kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
+                                         gen(pass & 1, pass), steps - pass, dCounts);
     CU(cudaGetLastError());
+    return AWFM_GPU_OK;
+  };
+  auto launchPassItems = [&](auto first, uint32_t pass) -> int {
+    switch (c->sweepItems) {
+      case 1: return launchPass(first, std::integral_constant<int, 1>(), pass);
+      case 2: return launchPass(first, std::integral_constant<int, 2>(), pass);
+      case 8: return launchPass(first, std::integral_constant<int, 8>(), pass);
+      default: return launchPass(first, std::integral_constant<int, 4>(), pass);
+    }
+  };
+  if (int r = launchPassItems(std::true_type(), 0)) return r;
+  mark();
+  for (uint32_t pass = 1; pass < steps; pass++) {
+    if (int r = launchPassItems(std::false_type(), pass)) return r;
     mark();
   }
   sweepIrregular<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts);

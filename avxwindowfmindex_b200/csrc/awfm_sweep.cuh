@@ -35,7 +35,7 @@
 
 namespace awfm {
 
-constexpr int kSweepThreads = 256, kSweepItems = 2, kSweepTile = kSweepThreads * kSweepItems;
+constexpr int kSweepThreads = 256;
 constexpr uint32_t kSweepNoId = 0xFFFFFFFFu;
 constexpr int kSweepMaxPasses = 18;
 
@@ -46,29 +46,6 @@ struct SweepRecs {
   uint32_t *count;  // [4] device counters of this generation
   uint64_t cap;
 };
-__device__ __forceinline__ uint64_t sweepSlot(uint64_t cap, uint32_t bucket, uint32_t r) {
-  return (bucket & 1u) ? cap - 1 - (uint64_t)r : (uint64_t)r;
-}
-
-// whole-line loads (no .L2::64B hint): the neighbours of this record want the rest of the line
-__device__ __forceinline__ NucSector sectorIssueFull(const DevIndex &ix, uint64_t p) {
-  const uint4 *s = ix.lines + (p >> 6) * kSectorU4;
-  NucSector x;
-  x.v0 = __ldg(s);
-  x.v1 = __ldg(s + 1);
-  return x;
-}
-// LF step on letters 0..3 with 32-bit positions (bwtLength <= 2^32)
-__device__ __forceinline__ void lfStepSweep(const DevIndex &ix, uint32_t &sp, uint32_t &ep, uint32_t letter) {
-  const uint64_t pa = (uint64_t)sp - 1, pb = ep;
-  const NucSector a = sectorIssueFull(ix, pa), b = sectorIssueFull(ix, pb);
-  const uint64_t ca = __ldg(ix.superC + (pa >> kSectorSuperShift) * kSectorSuperStride + letter);
-  const uint64_t cb = __ldg(ix.superC + (pb >> kSectorSuperShift) * kSectorSuperStride + letter);
-  const uint64_t nsp = ca + sectorCount(a, letter) + sectorPop(a, letter, (uint32_t)pa & 63u);
-  const uint64_t nep = cb + sectorCount(b, letter) + sectorPop(b, letter, (uint32_t)pb & 63u) - 1;
-  sp = (uint32_t)nsp;  // nsp <= bwtLength - 1 + 1; an empty result has nep == nsp - 1, kept as width 0xFFFFFFFF below
-  ep = (uint32_t)nep;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // sweepPackWords: len % 4 == 0 and `letters` 16-B aligned.  One thread per query reads its len/4 words straight from
@@ -88,17 +65,22 @@ __device__ __forceinline__ uint32_t packFourLetters(uint32_t w, uint32_t &bad) {
   t = (t | (t >> 6)) & 0x000F000Fu;
   return (t | (t >> 12)) & 0xFFu;                                          // first letter in bits 7..6
 }
+template <int WORDS>  // words per query (len / 4), fully unrolled
 __global__ void __launch_bounds__(256)
-    sweepPackWords(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t wordsPerQuery, uint32_t k,
-                   uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
+    sweepPackWords(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
+                   uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
                    uint32_t *__restrict__ irregularCount) {
   const uint64_t keyMask = (k >= 16) ? 0xFFFFFFFFull : ((1ull << (2 * k)) - 1ull);
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
        q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t *src = words + q * wordsPerQuery;
+    const uint32_t *src = words + q * WORDS;
+    uint32_t w[WORDS];
+#pragma unroll
+    for (int i = 0; i < WORDS; i++) w[i] = __ldg(src + i);
     uint64_t Q = 0;
     uint32_t bad = 0;
-    for (uint32_t i = 0; i < wordsPerQuery; i++) Q = (Q << 8) | packFourLetters(__ldg(src + i), bad);
+#pragma unroll
+    for (int i = 0; i < WORDS; i++) Q = (Q << 8) | packFourLetters(w[i], bad);
     uint32_t id = (uint32_t)q;
     if (bad) {
       irregularIds[atomicAdd(irregularCount, 1u)] = id;
@@ -167,98 +149,153 @@ __global__ void __launch_bounds__(256)
 // sweepStep: one pass.  FIRST: input = sorted (key, payload) pairs, range from the seed table; else input = the
 // previous generation's buckets in letter order.  `steps` = LF steps the queries of this pass still have to do
 // INCLUDING this pass's (0 only for FIRST with len == k).
+// The pass is issue-bound before it is DRAM-bound (profiles/r01_ncu_sweep_*.json), so everything is 32-bit: positions
+// (bwtLength < 2^32), record indices (n < 2^31), and the rank works on 32-bit halves of the sector with a selector
+// specialised for the four plain letters (same truth table as nucCodeCare: A = b2&b1, C = b2&b0, G = b1&b0,
+// T = ~b2&~b1&b0, src/AwFmOccurrence.c:18-35).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIRST>
+struct SweepSelector {
+  uint32_t flipHi;               // T: match zeros in b2 and b1
+  uint32_t any0, any1, any2;     // A ignores b0, C ignores b1, G ignores b2
+};
+__device__ __forceinline__ SweepSelector sweepSelector(uint32_t letter) {
+  SweepSelector s;
+  s.flipHi = letter == 3u ? 0xFFFFFFFFu : 0u;
+  s.any0 = letter == 0u ? 0xFFFFFFFFu : 0u;
+  s.any1 = letter == 1u ? 0xFFFFFFFFu : 0u;
+  s.any2 = letter == 2u ? 0xFFFFFFFFu : 0u;
+  return s;
+}
+// C[letter] + Occ(letter, p) for letter 0..3, p < 2^32: sector read by this thread, superblock row from L1/L2
+__device__ __forceinline__ uint32_t sweepRank(const DevIndex &ix, uint32_t p, uint32_t letter, const SweepSelector &s) {
+  const uint4 *sec = ix.lines + (uint64_t)(p >> 6) * kSectorU4;
+  const uint4 v0 = __ldg(sec), v1 = __ldg(sec + 1);
+  const uint32_t super = __ldg(reinterpret_cast<const uint32_t *>(ix.superC) +
+                               ((uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter) * 2u);
+  const int local = (int)(p & 63u) + 1;                       // positions 0..local-1 of the sector count
+  const uint32_t maskLo = lowBits(local), maskHi = lowBits(local - 32);
+  const uint32_t lo = ((v0.z ^ s.flipHi) | s.any1) & ((v1.x ^ s.flipHi) | s.any2) & (v0.x | s.any0) & maskLo;
+  const uint32_t hi = ((v0.w ^ s.flipHi) | s.any1) & ((v1.y ^ s.flipHi) | s.any2) & (v0.y | s.any0) & maskHi;
+  const uint32_t rel = (((letter & 2u) ? v1.w : v1.z) >> ((letter & 1u) * 16u)) & 0xFFFFu;
+  return super + rel + __popc(lo) + __popc(hi);
+}
+
+template <bool FIRST, int kSweepItems>
 __global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t *__restrict__ counts) {
+  constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][4];
   __shared__ uint32_t bucketBase[4];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lanesBelow = (1u << lane) - 1u;
+  const uint32_t inLast = (uint32_t)in.cap - 1u, outLast = (uint32_t)out.cap - 1u;
+  const uint4 *in0 = in.arr[0], *in1 = in.arr[1];
+  uint4 *out0 = out.arr[0], *out1 = out.arr[1];
 
-  uint64_t total;
-  uint32_t before1 = 0, before2 = 0, before3 = 0;  // records in the buckets before bucket 1, 2, 3
+  uint32_t total, before1 = 0, before2 = 0, before3 = 0;  // records in the buckets before bucket 1, 2, 3
   if (FIRST) {
-    total = numPairs;
+    total = (uint32_t)numPairs;
   } else {
     const uint32_t c0 = in.count[0], c1 = in.count[1], c2 = in.count[2], c3 = in.count[3];
     before1 = c0;
     before2 = c0 + c1;
     before3 = c0 + c1 + c2;
-    total = (uint64_t)c0 + c1 + c2 + c3;
+    total = before3 + c3;  // <= number of queries < 2^31
   }
 
-  for (uint64_t base = (uint64_t)blockIdx.x * kSweepTile; base < total; base += (uint64_t)gridDim.x * kSweepTile) {
-    uint32_t sp[kSweepItems], ep[kSweepItems], id[kSweepItems], rest[kSweepItems], bucket[kSweepItems],
-        rank[kSweepItems];
+  for (uint32_t base = blockIdx.x * kSweepTile; base < total; base += gridDim.x * kSweepTile) {
+    uint32_t sp[kSweepItems], ep[kSweepItems], id[kSweepItems], rest[kSweepItems], bucket[kSweepItems];
+    // Every load of a stage is issued for all items before anything waits on it (no branches around the loads:
+    // out-of-range items read a clamped, valid address and are disabled afterwards).
+    // ---- stage A: this tile's records / (key, payload) pairs ----
+    [[maybe_unused]] uint32_t key[kSweepItems];
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
-      const uint64_t i = base + (uint64_t)it * kSweepThreads + threadIdx.x;
+      const uint32_t want = base + it * kSweepThreads + threadIdx.x;
+      const uint32_t i = min(want, total - 1u);
+      if (FIRST) {
+        const uint64_t v = __ldg(vals + i);
+        key[it] = __ldg(keys + i);
+        id[it] = (uint32_t)v;
+        rest[it] = (uint32_t)(v >> 32);
+        sp[it] = 1;
+        ep[it] = 0;
+      } else {
+        // bucket of record i and its slot: buckets 0/2 grow up in arrays 0/1, buckets 1/3 grow down from the end
+        const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;
+        const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
+        const bool odd = ge1 != ge2 || ge3;  // bucket 1 or 3
+        const uint32_t r = i - first;
+        const uint4 rec = __ldg((ge2 ? in1 : in0) + (odd ? inLast - r : r));
+        sp[it] = rec.x;
+        ep[it] = rec.x + rec.y;
+        id[it] = rec.z;
+        rest[it] = rec.w;
+      }
+      if (want >= total) id[it] = kSweepNoId;
+    }
+    // ---- stage A2 (first pass): seed-table entries (any key is inside the table) ----
+    if (FIRST) {
+      uint64_t s64[kSweepItems], e64[kSweepItems];
+#pragma unroll
+      for (int it = 0; it < kSweepItems; it++) loadSeedEntry(ix, deep, key[it], s64[it], e64[it]);
+#pragma unroll
+      for (int it = 0; it < kSweepItems; it++) {
+        if (s64[it] > e64[it]) id[it] = kSweepNoId;  // empty seed range: count stays 0
+        if (id[it] != kSweepNoId) sp[it] = (uint32_t)s64[it], ep[it] = (uint32_t)e64[it];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kSweepItems; it++)
+      if (id[it] == kSweepNoId) sp[it] = 1, ep[it] = 0;  // disabled items rank position 0: a valid address
+    // ---- stage B: pull the two sectors of every item towards L1 (no registers, no scoreboard held) ----
+    if (steps > 0) {
+#pragma unroll
+      for (int it = 0; it < kSweepItems; it++) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kSectorU4));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)(ep[it] >> 6) * kSectorU4));
+      }
+    }
+    // ---- stage C: the LF steps (src/AwFmSearch.c:42-103) ----
+#pragma unroll
+    for (int it = 0; it < kSweepItems; it++) {
+      const uint32_t letter = rest[it] & 3u;
+      bool valid = id[it] != kSweepNoId;
+      if (steps > 0) {
+        const SweepSelector sel = sweepSelector(letter);
+        const uint32_t nsp = sweepRank(ix, sp[it] - 1u, letter, sel);
+        const uint32_t nep = sweepRank(ix, ep[it], letter, sel) - 1u;
+        sp[it] = nsp;
+        ep[it] = nep;
+        rest[it] >>= 2;
+        valid = valid && nep != nsp - 1u;  // ep == sp - 1 <=> empty
+      }
       bucket[it] = 4;  // no output
-      sp[it] = 1;
-      ep[it] = 0;
-      id[it] = kSweepNoId;
-      rest[it] = 0;
-      if (i < total) {
-        if (FIRST) {
-          const uint64_t v = __ldg(vals + i);
-          id[it] = (uint32_t)v;
-          rest[it] = (uint32_t)(v >> 32);
-          if (id[it] != kSweepNoId) {
-            uint64_t s64, e64;
-            loadSeedEntry(ix, deep, __ldg(keys + i), s64, e64);
-            sp[it] = (uint32_t)s64;
-            ep[it] = (uint32_t)e64;
-            if (s64 > e64) id[it] = kSweepNoId;  // empty seed range: count stays 0
-          }
-        } else {
-          uint32_t b = 0, first = 0;
-          if (i >= before1) b = 1, first = before1;
-          if (i >= before2) b = 2, first = before2;
-          if (i >= before3) b = 3, first = before3;
-          const uint4 r = in.arr[b >> 1][sweepSlot(in.cap, b, (uint32_t)i - first)];
-          sp[it] = r.x;
-          ep[it] = r.x + r.y;
-          id[it] = r.z;
-          rest[it] = r.w;
-        }
+      if (valid) {
+        if (steps <= 1) counts[id[it]] = ep[it] - sp[it] + 1u;
+        else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
       }
     }
-#pragma unroll
-    for (int it = 0; it < kSweepItems; it++) {
-      if (id[it] != kSweepNoId) {
-        bool valid = true;
-        const uint32_t letter = rest[it] & 3u;
-        if (steps > 0) {
-          lfStepSweep(ix, sp[it], ep[it], letter);
-          rest[it] >>= 2;
-          valid = (ep[it] - sp[it]) != 0xFFFFFFFFu;  // ep == sp - 1 <=> empty (bwtLength < 2^32 - 16)
-        }
-        if (valid) {
-          if (steps <= 1) counts[id[it]] = ep[it] - sp[it] + 1u;
-          else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
-        }
-      }
-    }
+    if (steps <= 1) continue;  // last pass: nothing to append (uniform for the whole grid)
     // ---- stable (inside the tile) append to the four output buckets ----
+    uint32_t rank[kSweepItems];
     __syncthreads();  // warpCount / bucketBase of the previous tile consumed
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
-      rank[it] = 0;
-#pragma unroll
-      for (uint32_t b = 0; b < 4; b++) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, bucket[it] == b);
-        if (bucket[it] == b) rank[it] = __popc(m & lanesBelow);
-        if (lane == 0) warpCount[it][warp][b] = __popc(m);
-      }
+      const unsigned live = __ballot_sync(0xFFFFFFFFu, bucket[it] < 4u);
+      const unsigned bit0 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 1u), bit1 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 2u);
+      const unsigned mine = live & ((bucket[it] & 1u) ? bit0 : ~bit0) & ((bucket[it] & 2u) ? bit1 : ~bit1);
+      rank[it] = __popc(mine & lanesBelow);
+      if (lane < 4) warpCount[it][warp][lane] = __popc(live & ((lane & 1u) ? bit0 : ~bit0) & ((lane & 2u) ? bit1 : ~bit1));
     }
     __syncthreads();
     if (threadIdx.x < 4) {
       uint32_t run = 0;
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++)
+#pragma unroll
         for (int w = 0; w < kSweepThreads / 32; w++) {
           const uint32_t t = warpCount[it][w][threadIdx.x];
           warpCount[it][w][threadIdx.x] = run;
@@ -272,7 +309,7 @@ __global__ void __launch_bounds__(kSweepThreads)
       const uint32_t b = bucket[it];
       if (b < 4) {
         const uint32_t r = bucketBase[b] + warpCount[it][warp][b] + rank[it];
-        out.arr[b >> 1][sweepSlot(out.cap, b, r)] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
+        ((b & 2u) ? out1 : out0)[(b & 1u) ? outLast - r : r] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
       }
     }
   }

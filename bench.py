@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--sa-ratio", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="queries per CPU-baseline pass")
-    ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--count-path", default="auto", choices=["auto", "sweep", "tile"],
+                    help="auto = the library's own choice (sweep for batches this large), tile = force the tile kernel")
     ap.add_argument("--locate-queries", type=int, default=10_000_000, help="cfg 3 leg: random 16-mers located per GPU")
     ap.add_argument("--locate-kmer", type=int, default=16)
     ap.add_argument("--derived-seed-depth", type=int, default=16, help="0 = skip the derived-structures leg")
@@ -128,12 +129,14 @@ def measured_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the count kernel from the committed ncu capture (profiles/), or None."""
+def ncu_traffic_per_launch(path_name):
+    """dram bytes of one count call over the bench batch from the committed ncu capture (profiles/), or None:
+    "tile" = the single countKernelV1 launch, "sweep" = sum over the kernels of the sweep pipeline."""
     path = os.path.join(ROOT, "profiles", "ncu_count_traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("dram_bytes_per_launch")
+            d = json.load(open(path))
+            return d.get("dram_bytes_per_launch" if path_name == "tile" else "sweep_dram_bytes_per_call")
         except Exception:
             return None
     return None
@@ -223,7 +226,7 @@ def workload_config(args, world):
         "workload": f"count: {args.bp} bp synthetic nucleotide index (seed k={args.seed_k}, SA ratio {args.sa_ratio}), "
                     f"{args.queries} random {args.kmer}-mers per GPU (BASELINE.json configs[1])",
         "text_bp": args.bp, "seed_k": args.seed_k, "sa_ratio": args.sa_ratio, "kmer": args.kmer,
-        "queries_per_gpu": args.queries, "parallelism": f"query-sharded x{world}, index replicated per GPU",
+        "queries_per_gpu": args.queries, "parallelism": f"query-sharded x{world}, index replicated per GPU" + ("; counts gathered to rank 0 over NCCL, the gather of step s overlapped with the search of step s+1" if world > 1 else ""),
         "l2_policy": "inputs larger than L2 (index 3.5 GB + packed queries 2 GB per step vs 126 MB L2)",
         "index_built_by": "device builder, byte-identical to the reference's awFmCreateIndex (tests/test_gpu_build_index.py)",
     }
@@ -263,41 +266,51 @@ def run_ours(args):
     capi.check(lib.awfm_gpu_synth_letters(local, d_letters.data_ptr(), n * L, synth.QUERY_SEED + 2, rank * n * L, 0))
     d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-    chunks = args.gather_chunks if world > 1 else 1
-    bounds = [n * i // chunks for i in range(chunks + 1)]
+    if args.count_path != "auto":
+        gpu.set_tuning(sweep_min_queries=1 if args.count_path == "sweep" else -1)
+    # N > 1: every step's counts are gathered onto rank 0 over NCCL/NVLink (the only collective on this path).  The
+    # gather of step s runs on NCCL's stream while step s+1 searches into the other count buffer; the last gather is
+    # drained inside the timed region.
+    bufs = [d_counts, torch.zeros(n, dtype=torch.int32, device=dev)] if world > 1 else [d_counts]
+    works = [None] * len(bufs)
     gathered = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    def step():
-        works = []
-        for c in range(chunks):
-            a, b = bounds[c], bounds[c + 1]
-            gpu.count_device(d_letters.data_ptr() + a * L, None, L, b - a, d_counts.data_ptr() + 4 * a, None,
-                             stream.cuda_stream)
-            if world > 1:  # gather this chunk's counts onto rank 0 while the next chunk is searched
-                works.append(dist.gather(d_counts[a:b], [g[a:b] for g in gathered] if rank == 0 else None, dst=0,
-                                         async_op=True))
-        for w in works:
-            w.wait()
-        return chunks
+    def step(s):
+        b = s % len(bufs)
+        if works[b] is not None:  # the gather that last read this buffer (stream dependency, the host does not block)
+            works[b].wait()
+            works[b] = None
+        gpu.count_device(d_letters.data_ptr(), None, L, n, bufs[b].data_ptr(), None, stream.cuda_stream)
+        if world > 1:
+            works[b] = dist.gather(bufs[b], gathered if rank == 0 else None, dst=0, async_op=True)
 
-    for _ in range(args.warmup):
-        step()
+    def drain():
+        for b, w in enumerate(works):
+            if w is not None:
+                w.wait()
+                works[b] = None
+
+    for s in range(args.warmup):
+        step(s)
+    drain()
     torch.cuda.synchronize()
+    launches_per_step = int(gpu.stats()["launches"])  # kernels of ours in one count call (same for every step)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    launches = 0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     with ClockSampler(local) as clocks:
         ev[0].record(stream)
         for s in range(args.steps):
-            launches += step()
-            ev[s + 1].record(stream)
+            step(s)
+        drain()
+        ev[1].record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = launches_per_step * args.steps
+    total_ms = ev[0].elapsed_time(ev[1])
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,16 +318,33 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
-    # kernel-only duration (one launch over the whole batch) for the roofline, CUDA events on the launching stream
+    # device time of one count call over the whole batch for the roofline, CUDA events on the launching stream
     ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    for _ in range(5):
-        ka.record(stream)
+
+    def count_call_ms(reps=5):
+        out = []
+        for _ in range(reps):
+            ka.record(stream)
+            gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
+            kb.record(stream)
+            torch.cuda.synchronize()
+            out.append(ka.elapsed_time(kb))
+        return sum(out) / len(out)
+
+    kernel_avg = count_call_ms()
+    gpu.set_tuning(sweep_profile=1)
+    gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
+    torch.cuda.synchronize()
+    stage_ms = gpu.sweep_stage_ms()  # [] when the call took the tile kernel
+    gpu.set_tuning(sweep_profile=0)
+    tile_ms = None
+    if stage_ms and args.count_path == "auto":  # the single-kernel path on the same batch, for the record
+        gpu.set_tuning(sweep_min_queries=-1)
         gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
-        kb.record(stream)
+        tile_ms = count_call_ms(reps=3)
+        gpu.set_tuning(sweep_min_queries=0)
+        gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
         torch.cuda.synchronize()
-        kernel_ms.append(ka.elapsed_time(kb))
-    kernel_avg = sum(kernel_ms) / len(kernel_ms)
 
     # ---- second half of BASELINE's metric: located hits/s (configs[2] shape: random 16-mers, this index's SA ratio),
     #      device-resident, ranges -> scan -> expand -> backtrace walk -> positions; outside the timed count steps ----
@@ -557,17 +587,39 @@ def run_ours(args):
         return
     peak, peak_src = measured_peak()
     achieved = (bytes_per_query * n / (kernel_avg * 1e-3) / 1e9) if bytes_per_query else None
-    traffic = ncu_traffic_per_launch()
+    traffic = ncu_traffic_per_launch("sweep" if stage_ms else "tile")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": kernel_avg,
+                "algorithmic_bytes_per_launch": bytes_per_query * n if bytes_per_query else None}
+    if stage_ms:
+        names = ["clear+sweepPack", "radix sort (CUB)", "sweepStep<first>"] + \
+                [f"sweepStep pass {i + 2}" for i in range(len(stage_ms) - 4)] + ["sweepIrregular"]
+        roofline["kernel"] = ("sweep pipeline, one count call over the rank's whole batch: pack -> radix sort on the seed "
+                              "index -> one sweepStep pass per LF step (csrc/awfm_sweep.cuh)")
+        roofline["stages_ms"] = {k: round(v, 3) for k, v in zip(names, stage_ms)}
+        roofline["note"] = ("algorithmic bytes (SURVEY 8d) charge every rank its own 104-B block read; the sweep orders the "
+                            "live queries by range start, so queries on the same 128-B line share one DRAM fetch and the "
+                            "index is streamed once per pass: achieved/peak may exceed 1, `traffic` is what DRAM really "
+                            "moved (sum over the pipeline's kernels, ncu)")
+        if traffic:
+            roofline["dram_GBps"] = traffic / (kernel_avg * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_GBps"] / peak
+        if tile_ms and bytes_per_query:
+            t_traffic = ncu_traffic_per_launch("tile")
+            roofline["tile_kernel"] = {"kernel": "countKernelV1 (one launch, one random line per rank)", "kernel_ms": tile_ms,
+                                       "queries_per_s": n / tile_ms * 1e3,
+                                       "achieved": bytes_per_query * n / (tile_ms * 1e-3) / 1e9,
+                                       "frac": bytes_per_query * n / (tile_ms * 1e-3) / 1e9 / peak, "traffic": t_traffic}
+    else:
+        roofline["kernel"] = "countKernelV1 (one launch over the rank's whole batch)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "countKernel (one launch over the rank's whole batch)", "kernel_ms": kernel_avg,
-                     "algorithmic_bytes_per_launch": bytes_per_query * n if bytes_per_query else None},
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "index": {"device_bytes": gpu.device_bytes(), "build_s": round(build_s, 2), "build_gpu_ms": round(build_ms, 1),
                   "tie_suffixes_resolved_on_host": tie_suffixes},

@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--bits", type=str, default="16,24,8,12,20")
     ap.add_argument("--sizes", type=str, default="50000000,25000000,12500000,4194304")
     ap.add_argument("--deep", type=int, default=0)
+    ap.add_argument("--items", type=str, default="4")
+    ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--no-tile", action="store_true")
+    ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
     lib = capi.load()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -48,7 +52,7 @@ def main():
     stream = torch.cuda.current_stream()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(nq, dst, reps=4):
+    def timed(nq, dst, reps=args.reps):
         best = 1e30
         for _ in range(reps + 1):
             a.record(stream)
@@ -59,17 +63,25 @@ def main():
         return best
 
     gpu.set_tuning(sweep_min_queries=-1)
-    ms = timed(n, d_ref)
-    emit({"variant": "tile", "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6, "hits": int(d_ref.sum(dtype=torch.int64))})
+    ms = 0.0 if args.no_tile else timed(n, d_ref)
+    emit({"variant": "tile", "queries": n, "ms": ms, "Gq_per_s": n / max(ms, 1e-9) / 1e6, "hits": int(d_ref.sum(dtype=torch.int64))})
     gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
-    for bits in [int(x) for x in args.bits.split(",") if x]:
-        gpu.set_tuning(sweep_sort_bits=bits)
+    for items, bits in [(int(i), int(x)) for i in args.items.split(",") for x in args.bits.split(",") if x]:
+        gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items)
         d_counts.fill_(-1)
         ms = timed(n, d_counts)
-        emit({"variant": "sweep", "sort_bits": bits, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+        emit({"variant": "sweep", "sort_bits": bits, "items": items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
-              "equal_to_tile": bool(torch.equal(d_counts, d_ref)), "device_bytes": gpu.device_bytes()})
-    gpu.set_tuning(sweep_sort_bits=16)
+              "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
+              "device_bytes": gpu.device_bytes()})
+    if args.nvtx:
+        gpu.set_tuning(sweep_sort_bits=32, sweep_items=4, sweep_profile=0)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("sweepcall")
+        gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+    gpu.set_tuning(sweep_sort_bits=32)
     for nq in [int(x) for x in args.sizes.split(",") if x]:
         gpu.set_tuning(sweep_min_queries=-1)
         t_tile = timed(nq, d_ref, reps=2)

@@ -131,7 +131,7 @@ struct awfm_gpu_ctx {
   LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
   SweepScratch sweep;
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
-  int sweepSortBits = 32, sweepProfile = 0, sweepItems = 4;
+  int sweepSortBits = 32, sweepLocalBits = 8, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
   uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
@@ -494,7 +494,9 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_min_queries") c->sweepMinQueries = value;
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
+  else if (k == "sweep_local_bits" && value >= 0 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
+  else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
   else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
   else if (k == "locate_chunk_queries" && value >= 64 && value <= (1ll << 30)) c->locateChunkQueries = value;
   else if (k == "locate_inline_hits" && value >= 0 && value <= (1ll << 32)) c->locateInlineHits = value;
@@ -718,7 +720,10 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
   }
   mark();
   int cur = 0;
-  const int endBit = 2 * (int)k, beginBit = std::max(0, endBit - c->sweepSortBits);
+  // the radix sort orders the key's top bits; the first pass finishes up to 8 more inside each tile (shared memory)
+  const int endBit = 2 * (int)k;
+  const uint32_t localBits = (uint32_t)std::min({c->sweepLocalBits, endBit, 8});
+  const int beginBit = std::max(0, endBit - std::min(c->sweepSortBits, endBit - (int)localBits));
   if (endBit > beginBit) {
     cub::DoubleBuffer<uint32_t> dk(w.keys[0], w.keys[1]);
     cub::DoubleBuffer<uint64_t> dv(w.vals[0], w.vals[1]);
@@ -755,15 +760,15 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
-                                         steps, dCounts);
+                                         steps, localBits, dCounts);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
-                                         gen(pass & 1, pass), steps - pass, dCounts);
+                                         gen(pass & 1, pass), steps - pass, 0u, dCounts);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   };
   auto launchPassItems = [&](auto first, uint32_t pass) -> int {
-    switch (c->sweepItems) {
+    switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
       case 1: return launchPass(first, std::integral_constant<int, 1>(), pass);
       case 2: return launchPass(first, std::integral_constant<int, 2>(), pass);
       case 8: return launchPass(first, std::integral_constant<int, 8>(), pass);

@@ -184,10 +184,15 @@ template <bool FIRST, int kSweepItems>
 __global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
-              uint32_t steps, uint32_t *__restrict__ counts) {
+              uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts) {
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][4];
   __shared__ uint32_t bucketBase[4];
+  // first pass only: tile-local counting sort on the key bits the global radix sort left unordered
+  __shared__ uint32_t localBins[FIRST ? 1024 : 1];
+  __shared__ uint32_t localKeys[FIRST ? kSweepTile : 1];
+  __shared__ uint64_t localVals[FIRST ? kSweepTile : 1];
+  __shared__ uint32_t localWarpSum[kSweepThreads / 32];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lanesBelow = (1u << lane) - 1u;
   const uint32_t inLast = (uint32_t)in.cap - 1u, outLast = (uint32_t)out.cap - 1u;
@@ -235,6 +240,63 @@ __global__ void __launch_bounds__(kSweepThreads)
         rest[it] = rec.w;
       }
       if (want >= total) id[it] = kSweepNoId;
+    }
+    // ---- stage A1 (first pass, optional): finish the ordering inside the tile.  The radix sort ordered the pairs
+    //      by the key bits above `localBits`; here the tile's pairs are counting-sorted in shared memory by
+    //      (distance of those upper bits from the tile's first pair, clamped to 3) : (low localBits bits), so a
+    //      warp's 32 consecutive pairs touch a handful of neighbouring lines instead of 32 scattered ones.  Order is
+    //      a locality matter only — the result of a query does not depend on it. ----
+    if constexpr (FIRST) {
+      if (localBits) {  // uniform
+        uint32_t val32[kSweepItems][2], lk[kSweepItems], pos[kSweepItems];
+        const uint32_t firstUpper = __ldg(keys + base) >> localBits;
+        for (uint32_t b = threadIdx.x; b < 1024; b += kSweepThreads) localBins[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kSweepItems; it++) {
+          const uint32_t delta = min((key[it] >> localBits) - firstUpper, 3u);
+          lk[it] = base + it * kSweepThreads + threadIdx.x >= total  // padding of the last tile goes to the end
+                       ? 1023u : ((delta << localBits) | (key[it] & ((1u << localBits) - 1u)));
+          pos[it] = atomicAdd(&localBins[lk[it]], 1u);
+          val32[it][0] = id[it];
+          val32[it][1] = rest[it];
+        }
+        __syncthreads();
+        {  // exclusive scan of the 1024 bins: 4 consecutive bins per thread, warp scan, warp totals
+          const uint32_t b0 = localBins[4 * threadIdx.x], b1 = localBins[4 * threadIdx.x + 1],
+                         b2 = localBins[4 * threadIdx.x + 2], b3 = localBins[4 * threadIdx.x + 3];
+          const uint32_t mine = b0 + b1 + b2 + b3;
+          uint32_t incl = mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (unsigned)d) incl += up;
+          }
+          if (lane == 31) localWarpSum[warp] = incl;
+          __syncthreads();
+          uint32_t start = incl - mine;
+          for (unsigned w = 0; w < warp; w++) start += localWarpSum[w];
+          localBins[4 * threadIdx.x] = start;
+          localBins[4 * threadIdx.x + 1] = start + b0;
+          localBins[4 * threadIdx.x + 2] = start + b0 + b1;
+          localBins[4 * threadIdx.x + 3] = start + b0 + b1 + b2;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kSweepItems; it++) {
+          const uint32_t dst = localBins[lk[it]] + pos[it];
+          localKeys[dst] = key[it];
+          localVals[dst] = ((uint64_t)val32[it][1] << 32) | val32[it][0];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kSweepItems; it++) {
+          const uint32_t src = it * kSweepThreads + threadIdx.x;
+          key[it] = localKeys[src];
+          id[it] = (uint32_t)localVals[src];
+          rest[it] = (uint32_t)(localVals[src] >> 32);
+        }
+      }
     }
     // ---- stage A2 (first pass): seed-table entries (any key is inside the table) ----
     if (FIRST) {

@@ -117,7 +117,8 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
  * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length nucleotide batches, counts only): "sweep_min_queries"
  * (0 = automatic: batches of at least max(2^22, bwtLength/256) queries; n > 0 = batches of at least n; -1 = never),
- * "sweep_sort_bits" (top bits of the seed index the initial radix sort orders, default 32 = all), "sweep_items"
+ * "sweep_sort_bits" (top bits of the seed index the initial radix sort orders, default 32 = all but the low
+ * "sweep_local_bits"), "sweep_local_bits" (0..8, default 8: low bits ordered inside each tile of the first pass instead), "sweep_items"
  * (records per thread and tile pass: 1, 2, 4, 8; default 4), "sweep_profile" (0/1:
  * record an event after every stage of the next calls). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);

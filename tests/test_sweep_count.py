@@ -41,10 +41,11 @@ def test_sweep_matches_oracle(small_indexes, name):
     for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 5, 255), (k + 8, 5000), (k + 16, 1031), (k + 3, 20000)):
         letters = fixed_batch(b, length, num, seed=length * 31 + num)
         o_counts, _, _ = oracle.count(letters, fixed_len=length)
-        for bits in (16, 0, 3):
-            gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_profile=1)
+        for bits, local, items in ((32, 8, 4), (16, 0, 2), (0, 8, 1), (3, 5, 8), (32, 0, 4)):
+            gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_local_bits=local, sweep_items=items,
+                           sweep_profile=1)
             counts = gpu.count(letters, fixed_len=length)
-            assert np.array_equal(counts, o_counts), (name, length, num, bits)
+            assert np.array_equal(counts, o_counts), (name, length, num, bits, local, items)
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
         gpu.set_tuning(sweep_min_queries=-1)
         assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--deep", type=int, default=0)
     ap.add_argument("--items", type=str, default="4")
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--local", type=str, default="8")
+    ap.add_argument("--first-items", type=int, default=4)
     ap.add_argument("--no-tile", action="store_true")
     ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
@@ -66,11 +68,12 @@ def main():
     ms = 0.0 if args.no_tile else timed(n, d_ref)
     emit({"variant": "tile", "queries": n, "ms": ms, "Gq_per_s": n / max(ms, 1e-9) / 1e6, "hits": int(d_ref.sum(dtype=torch.int64))})
     gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
-    for items, bits in [(int(i), int(x)) for i in args.items.split(",") for x in args.bits.split(",") if x]:
-        gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items)
+    for items, bits, local in [(int(i), int(x), int(l)) for i in args.items.split(",") for x in args.bits.split(",") if x
+                               for l in args.local.split(",")]:
+        gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items, sweep_local_bits=local, sweep_first_items=args.first_items)
         d_counts.fill_(-1)
         ms = timed(n, d_counts)
-        emit({"variant": "sweep", "sort_bits": bits, "items": items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+        emit({"variant": "sweep", "sort_bits": bits, "local_bits": local, "items": items, "first_items": args.first_items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
               "device_bytes": gpu.device_bytes()})

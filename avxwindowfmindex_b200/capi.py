@@ -20,6 +20,7 @@ GPU_SYMBOLS = [
     "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
     "awfm_gpu_ctx_create_from_file", "awfm_gpu_ctx_set_sequences", "awfm_gpu_ctx_extend_seed_table",
     "awfm_gpu_ctx_densify_suffix_array", "awfm_gpu_map_positions_device", "awfm_gpu_map_positions_host",
+    "awfm_gpu_ctx_sweep_stage_ms",
 ]
 DROPIN_SYMBOLS = [
     "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",

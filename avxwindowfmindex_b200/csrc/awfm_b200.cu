@@ -77,6 +77,7 @@ struct LocateScratch {  // per-stream scratch of scan + walk (two streams may no
 
 struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grown on demand, one call at a time
   uint64_t cap = 0;                       // queries the buffers hold
+  void *arena = nullptr;                  // one allocation carved into the buffers below
   uint32_t *keys[2] = {nullptr, nullptr};  // seed-table index per query, radix-sort double buffer
   uint64_t *vals[2] = {nullptr, nullptr};  // (remaining letters << 32) | query id
   uint4 *recs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // two generations x two double-ended arrays
@@ -101,6 +102,7 @@ struct PipeSlot {  // one in-flight chunk of the search-list engine
   cudaEvent_t done = nullptr;
   uint64_t first = 0, n = 0;
   bool busy = false;
+  bool ready = false;  // count engine: D2H complete, counts not scattered yet
   // locate pipeline: hit offsets and positions of the chunk, both sides of the bus
   LocateScratch sc;
   uint64_t *hHit = nullptr, *dHit = nullptr, hitCap = 0;
@@ -124,13 +126,14 @@ struct awfm_gpu_ctx {
   bool hasSa = false;
   // tuning
   int countLpq = 2, locateLpq = 2, countVariant = 1, locateVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
-  int64_t chunkQueries = 1 << 18;
+  int64_t chunkQueries = 1 << 16;
   int64_t locateChunkQueries = 1 << 18;
   int64_t locateInlineHits = 1 << 22;  // a chunk with more hits than this is finished through windows of ...
   int64_t locateWindowHits = 1 << 26;  // ... this many flat hit indices
   LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
   SweepScratch sweep;
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
+  int64_t sweepMaxBatch = 1ll << 27;
   int sweepSortBits = 32, sweepLocalBits = 8, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
   uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
@@ -422,14 +425,8 @@ static void freeScratch(LocateScratch &sc) {
 }
 
 static void freeSweep(SweepScratch &w) {
-  for (int i = 0; i < 2; i++) {
-    cudaFree(w.keys[i]);
-    cudaFree(w.vals[i]);
-    cudaFree(w.recs[i][0]);
-    cudaFree(w.recs[i][1]);
-  }
+  cudaFree(w.arena);
   cudaFree(w.ctrl);
-  cudaFree(w.irregularIds);
   cudaFree(w.sortTemp);
   if (w.done) cudaEventDestroy(w.done);
   for (int i = 0; i < w.numStages; i++) cudaEventDestroy(w.stage[i]);
@@ -492,6 +489,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "locate_variant" && (value == 0 || value == 1)) c->locateVariant = (int)value;
   else if (k == "blocks_per_sm" && value >= 0 && value <= 32) c->blocksPerSm = (int)value;
   else if (k == "sweep_min_queries") c->sweepMinQueries = value;
+  else if (k == "sweep_max_batch" && value >= 256 && value <= (1ll << 30)) c->sweepMaxBatch = value;
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "sweep_local_bits" && value >= 0 && value <= 8) c->sweepLocalBits = (int)value;
@@ -656,35 +654,32 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
   if (!w.ctrl) CU(cudaMalloc(&w.ctrl, (kSweepMaxPasses * 4 + 4) * sizeof(uint32_t)));
   if (w.cap >= n) return AWFM_GPU_OK;
   CU(cudaDeviceSynchronize());
-  for (int i = 0; i < 2; i++) {
-    cudaFree(w.keys[i]);
-    cudaFree(w.vals[i]);
-    cudaFree(w.recs[i][0]);
-    cudaFree(w.recs[i][1]);
-    w.keys[i] = nullptr, w.vals[i] = nullptr, w.recs[i][0] = w.recs[i][1] = nullptr;
-  }
-  cudaFree(w.irregularIds);
-  w.irregularIds = nullptr;
+  cudaFree(w.arena);
+  w.arena = nullptr;
   c->deviceBytes -= w.bytes;
   w.bytes = 0;
   w.cap = 0;
-  const uint64_t cap = n + (n >> 4) + 1024;
-  for (int i = 0; i < 2; i++) {
-    CU(cudaMalloc(&w.keys[i], cap * 4));
-    CU(cudaMalloc(&w.vals[i], cap * 8));
-    CU(cudaMalloc(&w.recs[i][0], cap * 16));
-    CU(cudaMalloc(&w.recs[i][1], cap * 16));
+  const uint64_t cap = (n + (n >> 4) + 1024 + 15) & ~15ull;  // multiple of 16 records: every carved buffer 64-B aligned
+  const uint64_t bytes = cap * (2 * 4 + 2 * 8 + 4 * 16 + 4);
+  if (cudaMalloc(&w.arena, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    w.arena = nullptr;
+    return fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");
   }
-  CU(cudaMalloc(&w.irregularIds, cap * 4));
+  uint8_t *p = static_cast<uint8_t *>(w.arena);
+  for (int g = 0; g < 2; g++)
+    for (int a = 0; a < 2; a++) w.recs[g][a] = reinterpret_cast<uint4 *>(p), p += cap * 16;
+  for (int i = 0; i < 2; i++) w.vals[i] = reinterpret_cast<uint64_t *>(p), p += cap * 8;
+  for (int i = 0; i < 2; i++) w.keys[i] = reinterpret_cast<uint32_t *>(p), p += cap * 4;
+  w.irregularIds = reinterpret_cast<uint32_t *>(p);
   w.cap = cap;
-  w.bytes = cap * (2 * (4 + 8 + 32) + 4);
-  c->deviceBytes += w.bytes;
+  w.bytes = bytes;
+  c->deviceBytes += bytes;
   return AWFM_GPU_OK;
 }
 
-static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
-                      cudaStream_t st) {
-  if (int r = ensureSweep(c, n)) return r;
+static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
+                           cudaStream_t st) {
   SweepScratch &w = c->sweep;
   const uint32_t k = sweepSeedK(c, len), steps = len - k;
   const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
@@ -790,6 +785,16 @@ static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, ui
   return AWFM_GPU_OK;
 }
 
+// Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query).
+static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
+                      cudaStream_t st) {
+  const uint64_t slice = std::min<uint64_t>(n, (uint64_t)c->sweepMaxBatch & ~255ull);  // slices start 16-B aligned
+  if (int r = ensureSweep(c, slice)) return r;
+  for (uint64_t first = 0; first < n; first += slice)
+    if (int r = sweepCountBatch(c, dLetters + first * len, len, std::min(slice, n - first), dCounts + first, st)) return r;
+  return AWFM_GPU_OK;
+}
+
 static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
                            uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
   if (n == 0) return AWFM_GPU_OK;
@@ -797,9 +802,10 @@ static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint6
   EventPair *ev = nextEvents(c);
   if (ev) CU(cudaEventRecord(ev->a, st));
   int r;
-  if (sweepEligible(c, dLetters, dOffsets, fixedLen, n, dRanges)) {
-    r = sweepCount(c, dLetters, fixedLen, n, dCounts, st);
-  } else {
+  const bool sweep = sweepEligible(c, dLetters, dOffsets, fixedLen, n, dRanges);
+  r = sweep ? sweepCount(c, dLetters, fixedLen, n, dCounts, st) : AWFM_GPU_OK;
+  if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
+    c->sweep.stagesRecorded = 0;
     r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
     c->stats.launches += 1;
   }
@@ -1309,7 +1315,8 @@ static void teamPackPrepare(TeamPack &tp, PipeSlot &s, const awfm_kmer_search_da
 static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
   const awfm_kmer_search_data *d0 = tp.d0;
   const uint64_t n = tp.n, len0 = tp.len0;
-  const uint64_t a = n * t / T, b = n * (t + 1) / T;
+  const bool worker = t >= 0;  // t < 0: a thread that only keeps the team's barriers (the count engine's driver)
+  const uint64_t a = worker ? n * t / T : 0, b = worker ? n * (t + 1) / T : 0;
   if (n && tp.rc == AWFM_GPU_OK && tp.optimistic) {
     bool uni = true, con = true;
     if (tp.direct) {
@@ -1354,7 +1361,7 @@ static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
     } else if (!tp.optimistic || !tp.uniformAll) {
       uint64_t sum = 0;
       for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
-      tp.partSum[t + 1] = sum;
+      if (worker) tp.partSum[t + 1] = sum;
 #pragma omp barrier
 #pragma omp master
       {
@@ -1408,11 +1415,16 @@ static int teamSize(uint32_t numThreads, uint64_t n, uint64_t chunk) {
   return (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(1, numThreads), std::min(n, chunk) / 64));
 }
 
-// awFmParallelSearchCount over the reference's list layout.  One persistent OpenMP region runs the whole call: per
-// chunk the calling thread (the only one that talks to CUDA) waits for the slot that is being recycled, then ALL
-// threads scatter that slot's counts into the entries and pack the next chunk, then the calling thread ships it.
-// Chunks are small (default 2^18 queries / 3 slots in flight) so the 32-B entries written by the scatter are still
-// in the host caches from the packing pass two chunks earlier.
+// awFmParallelSearchCount over the reference's list layout.  One persistent OpenMP region runs the whole call in
+// rounds, one chunk entering the pipeline per round, ONE team-wide synchronisation point per round besides the one
+// inside teamPack():
+//   workers (all threads but the calling one when the team has more than 4): scatter the counts of chunk r-LAG into the
+//            32-B entries (src/AwFmParallelSearch.c:187-190), then pack chunk r;
+//   driver  (the calling thread, the only one that talks to CUDA), meanwhile: ship chunk r-1 (H2D, kernel, D2H on the
+//            slot's stream), prepare the packing of chunk r+1, wait for the D2H of chunk r-LAG+1.
+// Nothing the driver does is on the workers' critical path unless the GPU falls LAG-2 rounds behind.  Chunks are small
+// (default 2^16 queries) so the entries written by the scatter are still in the packing thread's L2 from LAG rounds
+// earlier: the list is read from DRAM once and written back once (tools/host_list_floor.c measures that floor).
 extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
                                           uint32_t numThreads) {
   if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
@@ -1423,84 +1435,94 @@ extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data
   const uint64_t chunk = (uint64_t)c->chunkQueries;
   const uint64_t numChunks = (n + chunk - 1) / chunk;
   const int T = teamSize(numThreads, n, chunk);
-  constexpr int NS = 3;
+  constexpr uint64_t LAG = 4;
+  constexpr int NS = awfm_gpu_ctx::kSlots;  // >= LAG + 2: a slot is prepared again only after its counts were scattered
+  static_assert(NS >= (int)LAG + 2, "count pipeline needs LAG + 2 slots");
+  const bool dual = T <= 4;                 // small teams: the calling thread drives the GPU and packs as well
+  const int W = dual ? T : T - 1;           // packing / scattering threads
   const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
   const double tStart = omp_get_wtime();
-  double tWait = 0, tWork = 0, tSubmit = 0;
+  double tDriver = 0, tWait = 0, tWork = 0;
 
-  // state shared by the team (written by the calling thread between barriers)
-  int rc = AWFM_GPU_OK;
-  uint64_t oldFirst = 0, oldN = 0;  // chunk whose counts are scattered this round
-  const uint32_t *oldCounts = nullptr;
-  uint64_t newFirst = 0;            // chunk packed this round
-  TeamPack tp;
-  tp.partSum.assign(T + 1, 0);
+  int rc = AWFM_GPU_OK;  // written by the driver only; workers act on per-slot / per-chunk state published at barriers
+  TeamPack tps[2];
+  tps[0].partSum.assign(W + 1, 0);
+  tps[1].partSum.assign(W + 1, 0);
+  for (auto &s : c->slots) s.busy = s.ready = false;
+  teamPackPrepare(tps[0], c->slots[0], data, std::min(chunk, n), sourcePinned, false);
+  if (tps[0].rc != AWFM_GPU_OK) return tps[0].rc;
 
 #pragma omp parallel num_threads(T)
   {
     const int t = omp_get_thread_num();
-    for (uint64_t ci = 0; ci < numChunks + NS; ci++) {
-      PipeSlot &s = c->slots[ci % NS];
-#pragma omp master
-      {
-        const double t0 = omp_get_wtime();
-        oldN = 0;
-        if (s.busy) {  // recycle the slot: its D2H has to be complete
-          if (rc == AWFM_GPU_OK && cudaEventSynchronize(s.done) != cudaSuccess)
-            rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", "event synchronize failed");
-          else if (rc != AWFM_GPU_OK) cudaEventSynchronize(s.done);
-          if (rc == AWFM_GPU_OK) oldFirst = s.first, oldN = s.n, oldCounts = s.hCounts;
-          s.busy = false;
-        }
-        tp.n = 0;
-        if (ci < numChunks && rc == AWFM_GPU_OK) {
-          newFirst = ci * chunk;
-          teamPackPrepare(tp, s, data + newFirst, std::min(chunk, n - newFirst), sourcePinned, false);
-          if (tp.rc != AWFM_GPU_OK) rc = tp.rc;
-        }
-        tWait += omp_get_wtime() - t0;
-      }
-#pragma omp barrier
-      const double w0 = omp_get_wtime();
-      if (oldN) {  // src/AwFmParallelSearch.c:187-190: count = range length, stored as uint32
-        awfm_kmer_search_data *dst = data + oldFirst;
-        const uint64_t a = oldN * t / T, b = oldN * (t + 1) / T;
-        for (uint64_t i = a; i < b; i++) dst[i].count = oldCounts[i];
-      }
-      teamPack(tp, s, t, T);
-      const double w1 = omp_get_wtime();
-#pragma omp master
-      {
-        tWork += w1 - w0;
-        if (tp.n && tp.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = tp.rc;
-        if (tp.n && rc == AWFM_GPU_OK) {
-          const Packed pk = teamPackResult(tp, s, T);
-          s.first = newFirst, s.n = tp.n;
-          rc = submitCount(c, s, pk, false);
-          if (rc == AWFM_GPU_OK) {
-            cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
-            if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
-            if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
-            else {
-              c->stats.d2hBytes += s.n * 4;
-              s.busy = true;
+    const bool driver = t == 0, worker = dual || t > 0;
+    const int wi = dual ? t : t - 1;
+    for (uint64_t r = 0; r < numChunks + LAG; r++) {
+      TeamPack &tp = tps[r & 1];  // chunk r (tp.n == 0: none)
+      if (driver) {
+        const double d0 = omp_get_wtime();
+        if (r >= 1 && r - 1 < numChunks) {  // ship chunk r-1, packed in the previous round
+          TeamPack &done = tps[(r - 1) & 1];
+          PipeSlot &s = c->slots[(r - 1) % NS];
+          if (done.n && done.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = done.rc;
+          if (done.n && rc == AWFM_GPU_OK) {
+            const Packed pk = teamPackResult(done, s, W);
+            s.first = (r - 1) * chunk, s.n = done.n, s.ready = false;
+            rc = submitCount(c, s, pk, false);
+            if (rc == AWFM_GPU_OK) {
+              cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
+              if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+              if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
+              else {
+                c->stats.d2hBytes += s.n * 4;
+                s.busy = true;
+              }
             }
           }
         }
-        tSubmit += omp_get_wtime() - w1;
+        TeamPack &next = tps[(r + 1) & 1];  // chunk r+1 is packed next round
+        next.n = 0;
+        if (r + 1 < numChunks && rc == AWFM_GPU_OK) {
+          const uint64_t first = (r + 1) * chunk;
+          teamPackPrepare(next, c->slots[(r + 1) % NS], data + first, std::min(chunk, n - first), sourcePinned, false);
+          if (next.rc != AWFM_GPU_OK) rc = next.rc, next.n = 0;
+        }
+        const double d1 = omp_get_wtime();
+        if (r + 1 >= LAG && r + 1 - LAG < numChunks) {  // chunk r+1-LAG is scattered next round: its D2H must be complete
+          PipeSlot &s = c->slots[(r + 1 - LAG) % NS];
+          if (s.busy) {
+            const bool ok = cudaEventSynchronize(s.done) == cudaSuccess;
+            if (!ok && rc == AWFM_GPU_OK) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", "event synchronize failed");
+            s.busy = false;
+            s.ready = ok && rc == AWFM_GPU_OK;
+          }
+        }
+        tDriver += d1 - d0;
+        tWait += omp_get_wtime() - d1;
       }
+      const double w0 = omp_get_wtime();
+      if (worker && r >= LAG) {  // src/AwFmParallelSearch.c:187-190: count = range length, stored as uint32
+        PipeSlot &s = c->slots[(r - LAG) % NS];
+        if (s.ready) {
+          awfm_kmer_search_data *dst = data + s.first;
+          const uint32_t *src = s.hCounts;
+          const uint64_t a = s.n * wi / W, b = s.n * (wi + 1) / W;
+          for (uint64_t i = a; i < b; i++) dst[i].count = src[i];
+        }
+      }
+      teamPack(tp, c->slots[r % NS], worker ? wi : -1, W);
+      if (t == T - 1) tWork += omp_get_wtime() - w0;
 #pragma omp barrier
     }
   }
-  for (auto &s : c->slots)  // only reachable with rc != OK: never leave a DMA in flight
-    if (s.busy) {
-      cudaStreamSynchronize(s.stream);
-      s.busy = false;
-    }
+  for (auto &s : c->slots) {  // busy slots are only left behind with rc != OK: never leave a DMA in flight
+    if (s.busy) cudaStreamSynchronize(s.stream);
+    s.busy = s.ready = false;
+  }
   if (getenv("AWFM_GPU_VERBOSE"))
-    fprintf(stderr, "[awfm_gpu] count list: %llu queries, %llu chunks, %d threads, pinned=%d: total %.1f ms = wait %.1f + scatter/pack %.1f + submit %.1f\n",
-            (unsigned long long)n, (unsigned long long)numChunks, T, (int)sourcePinned, 1e3 * (omp_get_wtime() - tStart),
-            1e3 * tWait, 1e3 * tWork, 1e3 * tSubmit);
+    fprintf(stderr, "[awfm_gpu] count list: %llu queries, %llu chunks, %d threads (%d packing), pinned=%d: total %.1f ms; driver: submit+prepare %.1f, wait %.1f; last worker: scatter/pack incl. barrier waits %.1f\n",
+            (unsigned long long)n, (unsigned long long)numChunks, T, W, (int)sourcePinned, 1e3 * (omp_get_wtime() - tStart),
+            1e3 * tDriver, 1e3 * tWait, 1e3 * tWork);
   return rc;
 }
 

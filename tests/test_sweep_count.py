@@ -71,6 +71,22 @@ def test_sweep_falls_back_outside_its_domain(small_indexes):
     gpu.close()
 
 
+def test_sweep_slices_large_batches(small_indexes):
+    """A batch larger than sweep_max_batch goes through the scratch in slices; slice starts stay 16-B aligned."""
+    b = small_indexes["nuc_r8"]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    for length in (k + 3, k + 6):
+        letters = fixed_batch(b, length, 5000, seed=77 + length)
+        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        for max_batch in (256, 1000, 4999, 5000):
+            gpu.set_tuning(sweep_min_queries=1, sweep_max_batch=max_batch, sweep_profile=1)
+            assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts), (length, max_batch)
+            assert gpu.sweep_stage_ms()
+    gpu.close()
+
+
 def test_sweep_with_derived_seed_table(small_indexes):
     b = small_indexes["nuc_r16"]
     k = b.arrays.seed_k

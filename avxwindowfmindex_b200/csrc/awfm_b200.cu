@@ -723,7 +723,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     cub::DoubleBuffer<uint32_t> dk(w.keys[0], w.keys[1]);
     cub::DoubleBuffer<uint64_t> dv(w.vals[0], w.vals[1]);
     size_t need = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int64_t)n, beginBit, endBit, st));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, beginBit, endBit, st));
     if (need > w.sortTempBytes) {
       CU(cudaStreamSynchronize(st));
       cudaFree(w.sortTemp);
@@ -733,7 +733,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
       w.sortTempBytes = need;
     }
     size_t have = w.sortTempBytes;
-    CU(cub::DeviceRadixSort::SortPairs(w.sortTemp, have, dk, dv, (int64_t)n, beginBit, endBit, st));
+    CU(cub::DeviceRadixSort::SortPairs(w.sortTemp, have, dk, dv, (int)n, beginBit, endBit, st));
     cur = dk.selector;
   }
   mark();
@@ -766,7 +766,9 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
       case 1: return launchPass(first, std::integral_constant<int, 1>(), pass);
       case 2: return launchPass(first, std::integral_constant<int, 2>(), pass);
+#if AWFM_SWEEP_THREADS <= 256  // 8 records per thread of a 512-thread CTA would need more than 48 KB of static shared memory
       case 8: return launchPass(first, std::integral_constant<int, 8>(), pass);
+#endif
       default: return launchPass(first, std::integral_constant<int, 4>(), pass);
     }
   };

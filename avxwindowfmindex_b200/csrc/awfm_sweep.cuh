@@ -35,7 +35,10 @@
 
 namespace awfm {
 
-constexpr int kSweepThreads = 256;
+#ifndef AWFM_SWEEP_THREADS
+#define AWFM_SWEEP_THREADS 256
+#endif
+constexpr int kSweepThreads = AWFM_SWEEP_THREADS;  // 256 or 512 (measured: profiles/r01_sweep_probe.jsonl)
 constexpr uint32_t kSweepNoId = 0xFFFFFFFFu;
 constexpr int kSweepMaxPasses = 18;
 
@@ -262,10 +265,11 @@ __global__ void __launch_bounds__(kSweepThreads)
           val32[it][1] = rest[it];
         }
         __syncthreads();
-        {  // exclusive scan of the 1024 bins: 4 consecutive bins per thread, warp scan, warp totals
-          const uint32_t b0 = localBins[4 * threadIdx.x], b1 = localBins[4 * threadIdx.x + 1],
-                         b2 = localBins[4 * threadIdx.x + 2], b3 = localBins[4 * threadIdx.x + 3];
-          const uint32_t mine = b0 + b1 + b2 + b3;
+        {  // exclusive scan of the 1024 bins: consecutive bins per thread, warp scan, warp totals
+          constexpr int kPer = 1024 / kSweepThreads;
+          uint32_t bin[kPer], mine = 0;
+#pragma unroll
+          for (int j = 0; j < kPer; j++) bin[j] = localBins[kPer * threadIdx.x + j], mine += bin[j];
           uint32_t incl = mine;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -276,10 +280,8 @@ __global__ void __launch_bounds__(kSweepThreads)
           __syncthreads();
           uint32_t start = incl - mine;
           for (unsigned w = 0; w < warp; w++) start += localWarpSum[w];
-          localBins[4 * threadIdx.x] = start;
-          localBins[4 * threadIdx.x + 1] = start + b0;
-          localBins[4 * threadIdx.x + 2] = start + b0 + b1;
-          localBins[4 * threadIdx.x + 3] = start + b0 + b1 + b2;
+#pragma unroll
+          for (int j = 0; j < kPer; j++) localBins[kPer * threadIdx.x + j] = start, start += bin[j];
         }
         __syncthreads();
 #pragma unroll

@@ -80,7 +80,8 @@ struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grow
   void *arena = nullptr;                  // one allocation carved into the buffers below
   uint32_t *keys[2] = {nullptr, nullptr};  // seed-table index per query, radix-sort double buffer
   uint64_t *vals[2] = {nullptr, nullptr};  // (remaining letters << 32) | query id
-  uint4 *recs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // two generations x two double-ended arrays
+  uint4 *recs[2][kSweepMaxArrays] = {};   // two generations x (2 | 10) double-ended arrays
+  int arrays = 0;                         // arrays per generation the arena was carved for
   uint32_t *ctrl = nullptr;               // [kSweepMaxPasses][4] bucket counters, then the irregular-query counter
   uint32_t *irregularIds = nullptr;
   void *sortTemp = nullptr;
@@ -134,7 +135,7 @@ struct awfm_gpu_ctx {
   SweepScratch sweep;
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
   int64_t sweepMaxBatch = 1ll << 27;
-  int sweepSortBits = 32, sweepLocalBits = 8, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
+  int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
   uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
   std::vector<EventPair> kernelEvents;  // of the most recent call
   size_t eventsUsed = 0;
@@ -492,7 +493,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_max_batch" && value >= 256 && value <= (1ll << 30)) c->sweepMaxBatch = value;
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
-  else if (k == "sweep_local_bits" && value >= 0 && value <= 8) c->sweepLocalBits = (int)value;
+  else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
   else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
@@ -629,30 +630,42 @@ static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cu
 static uint32_t sweepSeedK(const awfm_gpu_ctx *c, uint32_t len) {
   return (c->ix.deepSeedK && len >= c->ix.deepSeedK) ? c->ix.deepSeedK : c->ix.seedK;
 }
+static uint32_t sweepKeyBits(const awfm_gpu_ctx *c, uint32_t k) {  // bits of a seed-table index of depth k
+  if (!c->ix.amino) return 2 * k;
+  uint64_t entries = 1;
+  for (uint32_t i = 0; i < k; i++) entries *= 20;
+  uint32_t bits = 0;
+  while ((1ull << bits) < entries) bits++;
+  return bits;
+}
 static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t len,
                           uint64_t n, const awfm_range *dRanges) {
-  if (c->sweepMinQueries < 0 || c->countVariant != 1 || c->ix.amino || dOffsets || dRanges) return false;
+  if (c->sweepMinQueries < 0 || c->countVariant != 1 || dOffsets || dRanges) return false;
   if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
   if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0x70000000ull) return false;  // 32-bit positions and record indices
   const uint32_t k = sweepSeedK(c, len);
-  if (k == 0 || k > 16 || len < k || len - k > 16) return false;
+  if (c->ix.amino) {  // 5 bits per remaining letter in a 32-bit payload, 20^k seed entries in a 32-bit key
+    if (k == 0 || k > 7 || len < k || len - k > 6 || len > 64) return false;
+  } else if (k == 0 || k > 16 || len < k || len - k > 16) {
+    return false;
+  }
   if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
   // automatic: pays off once the batch puts about one query on every 128-B line of the index (measured break-even
   // at 3.1 Gbp: 12 M queries, profiles/r01_sweep_probe.jsonl).  With a derived deep seed table most of the LF steps
   // the sweep would stream for are gone already and the tile kernel is the faster of the two.
   if (c->ix.deepSeedK && len >= c->ix.deepSeedK) return false;
-  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> 8);
+  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : 8));
 }
 
-static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
+static int ensureSweep(awfm_gpu_ctx *c, uint64_t n, int arrays) {
   SweepScratch &w = c->sweep;
   if (!w.done) CU(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   while (w.numStages < kSweepMaxPasses + 4) {
     CU(cudaEventCreate(&w.stage[w.numStages]));
     w.numStages++;
   }
-  if (!w.ctrl) CU(cudaMalloc(&w.ctrl, (kSweepMaxPasses * 4 + 4) * sizeof(uint32_t)));
-  if (w.cap >= n) return AWFM_GPU_OK;
+  if (!w.ctrl) CU(cudaMalloc(&w.ctrl, (kSweepMaxPasses * kSweepCtrlStride + 4) * sizeof(uint32_t)));
+  if (w.cap >= n && w.arrays == arrays) return AWFM_GPU_OK;
   CU(cudaDeviceSynchronize());
   cudaFree(w.arena);
   w.arena = nullptr;
@@ -660,7 +673,7 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
   w.bytes = 0;
   w.cap = 0;
   const uint64_t cap = (n + (n >> 4) + 1024 + 15) & ~15ull;  // multiple of 16 records: every carved buffer 64-B aligned
-  const uint64_t bytes = cap * (2 * 4 + 2 * 8 + 4 * 16 + 4);
+  const uint64_t bytes = cap * (2 * 4 + 2 * 8 + 2 * (uint64_t)arrays * 16 + 4);
   if (cudaMalloc(&w.arena, bytes) != cudaSuccess) {
     cudaGetLastError();
     w.arena = nullptr;
@@ -668,16 +681,18 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n) {
   }
   uint8_t *p = static_cast<uint8_t *>(w.arena);
   for (int g = 0; g < 2; g++)
-    for (int a = 0; a < 2; a++) w.recs[g][a] = reinterpret_cast<uint4 *>(p), p += cap * 16;
+    for (int a = 0; a < arrays; a++) w.recs[g][a] = reinterpret_cast<uint4 *>(p), p += cap * 16;
   for (int i = 0; i < 2; i++) w.vals[i] = reinterpret_cast<uint64_t *>(p), p += cap * 8;
   for (int i = 0; i < 2; i++) w.keys[i] = reinterpret_cast<uint32_t *>(p), p += cap * 4;
   w.irregularIds = reinterpret_cast<uint32_t *>(p);
   w.cap = cap;
+  w.arrays = arrays;
   w.bytes = bytes;
   c->deviceBytes += bytes;
   return AWFM_GPU_OK;
 }
 
+template <bool AMINO>
 static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
                            cudaStream_t st) {
   SweepScratch &w = c->sweep;
@@ -690,12 +705,12 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
   CU(cudaStreamWaitEvent(st, w.done, 0));
   mark();
   CU(cudaMemsetAsync(dCounts, 0, n * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(w.ctrl, 0, (kSweepMaxPasses * 4 + 4) * sizeof(uint32_t), st));
-  uint32_t *irregularCount = w.ctrl + kSweepMaxPasses * 4;
+  CU(cudaMemsetAsync(w.ctrl, 0, (kSweepMaxPasses * kSweepCtrlStride + 4) * sizeof(uint32_t), st));
+  uint32_t *irregularCount = w.ctrl + kSweepMaxPasses * kSweepCtrlStride;
   {
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
-    if (len % 4 == 0) {
+    if (!AMINO && len % 4 == 0) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
 #define AWFM_PACK_CASE(W)                                                                                         \
@@ -709,15 +724,26 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
       }
     } else {
       const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
-      sweepPack<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount);
+      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount);
     }
     CU(cudaGetLastError());
   }
   mark();
   int cur = 0;
   // the radix sort orders the key's top bits; the first pass finishes up to 8 more inside each tile (shared memory)
-  const int endBit = 2 * (int)k;
-  const uint32_t localBits = (uint32_t)std::min({c->sweepLocalBits, endBit, 8});
+  const int endBit = (int)sweepKeyBits(c, k);
+  // Low key bits left to the first pass's tile-local sort.  Automatic: as many as keep a group of equal upper bits
+  // within about two 1024-pair tiles (beyond that the tiles of a group interleave too many runs for the warps to
+  // coalesce), then trimmed to what saves a whole 8-bit radix pass.
+  int wantLocal = c->sweepLocalBits;
+  if (wantLocal < 0) {
+    wantLocal = 0;
+    while (wantLocal < 8 && wantLocal < endBit && (double)n * (double)(2u << wantLocal) <= 2048.0 * (double)(1ull << endBit))
+      wantLocal++;
+    const int radixPasses = (endBit - wantLocal + 7) / 8;
+    wantLocal = std::max(0, endBit - 8 * radixPasses);
+  }
+  const uint32_t localBits = (uint32_t)std::min({wantLocal, endBit, 8});
   const int beginBit = std::max(0, endBit - std::min(c->sweepSortBits, endBit - (int)localBits));
   if (endBit > beginBit) {
     cub::DoubleBuffer<uint32_t> dk(w.keys[0], w.keys[1]);
@@ -739,16 +765,15 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
   mark();
   auto gen = [&](int g, int pass) {
     SweepRecs r;
-    r.arr[0] = w.recs[g][0];
-    r.arr[1] = w.recs[g][1];
-    r.count = w.ctrl + 4 * pass;
+    for (int a = 0; a < kSweepMaxArrays; a++) r.arr[a] = w.recs[g][a];
+    r.count = w.ctrl + kSweepCtrlStride * pass;
     r.cap = w.cap;
     return r;
   };
   auto launchPass = [&](auto first, auto items, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
-    auto kf = sweepStep<FIRST, ITEMS>;
+    auto kf = sweepStep<FIRST, ITEMS, AMINO>;
     int grid = 0;
     if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
     const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
@@ -778,7 +803,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     if (int r = launchPassItems(std::false_type(), pass)) return r;
     mark();
   }
-  sweepIrregular<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts);
+  sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts);
   CU(cudaGetLastError());
   mark();
   CU(cudaEventRecord(w.done, st));
@@ -787,13 +812,20 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
   return AWFM_GPU_OK;
 }
 
-// Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query).
+// Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
+// slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
 static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
                       cudaStream_t st) {
-  const uint64_t slice = std::min<uint64_t>(n, (uint64_t)c->sweepMaxBatch & ~255ull);  // slices start 16-B aligned
-  if (int r = ensureSweep(c, slice)) return r;
-  for (uint64_t first = 0; first < n; first += slice)
-    if (int r = sweepCountBatch(c, dLetters + first * len, len, std::min(slice, n - first), dCounts + first, st)) return r;
+  const bool amino = c->ix.amino != 0;
+  const uint64_t maxBatch = amino ? std::min<int64_t>(c->sweepMaxBatch, 1ll << 26) : c->sweepMaxBatch;
+  const uint64_t slice = std::min<uint64_t>(n, maxBatch & ~255ull);  // slices start 16-B aligned
+  if (int r = ensureSweep(c, slice, amino ? 10 : 2)) return r;
+  for (uint64_t first = 0; first < n; first += slice) {
+    const uint64_t m = std::min(slice, n - first);
+    const int r = amino ? sweepCountBatch<true>(c, dLetters + first * len, len, m, dCounts + first, st)
+                        : sweepCountBatch<false>(c, dLetters + first * len, len, m, dCounts + first, st);
+    if (r) return r;
+  }
   return AWFM_GPU_OK;
 }
 

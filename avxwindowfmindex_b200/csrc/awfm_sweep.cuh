@@ -1,4 +1,5 @@
-// awfm_sweep.cuh — the "sweep" count path for LARGE batches of fixed-length nucleotide queries (sm_100a).
+// awfm_sweep.cuh — the "sweep" count path for LARGE batches of fixed-length queries (sm_100a).  Described for the
+// nucleotide alphabet; amino indexes take the same path with 20 buckets and 5-bit letters (SweepAlphabet<true>).
 //
 // The tile kernels of awfm_kernels.cuh pay one random DRAM line per rank: 1 + 5.64 lines per 20-mer at 3.1 Gbp, and
 // the memory system delivers ~42 G random lines/s whatever their size (profiles/r01_granularity_probe.jsonl), so they
@@ -28,8 +29,8 @@
 // gathered line by line, and all other traffic (keys, records) is sequential.  No spin-waits anywhere.
 //
 // Exactness: same seed entries, same ranks (sectorRank), same stop rule; only the processing order differs, and the
-// result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels): amino
-// indexes, variable-length batches, range output, bwtLength > 2^32, len - k > 16, k > 16.
+// result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels):
+// variable-length batches, range output, bwtLength > 2^32, len - k > 16 (amino: 6), k > 16 (amino: 7).
 #pragma once
 #include "awfm_kernels.cuh"
 
@@ -43,11 +44,19 @@ constexpr uint32_t kSweepNoId = 0xFFFFFFFFu;
 constexpr int kSweepMaxPasses = 18;
 
 // One generation of live records: bucket b (= letter prepended last) lives in arr[b >> 1]; even buckets grow up
-// from slot 0, odd ones down from slot cap-1, so four buckets of unknown sizes share 2 x cap slots (total <= cap).
+// from slot 0, odd ones down from slot cap-1, so two buckets of unknown sizes share cap slots (total <= cap).
+// Nucleotide: 4 buckets in 2 arrays; amino: 20 buckets in 10 arrays.
+constexpr int kSweepMaxArrays = 10;
+constexpr int kSweepCtrlStride = 32;  // device counters reserved per generation (4 or 20 used)
 struct SweepRecs {
-  uint4 *arr[2];
-  uint32_t *count;  // [4] device counters of this generation
+  uint4 *arr[kSweepMaxArrays];
+  uint32_t *count;  // [4 | 20] device counters of this generation
   uint64_t cap;
+};
+template <bool AMINO>
+struct SweepAlphabet {
+  static constexpr uint32_t kCard = AMINO ? 20u : 4u;       // plain letters = buckets
+  static constexpr uint32_t kLetterBits = AMINO ? 5u : 2u;  // per remaining letter in the payload
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -97,10 +106,12 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------
 // sweepPack: 256 queries per tile staged through shared memory with coalesced 128-bit loads.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool AMINO>  // amino: key = mixed-radix seed index (radix 20), 5 bits per remaining letter
 __global__ void __launch_bounds__(256)
     sweepPack(const uint8_t *__restrict__ letters, uint64_t numQueries, uint32_t len, uint32_t k,
               uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
               uint32_t *__restrict__ irregularCount) {
+  constexpr uint32_t CARD = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   extern __shared__ __align__(16) uint8_t sLetters[];  // 256 * len bytes, rounded up to 16
   const uint64_t numTiles = (numQueries + 255) / 256;
   const uint64_t totalBytes = numQueries * (uint64_t)len;
@@ -128,14 +139,14 @@ __global__ void __launch_bounds__(256)
       const uint8_t *s = sLetters + threadIdx.x * len;
       uint32_t key = 0, packed = 0, bad = 0;
       for (uint32_t i = 0; i < k; i++) {  // leftmost of the last k letters most significant
-        const uint32_t l = nucLetterIndex(s[rest + i]);
-        bad |= l >> 2;
-        key = (key << 2) | (l & 3u);
+        const uint32_t l = letterIndex<AMINO>(s[rest + i]);
+        bad |= l >= CARD;
+        key = key * CARD + (l < CARD ? l : 0u);
       }
       for (uint32_t j = 0; j < rest; j++) {  // letter prepended at step j+1 is s[rest-1-j]: low bits first
-        const uint32_t l = nucLetterIndex(s[rest - 1 - j]);
-        bad |= l >> 2;
-        packed |= (l & 3u) << (2 * j);
+        const uint32_t l = letterIndex<AMINO>(s[rest - 1 - j]);
+        bad |= l >= CARD;
+        packed |= (l < CARD ? l : 0u) << (LB * j);
       }
       uint32_t id = (uint32_t)(q0 + threadIdx.x);
       if (bad) {
@@ -183,14 +194,51 @@ __device__ __forceinline__ uint32_t sweepRank(const DevIndex &ix, uint32_t p, ui
   return super + rel + __popc(lo) + __popc(hi);
 }
 
-template <bool FIRST, int kSweepItems>
+// Amino: one thread reads the code bits and the letter's count of one 128-B quarter-line (awfm_device.cuh): uint4 0/1 =
+// b0..b3 of the low/high 32 positions, words 8/9 = b4, word 11+c = count of letter c.  Selector = (code, care) of
+// kAminoCodeCare, the same the tile kernels use (src/AwFmOccurrence.c:65-134).
+struct AminoSweepSelector {
+  uint32_t flip[5], any[5];
+};
+__device__ __forceinline__ AminoSweepSelector aminoSweepSelector(uint32_t codeCare) {
+  AminoSweepSelector s;
+  const uint32_t code = codeCare & 0xFFu, care = codeCare >> 8;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    s.flip[i] = ((code >> i) & 1u) - 1u;  // code bit 1 -> keep, 0 -> invert
+    s.any[i] = ((care >> i) & 1u) - 1u;   // cared -> 0, ignored -> ~0
+  }
+  return s;
+}
+__device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t p, uint32_t letter,
+                                                   const AminoSweepSelector &s) {
+  const uint4 *line = ix.lines + (uint64_t)(p >> 6) * kAminoLineU4;
+  const uint4 v0 = __ldg(line), v1 = __ldg(line + 1);
+  const uint2 b4 = __ldg(reinterpret_cast<const uint2 *>(line + 2));
+  const uint32_t rel = __ldg(reinterpret_cast<const uint32_t *>(line) + kAminoRelWord + letter);
+  const uint32_t super = (uint32_t)__ldg(ix.superC + (uint64_t)(p >> kSuperShift) * kAminoSuperStride + letter);
+  const int local = (int)(p & 63u) + 1;
+  const uint32_t maskLo = lowBits(local), maskHi = lowBits(local - 32);
+  const uint32_t lo = ((v0.x ^ s.flip[0]) | s.any[0]) & ((v0.y ^ s.flip[1]) | s.any[1]) & ((v0.z ^ s.flip[2]) | s.any[2]) &
+                      ((v0.w ^ s.flip[3]) | s.any[3]) & ((b4.x ^ s.flip[4]) | s.any[4]) & maskLo;
+  const uint32_t hi = ((v1.x ^ s.flip[0]) | s.any[0]) & ((v1.y ^ s.flip[1]) | s.any[1]) & ((v1.z ^ s.flip[2]) | s.any[2]) &
+                      ((v1.w ^ s.flip[3]) | s.any[3]) & ((b4.y ^ s.flip[4]) | s.any[4]) & maskHi;
+  return super + rel + __popc(lo) + __popc(hi);
+}
+
+template <bool FIRST, int kSweepItems, bool AMINO = false>
 __global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts) {
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
-  __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][4];
-  __shared__ uint32_t bucketBase[4];
+  constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
+  constexpr uint32_t kLetterMask = (1u << LB) - 1u;
+  constexpr uint32_t kLineU4 = AMINO ? kAminoLineU4 : kSectorU4;
+  __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][NB];
+  __shared__ uint32_t bucketBase[NB];
+  __shared__ uint32_t inPrefixSh[AMINO ? 33 : 1];  // amino: records before bucket b, padded with the total
+  __shared__ uint16_t codeCareSh[AMINO ? 32 : 1];  // amino: kAminoCodeCare, lanes index it with different letters
   // first pass only: tile-local counting sort on the key bits the global radix sort left unordered
   __shared__ uint32_t localBins[FIRST ? 1024 : 1];
   __shared__ uint32_t localKeys[FIRST ? kSweepTile : 1];
@@ -203,7 +251,18 @@ __global__ void __launch_bounds__(kSweepThreads)
   uint4 *out0 = out.arr[0], *out1 = out.arr[1];
 
   uint32_t total, before1 = 0, before2 = 0, before3 = 0;  // records in the buckets before bucket 1, 2, 3
-  if (FIRST) {
+  if constexpr (AMINO) {
+    if (threadIdx.x < 21) codeCareSh[threadIdx.x] = kAminoCodeCare[threadIdx.x];
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (uint32_t b = 0; b < 33; b++) {
+        inPrefixSh[b] = run;
+        if (!FIRST && b < NB) run += in.count[b];
+      }
+    }
+    __syncthreads();
+    total = FIRST ? (uint32_t)numPairs : inPrefixSh[32];
+  } else if (FIRST) {
     total = (uint32_t)numPairs;
   } else {
     const uint32_t c0 = in.count[0], c1 = in.count[1], c2 = in.count[2], c3 = in.count[3];
@@ -230,6 +289,17 @@ __global__ void __launch_bounds__(kSweepThreads)
         rest[it] = (uint32_t)(v >> 32);
         sp[it] = 1;
         ep[it] = 0;
+      } else if constexpr (AMINO) {
+        uint32_t b = 0;  // bucket of record i: binary search over the padded prefix counts
+#pragma unroll
+        for (uint32_t step = 16; step > 0; step >>= 1)
+          if (i >= inPrefixSh[b + step]) b += step;
+        const uint32_t r = i - inPrefixSh[b];
+        const uint4 rec = __ldg(in.arr[b >> 1] + ((b & 1u) ? inLast - r : r));
+        sp[it] = rec.x;
+        ep[it] = rec.x + rec.y;
+        id[it] = rec.z;
+        rest[it] = rec.w;
       } else {
         // bucket of record i and its slot: buckets 0/2 grow up in arrays 0/1, buckets 1/3 grow down from the end
         const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;
@@ -318,44 +388,64 @@ __global__ void __launch_bounds__(kSweepThreads)
     if (steps > 0) {
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kSectorU4));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)(ep[it] >> 6) * kSectorU4));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kLineU4));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)(ep[it] >> 6) * kLineU4));
       }
     }
     // ---- stage C: the LF steps (src/AwFmSearch.c:42-103) ----
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
-      const uint32_t letter = rest[it] & 3u;
+      const uint32_t letter = AMINO ? min(rest[it] & kLetterMask, NB - 1u) : (rest[it] & kLetterMask);
       bool valid = id[it] != kSweepNoId;
       if (steps > 0) {
-        const SweepSelector sel = sweepSelector(letter);
-        const uint32_t nsp = sweepRank(ix, sp[it] - 1u, letter, sel);
-        const uint32_t nep = sweepRank(ix, ep[it], letter, sel) - 1u;
+        uint32_t nsp, nep;
+        if constexpr (AMINO) {
+          const AminoSweepSelector sel = aminoSweepSelector(codeCareSh[letter]);
+          nsp = aminoSweepRank(ix, sp[it] - 1u, letter, sel);
+          nep = aminoSweepRank(ix, ep[it], letter, sel) - 1u;
+        } else {
+          const SweepSelector sel = sweepSelector(letter);
+          nsp = sweepRank(ix, sp[it] - 1u, letter, sel);
+          nep = sweepRank(ix, ep[it], letter, sel) - 1u;
+        }
         sp[it] = nsp;
         ep[it] = nep;
-        rest[it] >>= 2;
+        rest[it] >>= LB;
         valid = valid && nep != nsp - 1u;  // ep == sp - 1 <=> empty
       }
-      bucket[it] = 4;  // no output
+      bucket[it] = NB;  // no output
       if (valid) {
         if (steps <= 1) counts[id[it]] = ep[it] - sp[it] + 1u;
         else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
       }
     }
     if (steps <= 1) continue;  // last pass: nothing to append (uniform for the whole grid)
-    // ---- stable (inside the tile) append to the four output buckets ----
+    // ---- stable (inside the tile) append to the output buckets ----
     uint32_t rank[kSweepItems];
     __syncthreads();  // warpCount / bucketBase of the previous tile consumed
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
-      const unsigned live = __ballot_sync(0xFFFFFFFFu, bucket[it] < 4u);
-      const unsigned bit0 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 1u), bit1 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 2u);
-      const unsigned mine = live & ((bucket[it] & 1u) ? bit0 : ~bit0) & ((bucket[it] & 2u) ? bit1 : ~bit1);
-      rank[it] = __popc(mine & lanesBelow);
-      if (lane < 4) warpCount[it][warp][lane] = __popc(live & ((lane & 1u) ? bit0 : ~bit0) & ((lane & 2u) ? bit1 : ~bit1));
+      if constexpr (AMINO) {
+        const uint32_t b = bucket[it];
+        unsigned mine = __ballot_sync(0xFFFFFFFFu, b < NB), forLane = mine;  // lanes in my bucket / in bucket `lane`
+#pragma unroll
+        for (uint32_t bit = 0; bit < LB; bit++) {
+          const unsigned m = __ballot_sync(0xFFFFFFFFu, (b >> bit) & 1u);
+          mine &= ((b >> bit) & 1u) ? m : ~m;
+          forLane &= ((lane >> bit) & 1u) ? m : ~m;
+        }
+        rank[it] = __popc(mine & lanesBelow);
+        if (lane < NB) warpCount[it][warp][lane] = __popc(forLane);
+      } else {
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, bucket[it] < 4u);
+        const unsigned bit0 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 1u), bit1 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 2u);
+        const unsigned mine = live & ((bucket[it] & 1u) ? bit0 : ~bit0) & ((bucket[it] & 2u) ? bit1 : ~bit1);
+        rank[it] = __popc(mine & lanesBelow);
+        if (lane < 4) warpCount[it][warp][lane] = __popc(live & ((lane & 1u) ? bit0 : ~bit0) & ((lane & 2u) ? bit1 : ~bit1));
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < NB) {
       uint32_t run = 0;
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++)
@@ -371,9 +461,10 @@ __global__ void __launch_bounds__(kSweepThreads)
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
       const uint32_t b = bucket[it];
-      if (b < 4) {
+      if (b < NB) {
         const uint32_t r = bucketBase[b] + warpCount[it][warp][b] + rank[it];
-        ((b & 2u) ? out1 : out0)[(b & 1u) ? outLast - r : r] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
+        uint4 *dst = AMINO ? out.arr[b >> 1] : ((b & 2u) ? out1 : out0);
+        dst[(b & 1u) ? outLast - r : r] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
       }
     }
   }
@@ -381,6 +472,7 @@ __global__ void __launch_bounds__(kSweepThreads)
 
 // Queries the sweep does not take (ambiguity letters, '$', anything not A/C/G/T/U): the reference's own order of
 // business for one query (countKernelV0's body), one thread per listed id.
+template <bool AMINO>
 __global__ void __launch_bounds__(256)
     sweepIrregular(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ letters, uint32_t len,
                    const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
@@ -390,15 +482,15 @@ __global__ void __launch_bounds__(256)
     const uint32_t q = ids[i];
     const uint8_t *s = letters + (uint64_t)q * len;
     uint64_t sp, ep;
-    uint64_t next = openRange<false>(ix, s, len, sp, ep);
+    uint64_t next = openRange<AMINO>(ix, s, len, sp, ep);
     while (next > 0 && sp <= ep) {
-      const uint32_t letter = nucLetterIndex(__ldg(s + next - 1));
-      if (letter > 4u) {
+      const uint32_t letter = letterIndex<AMINO>(__ldg(s + next - 1));
+      if (letter > SweepAlphabet<AMINO>::kCard) {
         sp = 1;
         ep = 0;
         break;
       }
-      lfStep<1, false>(ix, sp, ep, letter, 0u, 0xFFFFFFFFu);
+      lfStep<1, AMINO>(ix, sp, ep, letter, 0u, 0xFFFFFFFFu);
       next--;
     }
     counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);

@@ -118,7 +118,7 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length nucleotide batches, counts only): "sweep_min_queries"
  * (0 = automatic: batches of at least max(2^22, bwtLength/256) queries; n > 0 = batches of at least n; -1 = never),
  * "sweep_sort_bits" (top bits of the seed index the initial radix sort orders, default 32 = all but the low
- * "sweep_local_bits"), "sweep_local_bits" (0..8, default 8: low bits ordered inside each tile of the first pass instead), "sweep_items"
+ * "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 = automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items"
  * (records per thread and tile pass: 1, 2, 4, 8; default 4), "sweep_max_batch" (queries per slice of the 92-B-per-query scratch, default 2^27; when even that does not fit
  * the call is answered by the tile kernel), "sweep_profile" (0/1: record an event after every stage of the next calls). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);

@@ -11,6 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 def fixed_batch(b, length, num, seed, irregular=True):
+    if b.amino:
+        return fixed_batch_amino(b, length, num, seed, irregular)
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
     text = b.text
@@ -30,6 +32,54 @@ def fixed_batch(b, length, num, seed, irregular=True):
         rows[lower] |= 0x20
         rows[rng.choice(num, num // 25, replace=False)] = np.frombuffer(b"U", dtype=np.uint8)[0]
     return rows.reshape(-1)
+
+
+def fixed_batch_amino(b, length, num, seed, irregular=True):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    text = b.text
+    rows = np.empty((num, length), dtype=np.uint8)
+    for i in range(num):
+        if rng.random() < 0.6:
+            s = int(rng.integers(0, len(text) - length))
+            rows[i] = text[s:s + length]
+        else:
+            rows[i] = alphabet[rng.integers(0, 20, length)]
+    if irregular and num >= 40:
+        pick = rng.choice(num, num // 20, replace=False)
+        for j, i in enumerate(pick):
+            col = int(rng.integers(0, length))
+            rows[i, col] = (ord("X"), ord("b"), ord("$"), ord("z"), ord("-"), ord("j"), ord("O"))[j % 7]
+        lower = rng.choice(num, num // 10, replace=False)
+        rows[lower] |= 0x20
+    return rows.reshape(-1)
+
+
+@pytest.mark.parametrize("name", ["amino_r8", "amino_r2", "amino_r1"])
+def test_sweep_amino_matches_oracle(small_indexes, name):
+    """20 buckets in 10 double-ended arrays, 5 bits per remaining letter, mixed-radix seed index as the sort key."""
+    b = small_indexes[name]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 3, 5000), (k + 6, 1031), (k + 2, 20000)):
+        letters = fixed_batch(b, length, num, seed=length * 17 + num)
+        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        for bits, local, items in ((32, 8, 4), (16, 0, 2), (0, 8, 1), (3, 5, 8)):
+            gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_local_bits=local, sweep_items=items,
+                           sweep_first_items=items, sweep_profile=1)
+            counts = gpu.count(letters, fixed_len=length)
+            assert np.array_equal(counts, o_counts), (name, length, num, bits, local, items)
+            assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
+        gpu.set_tuning(sweep_min_queries=-1)
+        assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
+    # 7 letters left of the seed do not fit the 32-bit payload: the tile kernel answers
+    gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
+    letters = fixed_batch(b, k + 7, 300, seed=3)
+    o_counts, _, _ = oracle.count(letters, fixed_len=k + 7)
+    assert np.array_equal(gpu.count(letters, fixed_len=k + 7), o_counts)
+    assert not gpu.sweep_stage_ms()
+    gpu.close()
 
 
 @pytest.mark.parametrize("name", ["nuc_r8", "nuc_r3", "nuc_r16", "nuc_r1"])

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--local", type=str, default="8")
     ap.add_argument("--first-items", type=int, default=4)
     ap.add_argument("--no-tile", action="store_true")
+    ap.add_argument("--amino", action="store_true", help="cfg 4 shape: pass --bp 1000000000 --queries 50000000 --kmer 8 --seed-k 5")
     ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
     lib = capi.load()
@@ -40,15 +41,16 @@ def main():
         out.flush()
 
     d_text = torch.empty(args.bp, dtype=torch.uint8, device="cuda")
-    capi.check(lib.awfm_gpu_synth_letters(0, d_text.data_ptr(), args.bp, synth.TEXT_SEED + 2, 0, 0))
-    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), args.bp, abi.AwFmAlphabetDna, args.seed_k, 8)
+    capi.check(lib.awfm_gpu_synth_letters(0, d_text.data_ptr(), args.bp, synth.TEXT_SEED + 2, 0, int(args.amino)))
+    built = DeviceBuiltIndex.from_device_text(d_text.data_ptr(), args.bp,
+                                              abi.AwFmAlphabetAmino if args.amino else abi.AwFmAlphabetDna, args.seed_k, 8)
     del d_text
     gpu = built.gpu_index()
     built.close()
     torch.cuda.empty_cache()
     n, L = args.queries, args.kmer
     d_letters = torch.empty(n * L + 64, dtype=torch.uint8, device="cuda")
-    capi.check(lib.awfm_gpu_synth_letters(0, d_letters.data_ptr(), n * L, synth.QUERY_SEED + 2, 0, 0))
+    capi.check(lib.awfm_gpu_synth_letters(0, d_letters.data_ptr(), n * L, synth.QUERY_SEED + 2, 0, int(args.amino)))
     d_ref = torch.zeros(n, dtype=torch.int32, device="cuda")
     d_counts = torch.zeros(n, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream()
@@ -73,7 +75,7 @@ def main():
         gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items, sweep_local_bits=local, sweep_first_items=args.first_items)
         d_counts.fill_(-1)
         ms = timed(n, d_counts)
-        emit({"variant": "sweep", "sort_bits": bits, "local_bits": local, "items": items, "first_items": args.first_items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+        emit({"variant": "sweep", "amino": args.amino, "sort_bits": bits, "local_bits": local, "items": items, "first_items": args.first_items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
               "device_bytes": gpu.device_bytes()})

@@ -710,7 +710,14 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
   {
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
-    if (!AMINO && len % 4 == 0) {
+    if (AMINO && len % 4 == 0 && len <= 12) {
+      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
+      switch (len / 4) {
+        case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
+        case 2: sweepPackWordsAmino<2><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
+        default: sweepPackWordsAmino<3><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
+      }
+    } else if (!AMINO && len % 4 == 0) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
 #define AWFM_PACK_CASE(W)                                                                                         \

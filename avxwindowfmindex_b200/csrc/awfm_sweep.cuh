@@ -103,6 +103,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Amino counterpart (len % 4 == 0): the query's words straight from global memory, letters translated one by one
+// (src/AwFmLetter.c:55-67), key = mixed-radix seed index of the last k letters (src/AwFmKmerTable.c:36-51), five bits
+// per remaining letter with the letter prepended next in the low bits.
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+    sweepPackWordsAmino(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
+                        uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
+                        uint32_t *__restrict__ irregularCount) {
+  constexpr uint32_t LEN = 4 * WORDS;
+  const uint32_t rest = LEN - k;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
+       q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t *src = words + q * WORDS;
+    uint32_t w[WORDS];
+#pragma unroll
+    for (int i = 0; i < WORDS; i++) w[i] = __ldg(src + i);
+    uint32_t key = 0, packed = 0, bad = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < LEN; i++) {
+      const uint32_t l = aminoLetterIndex((w[i >> 2] >> (8u * (i & 3u))) & 0xFFu);
+      bad |= l >= 20u;
+      const uint32_t v = l < 20u ? l : 0u;
+      if (i >= rest) key = key * 20u + v;              // leftmost of the last k letters most significant
+      else packed |= v << (5u * (rest - 1u - i));      // letter prepended at step j+1 is s[rest-1-j]
+    }
+    uint32_t id = (uint32_t)q;
+    if (bad) {
+      irregularIds[atomicAdd(irregularCount, 1u)] = id;
+      id = kSweepNoId;
+    }
+    keys[q] = key;
+    vals[q] = ((uint64_t)packed << 32) | id;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // sweepPack: 256 queries per tile staged through shared memory with coalesced 128-bit loads.
 // ---------------------------------------------------------------------------------------------------------------

@@ -166,3 +166,40 @@ def test_caller_capacity_is_kept_and_grown_exactly(small_indexes, reference):
     assert np.array_equal(sl.entries()["capacity"][: len(queries)], expected_capacity)
     sl.close()
     lib.awFmGpuReleaseIndex(ip)
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "amino_r8"])
+def test_count_pipeline_rounds_and_driver_thread(small_indexes, reference, name):
+    """awFmParallelSearchCount in rounds (csrc/awfm_b200.cu: ship r-1 / pack r / scatter r-4): many chunks, teams small
+    enough for the calling thread to pack as well (<= 4) and large enough for a dedicated driver thread, mixed lengths,
+    equal lengths copied, equal lengths read in place from page-locked memory; the list is reused across calls."""
+    import torch
+    b = small_indexes[name]
+    lib = capi.load()
+    k = b.arrays.seed_k
+    ix = b.arrays.as_awfm_index()
+    ip = C.addressof(ix)
+    mixed = pack_queries(make_queries(b.text, b.amino, seed=5, num=6000, min_len=1, max_len=k + 9, seed_k=k))
+    length = k + 4
+    rng = np.random.default_rng(9)
+    starts = rng.integers(0, len(b.text) - length, 7001)
+    fixed = np.concatenate([b.text[s:s + length] for s in starts]).astype(np.uint8)
+    fixed[::53] = b.text[0]
+    fixed_offsets = np.arange(0, len(fixed) + 1, length, dtype=np.uint64)
+    pinned = torch.from_numpy(fixed.copy()).pin_memory()
+    cases = [("mixed", mixed[0], mixed[1], {}), ("equal, copied", fixed, fixed_offsets, {}),
+             ("equal, in place", pinned.numpy(), None, {"fixed_len": length})]
+    for label, letters, offsets, kw in cases:
+        r_counts = reference.count(b.ptr, np.asarray(letters), offsets if offsets is not None else fixed_offsets, threads=4)
+        n = len(r_counts)
+        for chunk, threads in ((512, 1), (512, 3), (512, 6), (640, 9), (1 << 16, 7)):
+            with engine_env(AWFM_GPU_CHUNK_QUERIES=chunk):
+                lib.awFmGpuReleaseIndex(ip)
+                sl = KmerSearchList(lib, n).fill(letters, offsets, **kw)
+                for _ in range(2):
+                    sl.entries()["count"][:n] = 0xDEAD
+                    parallel_search_count(lib, ip, sl, threads)
+                    assert lib.awFmGpuLastCountStatus() == abi.AwFmSuccess
+                    assert np.array_equal(sl.counts(), r_counts), (name, label, chunk, threads)
+                sl.close()
+    lib.awFmGpuReleaseIndex(ip)

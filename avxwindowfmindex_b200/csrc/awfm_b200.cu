@@ -640,7 +640,7 @@ static uint32_t sweepKeyBits(const awfm_gpu_ctx *c, uint32_t k) {  // bits of a 
 }
 static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t len,
                           uint64_t n, const awfm_range *dRanges) {
-  if (c->sweepMinQueries < 0 || c->countVariant != 1 || dOffsets || dRanges) return false;
+  if (c->sweepMinQueries < 0 || c->countVariant != 1 || dOffsets) return false;
   if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
   if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0x70000000ull) return false;  // 32-bit positions and record indices
   const uint32_t k = sweepSeedK(c, len);
@@ -694,7 +694,7 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n, int arrays) {
 
 template <bool AMINO>
 static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
-                           cudaStream_t st) {
+                           uint4 *dRanges, cudaStream_t st) {
   SweepScratch &w = c->sweep;
   const uint32_t k = sweepSeedK(c, len), steps = len - k;
   const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
@@ -787,10 +787,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
-                                         steps, localBits, dCounts);
+                                         steps, localBits, dCounts, dRanges);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
-                                         gen(pass & 1, pass), steps - pass, 0u, dCounts);
+                                         gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   };
@@ -810,7 +810,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     if (int r = launchPassItems(std::false_type(), pass)) return r;
     mark();
   }
-  sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts);
+  sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
   CU(cudaGetLastError());
   mark();
   CU(cudaEventRecord(w.done, st));
@@ -822,15 +822,16 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
 // Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
 // slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
 static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
-                      cudaStream_t st) {
+                      uint4 *dRanges, cudaStream_t st) {
   const bool amino = c->ix.amino != 0;
   const uint64_t maxBatch = amino ? std::min<int64_t>(c->sweepMaxBatch, 1ll << 26) : c->sweepMaxBatch;
   const uint64_t slice = std::min<uint64_t>(n, maxBatch & ~255ull);  // slices start 16-B aligned
   if (int r = ensureSweep(c, slice, amino ? 10 : 2)) return r;
   for (uint64_t first = 0; first < n; first += slice) {
     const uint64_t m = std::min(slice, n - first);
-    const int r = amino ? sweepCountBatch<true>(c, dLetters + first * len, len, m, dCounts + first, st)
-                        : sweepCountBatch<false>(c, dLetters + first * len, len, m, dCounts + first, st);
+    uint4 *ranges = dRanges ? dRanges + first : nullptr;
+    const int r = amino ? sweepCountBatch<true>(c, dLetters + first * len, len, m, dCounts + first, ranges, st)
+                        : sweepCountBatch<false>(c, dLetters + first * len, len, m, dCounts + first, ranges, st);
     if (r) return r;
   }
   return AWFM_GPU_OK;
@@ -844,7 +845,7 @@ static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint6
   if (ev) CU(cudaEventRecord(ev->a, st));
   int r;
   const bool sweep = sweepEligible(c, dLetters, dOffsets, fixedLen, n, dRanges);
-  r = sweep ? sweepCount(c, dLetters, fixedLen, n, dCounts, st) : AWFM_GPU_OK;
+  r = sweep ? sweepCount(c, dLetters, fixedLen, n, dCounts, (uint4 *)dRanges, st) : AWFM_GPU_OK;
   if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
     c->sweep.stagesRecorded = 0;
     r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);

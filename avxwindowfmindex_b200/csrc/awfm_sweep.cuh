@@ -265,7 +265,8 @@ template <bool FIRST, int kSweepItems, bool AMINO = false>
 __global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
-              uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts) {
+              uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
+              uint4 *__restrict__ ranges /* or nullptr: every query's final (sp, ep) as the reference leaves it */) {
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   constexpr uint32_t kLetterMask = (1u << LB) - 1u;
@@ -412,7 +413,11 @@ __global__ void __launch_bounds__(kSweepThreads)
       for (int it = 0; it < kSweepItems; it++) loadSeedEntry(ix, deep, key[it], s64[it], e64[it]);
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++) {
-        if (s64[it] > e64[it]) id[it] = kSweepNoId;  // empty seed range: count stays 0
+        if (s64[it] > e64[it]) {  // empty seed range: count stays 0, the stored pair is the query's final range
+          if (ranges && id[it] != kSweepNoId)
+            ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
+          id[it] = kSweepNoId;
+        }
         if (id[it] != kSweepNoId) sp[it] = (uint32_t)s64[it], ep[it] = (uint32_t)e64[it];
       }
     }
@@ -446,10 +451,14 @@ __global__ void __launch_bounds__(kSweepThreads)
         sp[it] = nsp;
         ep[it] = nep;
         rest[it] >>= LB;
-        valid = valid && nep != nsp - 1u;  // ep == sp - 1 <=> empty
+        if (valid && nep == nsp - 1u) {  // ep == sp - 1 <=> empty: the search stops here (src/AwFmParallelSearch.c:279-311)
+          valid = false;
+          if (ranges) ranges[id[it]] = make_uint4(nsp, 0u, nep, nep == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u);
+        }
       }
       bucket[it] = NB;  // no output
       if (valid) {
+        if (steps <= 1 && ranges) ranges[id[it]] = make_uint4(sp[it], 0u, ep[it], 0u);
         if (steps <= 1) counts[id[it]] = ep[it] - sp[it] + 1u;
         else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
       }
@@ -511,7 +520,7 @@ template <bool AMINO>
 __global__ void __launch_bounds__(256)
     sweepIrregular(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ letters, uint32_t len,
                    const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
-                   uint32_t *__restrict__ counts) {
+                   uint32_t *__restrict__ counts, uint4 *__restrict__ ranges) {
   const uint32_t n = *numIds;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t q = ids[i];
@@ -529,6 +538,7 @@ __global__ void __launch_bounds__(256)
       next--;
     }
     counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
+    if (ranges) ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
   }
 }
 

@@ -64,13 +64,17 @@ def test_sweep_amino_matches_oracle(small_indexes, name):
     gpu = GpuIndex(b.arrays)
     for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 3, 5000), (k + 6, 1031), (k + 2, 20000)):
         letters = fixed_batch(b, length, num, seed=length * 17 + num)
-        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
         for bits, local, items in ((32, 8, 4), (16, 0, 2), (0, 8, 1), (3, 5, 8)):
             gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_local_bits=local, sweep_items=items,
                            sweep_first_items=items, sweep_profile=1)
             counts = gpu.count(letters, fixed_len=length)
             assert np.array_equal(counts, o_counts), (name, length, num, bits, local, items)
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
+        gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=4, sweep_first_items=4, sweep_profile=1)
+        counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+        assert gpu.sweep_stage_ms(), "range output did not take the sweep path"
+        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num)
         gpu.set_tuning(sweep_min_queries=-1)
         assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
     # 7 letters left of the seed do not fit the 32-bit payload: the tile kernel answers
@@ -90,20 +94,25 @@ def test_sweep_matches_oracle(small_indexes, name):
     gpu = GpuIndex(b.arrays)
     for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 5, 255), (k + 8, 5000), (k + 16, 1031), (k + 3, 20000)):
         letters = fixed_batch(b, length, num, seed=length * 31 + num)
-        o_counts, _, _ = oracle.count(letters, fixed_len=length)
+        o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
         for bits, local, items in ((32, 8, 4), (16, 0, 2), (0, 8, 1), (3, 5, 8), (32, 0, 4)):
             gpu.set_tuning(sweep_min_queries=1, sweep_sort_bits=bits, sweep_local_bits=local, sweep_items=items,
                            sweep_profile=1)
             counts = gpu.count(letters, fixed_len=length)
             assert np.array_equal(counts, o_counts), (name, length, num, bits, local, items)
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
+        # range output: every query's final (sp, ep) as the reference leaves it, incl. the pair a dying search stops at
+        gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=4, sweep_profile=1)
+        counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+        assert gpu.sweep_stage_ms(), "range output did not take the sweep path"
+        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num)
         gpu.set_tuning(sweep_min_queries=-1)
         assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
     gpu.close()
 
 
 def test_sweep_falls_back_outside_its_domain(small_indexes):
-    """Too many letters left of the seed, ranges wanted, variable lengths: the tile kernels answer, same results."""
+    """Too many letters left of the seed, variable lengths: the tile kernels answer, same results."""
     b = small_indexes["nuc_r8"]
     k = b.arrays.seed_k
     oracle = harness.Oracle(b.arrays)

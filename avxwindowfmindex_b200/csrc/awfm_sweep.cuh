@@ -9,28 +9,32 @@
 // the next LF step ranks (sp-1, ep) are non-decreasing, and after the step the queries that prepended the same letter
 // c are still ordered (sp' = C[c] + Occ(c, sp-1) is monotone in sp).  So:
 //
-//   sweepPack    thread per query: seed-table index of the last k letters (src/AwFmKmerTable.c:21-51) as the sort key,
+//   sweepPack*   thread per query: seed-table index of the last k letters (src/AwFmKmerTable.c:21-51) as the sort key,
 //                the remaining len-k letters packed 2 bits each (next letter to prepend in the low bits) + query id as
 //                the payload.  Queries holding anything but A/C/G/T(/U) go to a side list (sweepIrregular).
-//   radix sort   CUB, only the top `sortBits` bits of the key: queries whose seed entries / first ranges share a few
-//                KB of the table / of the BWT become neighbours; exact order inside is irrelevant for correctness.
-//   sweepStep<FIRST>   reads the seed entry (src/AwFmParallelSearch.c:222-271), does the first LF step
-//                (src/AwFmSearch.c:42-103) and appends the still-valid query as a 16-B record {sp, ep-sp, id, letters}
-//                to the bucket of the letter it has just prepended;
+//   radix sort   CUB (stable), on all key bits but the lowest few: the order has to be exact at warp granularity —
+//                32 consecutive queries should rank within a handful of neighbouring lines — or the L1 data pipe pays
+//                one wavefront per lane (measured: DESIGN.md section 3, dropped variants).
+//   sweepStep<FIRST>   finishes the order on those low bits inside each tile (shared-memory counting sort), reads the
+//                seed entry (src/AwFmParallelSearch.c:222-271), does the first LF step (src/AwFmSearch.c:42-103) and
+//                appends the still-valid query as a 16-B record {sp, ep-sp, id, letters} to the bucket of the letter
+//                it has just prepended;
 //   sweepStep<!FIRST>  one pass per further letter over the buckets in letter order A,C,G,T — which is ascending sp
 //                order, because ranges of strings starting with A precede those starting with C, ... and inside a
-//                bucket the append order is the (ascending) input order — one LF step per record, same append.  A query whose range empties is dropped (its count
-//                stays at the zero the output was cleared to, src/AwFmParallelSearch.c:279-311 stops there too); one
-//                that has prepended all its letters writes count = ep-sp+1 (u32, :187-190).
+//                bucket the append order is the (ascending) input order — one LF step per record, same append.  A
+//                query whose range empties is dropped (its count stays at the zero the output was cleared to,
+//                src/AwFmParallelSearch.c:279-311 stops there too); one that has prepended all its letters writes
+//                count = ep-sp+1 (u32, :187-190).  With range output every query also stores its final (sp, ep) once:
+//                the seed entry if that is empty, the pair its search stops at, or its last range.
 //
 // Buckets are filled tile by tile through one atomicAdd per bucket per tile (order inside a tile is kept, tiles land
-// in roughly launch order), so the order is approximate: the ranks of the tiles in flight at any moment touch a
-// window of ~1 % of the BWT, which the 126 MB L2 holds.  The index is then STREAMED once per pass instead of being
-// gathered line by line, and all other traffic (keys, records) is sequential.  No spin-waits anywhere.
+// in roughly launch order), so the order of whole tiles is approximate: the ranks of the tiles in flight at any moment
+// touch a window of ~1 % of the BWT, which the 126 MB L2 holds.  The index is then STREAMED once per pass instead of
+// being gathered line by line, and all other traffic (keys, records) is sequential.  No spin-waits anywhere.
 //
 // Exactness: same seed entries, same ranks (sectorRank), same stop rule; only the processing order differs, and the
 // result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels):
-// variable-length batches, range output, bwtLength > 2^32, len - k > 16 (amino: 6), k > 16 (amino: 7).
+// variable-length batches, bwtLength > 2^32, len - k > 16 (amino: 6), k > 16 (amino: 7).
 #pragma once
 #include "awfm_kernels.cuh"
 

@@ -281,7 +281,7 @@ def run_ours(args):
             works[b].wait()
             works[b] = None
         gpu.count_device(d_letters.data_ptr(), None, L, n, bufs[b].data_ptr(), None, stream.cuda_stream)
-        if world > 1:
+        if world > 1 and not os.environ.get("AWFM_BENCH_SKIP_GATHER"):  # (development switch: search only)
             works[b] = dist.gather(bufs[b], gathered if rank == 0 else None, dst=0, async_op=True)
 
     def drain():

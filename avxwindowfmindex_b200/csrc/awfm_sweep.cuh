@@ -312,7 +312,21 @@ __global__ void __launch_bounds__(kSweepThreads)
     total = before3 + c3;  // <= number of queries < 2^31
   }
 
-  for (uint32_t base = blockIdx.x * kSweepTile; base < total; base += gridDim.x * kSweepTile) {
+  // Tiles are handed out in order by a ticket counter (word 31 of the output generation's control block), not by
+  // static striding: when other kernels hold part of the SMs (NCCL's gather of the previous step's counts at N > 1)
+  // some CTAs of this grid start late, and with static striding their tiles would simply run after everyone else's.
+  // The ticket of the next tile is drawn while this one is worked on; the barrier that publishes it doubles as the
+  // "previous tile's append buffers consumed" barrier.
+  __shared__ uint32_t tileTicket[2];
+  uint32_t nextTile = 0;  // thread 0
+  if (threadIdx.x == 0) nextTile = atomicAdd(out.count + 31, 1u);
+  for (uint32_t round = 0;; round++) {
+    if (threadIdx.x == 0) tileTicket[round & 1u] = nextTile;
+    __syncthreads();
+    const uint32_t tile = tileTicket[round & 1u];
+    if ((uint64_t)tile * kSweepTile >= total) break;
+    if (threadIdx.x == 0) nextTile = atomicAdd(out.count + 31, 1u);
+    const uint32_t base = tile * kSweepTile;
     uint32_t sp[kSweepItems], ep[kSweepItems], id[kSweepItems], rest[kSweepItems], bucket[kSweepItems];
     // Every load of a stage is issued for all items before anything waits on it (no branches around the loads:
     // out-of-range items read a clamped, valid address and are disabled afterwards).
@@ -469,8 +483,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     }
     if (steps <= 1) continue;  // last pass: nothing to append (uniform for the whole grid)
     // ---- stable (inside the tile) append to the output buckets ----
-    uint32_t rank[kSweepItems];
-    __syncthreads();  // warpCount / bucketBase of the previous tile consumed
+    uint32_t rank[kSweepItems];  // (warpCount / bucketBase of the previous tile were consumed before this tile's ticket barrier)
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
       if constexpr (AMINO) {

@@ -115,12 +115,15 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * A/B switch for a table already derived with awfm_gpu_ctx_extend_seed_table); of the search-list engine:
  * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
- * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length batches of either alphabet, counts and ranges): "sweep_min_queries"
- * (0 = automatic: batches of at least max(2^22, bwtLength/256) queries; n > 0 = batches of at least n; -1 = never),
- * "sweep_sort_bits" (top bits of the seed index the initial radix sort orders, default 32 = all but the low
- * "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 = automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items"
- * (records per thread and tile pass: 1, 2, 4, 8; default 4), "sweep_max_batch" (queries per slice of the 92-B-per-query scratch — 348 B for amino indexes —, default 2^27; when even that does not fit
- * the call is answered by the tile kernel), "sweep_profile" (0/1: record an event after every stage of the next calls). */
+ * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length batches of either alphabet, counts and ranges):
+ * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per 128-B line of the index) queries and no
+ * derived deep seed table; n > 0 = batches of at least n queries; -1 = never), "sweep_sort_bits" (top bits of the seed
+ * index the radix sort orders, default 32 = all but the low "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 =
+ * automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items" /
+ * "sweep_first_items" (records per thread and tile of the later passes / of the first pass: 1, 2, 4, 8; default 4),
+ * "sweep_max_batch" (queries per slice of the scratch — 92 B per query, 348 B for amino indexes —, default 2^27; when
+ * even that does not fit the call is answered by the tile kernel), "sweep_profile" (0/1: record an event after every
+ * stage of the next calls). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 /* Device time of every stage of the most recent sweep count call made with "sweep_profile" = 1, in launch order:
  * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.

@@ -54,3 +54,18 @@ def test_search_list_allocation_semantics():
     assert (e["capacity"] == 4).all() and (e["count"] == 0).all() and (e["positionList"] != 0).all()
     assert (e["kmerString"] == 0).all() and (e["kmerLength"] == 0).all()
     sl.close()
+
+
+def test_every_tuning_key_is_documented_in_the_header():
+    """awfm_gpu_ctx_set_tuning's keys (csrc/awfm_b200.cu) and the list in include/awfm_gpu.h must not drift apart."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "avxwindowfmindex_b200", "csrc", "awfm_b200.cu")).read()
+    body = src[src.index('extern "C" int awfm_gpu_ctx_set_tuning'):]
+    body = body[:body.index("unknown tuning key")]
+    keys = set(re.findall(r'k == "([a-z0-9_]+)"', body))
+    assert len(keys) >= 15
+    header = open(os.path.join(root, "include", "awfm_gpu.h")).read()
+    missing = sorted(k for k in keys if f'"{k}"' not in header)
+    assert not missing, f"tuning keys not documented in include/awfm_gpu.h: {missing}"

@@ -7,4 +7,5 @@ CUDA + C-ABI, include/awfm_gpu.h, include/awfm_abi.h); the Python modules are a 
 from . import abi, build_index, capi, index, search, synth  # noqa: F401
 from .build_index import DeviceBuiltIndex  # noqa: F401
 from .index import IndexArrays, read_awfmi, write_awfmi  # noqa: F401
-from .search import GpuIndex, KmerSearchList, parallel_search_count, parallel_search_locate  # noqa: F401
+from .search import (GpuGroup, GpuIndex, KmerSearchList, PinnedArray, pack_queries_bits, parallel_search_count,  # noqa: F401
+                     parallel_search_locate)

@@ -7,6 +7,7 @@ import ctypes as C
 
 AwFmAlphabetAmino, AwFmAlphabetDna, AwFmAlphabetRna = 1, 2, 3
 AwFmSuccess, AwFmFileReadOkay = 1, 2
+AwFmGpuKmerAscii, AwFmGpuKmer2Bit, AwFmGpuKmer5Bit = 0, 2, 5  # enum AwFmGpuKmerFormat (include/awfm_abi.h)
 AwFmGeneralFailure, AwFmAllocationFailure, AwFmFileReadFail = -1, -3, -11
 AwFmUnsupportedVersionError, AwFmNullPtrError, AwFmIllegalPositionError = -2, -4, -6
 NUC_BLOCK_BYTES, AMINO_BLOCK_BYTES = 160, 352

@@ -20,11 +20,18 @@ GPU_SYMBOLS = [
     "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
     "awfm_gpu_ctx_create_from_file", "awfm_gpu_ctx_set_sequences", "awfm_gpu_ctx_extend_seed_table",
     "awfm_gpu_ctx_densify_suffix_array", "awfm_gpu_map_positions_device", "awfm_gpu_map_positions_host",
-    "awfm_gpu_ctx_sweep_stage_ms",
+    "awfm_gpu_ctx_sweep_stage_ms", "awfm_gpu_count_device_format",
+    "awfm_gpu_group_create", "awfm_gpu_group_create_from_contexts", "awfm_gpu_group_destroy", "awfm_gpu_group_size",
+    "awfm_gpu_group_context", "awfm_gpu_group_set_sequences", "awfm_gpu_group_set_tuning", "awfm_gpu_group_get_stats",
+    "awfm_gpu_group_count", "awfm_gpu_group_locate", "awfm_gpu_group_search_list_count",
+    "awfm_gpu_group_search_list_locate", "awfm_gpu_host_alloc", "awfm_gpu_host_free", "awfm_gpu_host_register",
+    "awfm_gpu_host_unregister", "awfm_gpu_device_malloc", "awfm_gpu_device_free", "awfm_gpu_ipc_export",
+    "awfm_gpu_ipc_open", "awfm_gpu_ipc_close", "awfm_gpu_peer_copy_async",
 ]
 DROPIN_SYMBOLS = [
     "awFmCreateKmerSearchList", "awFmDeallocKmerSearchList", "awFmParallelSearchCount", "awFmParallelSearchLocate",
     "awFmGpuReleaseIndex", "awFmGpuPrepareIndex", "awFmGpuLastCountStatus", "awFmGpuGetLocalSequencePositions",
+    "awFmGpuNumDevices", "awFmGpuCountPacked", "awFmGpuLocatePacked", "awFmGpuHostAlloc", "awFmGpuHostFree",
 ]
 
 _lib = None
@@ -94,7 +101,43 @@ def load():
     lib.awfm_gpu_ctx_set_sequences.argtypes = [vp, vp, u64]
     lib.awfm_gpu_map_positions_device.argtypes = [vp, vp, u64, vp, vp, vp]
     lib.awfm_gpu_map_positions_host.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]
+    lib.awfm_gpu_count_device_format.argtypes = [vp, vp, u32, vp, u32, u64, vp, vp, vp]
+    lib.awfm_gpu_group_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(abi.awfm_index_view)]
+    lib.awfm_gpu_group_create_from_contexts.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int]
+    lib.awfm_gpu_group_destroy.argtypes = [vp]
+    lib.awfm_gpu_group_destroy.restype = None
+    lib.awfm_gpu_group_size.argtypes = [vp]
+    lib.awfm_gpu_group_context.argtypes = [vp, C.c_int]
+    lib.awfm_gpu_group_context.restype = vp
+    lib.awfm_gpu_group_set_sequences.argtypes = [vp, vp, u64]
+    lib.awfm_gpu_group_set_tuning.argtypes = [vp, C.c_char_p, i64]
+    lib.awfm_gpu_group_get_stats.argtypes = [vp, C.POINTER(abi.awfm_gpu_stats)]
+    lib.awfm_gpu_group_count.argtypes = [vp, vp, u32, vp, u32, u64, vp]
+    lib.awfm_gpu_group_locate.argtypes = [vp, vp, u32, vp, u32, u64, vp, vp, u64, vp, vp, C.POINTER(u64)]
+    lib.awfm_gpu_group_search_list_count.argtypes = [vp, vp, u64, u32]
+    lib.awfm_gpu_group_search_list_locate.argtypes = [vp, vp, u64, u32]
+    lib.awfm_gpu_host_alloc.argtypes = [C.POINTER(vp), u64]
+    lib.awfm_gpu_host_free.argtypes = [vp]
+    lib.awfm_gpu_host_free.restype = None
+    lib.awfm_gpu_host_register.argtypes = [vp, u64]
+    lib.awfm_gpu_host_unregister.argtypes = [vp]
+    lib.awfm_gpu_device_malloc.argtypes = [C.c_int, C.POINTER(vp), u64]
+    lib.awfm_gpu_device_free.argtypes = [C.c_int, vp]
+    lib.awfm_gpu_ipc_export.argtypes = [C.c_int, vp, vp]
+    lib.awfm_gpu_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.awfm_gpu_ipc_close.argtypes = [C.c_int, vp]
+    lib.awfm_gpu_peer_copy_async.argtypes = [C.c_int, vp, vp, u64, vp]
     declare_search_list_api(lib)
+    lib.awFmGpuNumDevices.argtypes = [vp]
+    lib.awFmGpuNumDevices.restype = C.c_int
+    lib.awFmGpuCountPacked.argtypes = [vp, vp, C.c_int, vp, u32, u64, vp]
+    lib.awFmGpuCountPacked.restype = C.c_int
+    lib.awFmGpuLocatePacked.argtypes = [vp, vp, C.c_int, vp, u32, u64, vp, vp, u64, vp, vp, C.POINTER(u64)]
+    lib.awFmGpuLocatePacked.restype = C.c_int
+    lib.awFmGpuHostAlloc.argtypes = [C.c_size_t]
+    lib.awFmGpuHostAlloc.restype = vp
+    lib.awFmGpuHostFree.argtypes = [vp]
+    lib.awFmGpuHostFree.restype = None
     lib.awFmGpuGetLocalSequencePositions.argtypes = [vp, vp, C.c_size_t, vp, vp]
     lib.awFmGpuGetLocalSequencePositions.restype = C.c_int
     lib.awFmGpuReleaseIndex.argtypes = [vp]

@@ -15,22 +15,20 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
 
-#include "../../include/awfm_gpu.h"
-#include "awfm_kernels.cuh"
-#include "awfm_sweep.cuh"
+#include "awfm_internal.cuh"
 
 using namespace awfm;
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string gLastError;
-static int fail(int code, const char *what, const char *detail = nullptr) {
+int awfm_fail(int code, const char *what, const char *detail) {
   gLastError = what;
   if (detail) {
     gLastError += ": ";
@@ -38,19 +36,7 @@ static int fail(int code, const char *what, const char *detail = nullptr) {
   }
   return code;
 }
-#define CU(call)                                                                                     \
-  do {                                                                                               \
-    cudaError_t e_ = (call);                                                                         \
-    if (e_ != cudaSuccess) {                                                                         \
-      cudaGetLastError();                                                                            \
-      return fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC                               \
-                  : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? AWFM_GPU_ERR_NO_DEVICE \
-                                                                                   : AWFM_GPU_ERR_CUDA, \
-                  #call, cudaGetErrorString(e_));                                                    \
-    }                                                                                                \
-  } while (0)
-
-int awfm_set_error(int code, const char *what, const char *detail) { return fail(code, what, detail); }
+int awfm_set_error(int code, const char *what, const char *detail) { return awfm_fail(code, what, detail); }
 
 extern "C" const char *awfm_gpu_last_error(void) { return gLastError.c_str(); }
 extern "C" int awfm_gpu_device_count(void) {
@@ -62,90 +48,71 @@ extern "C" int awfm_gpu_device_count(void) {
   return n;
 }
 
-// ------------------------------------------------------------------------------------------------ context
-struct EventPair {
-  cudaEvent_t a, b;
-};
+// ------------------------------------------------------------------------------------------------ lanes
+int GrowBuf::ensure(size_t bytes) {
+  if (cap >= bytes && p) return AWFM_GPU_OK;
+  release();
+  const size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = host ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+    return awfm_fail(AWFM_GPU_ERR_ALLOC, host ? "pinned host staging allocation failed" : "device scratch allocation failed",
+                     cudaGetErrorString(e));
+  }
+  cap = want;
+  return AWFM_GPU_OK;
+}
+void GrowBuf::release() {
+  if (p) {
+    if (host) cudaFreeHost(p);
+    else cudaFree(p);
+  }
+  p = nullptr;
+  cap = 0;
+}
 
-struct LocateScratch {  // per-stream scratch of scan + walk (two streams may not share one)
-  void *scanTemp = nullptr;
-  size_t scanTempBytes = 0;
-  uint64_t *dLengths = nullptr;
-  uint64_t lengthsCap = 0;
-  unsigned long long *dWorkCounter = nullptr;  // locateKernelRefill's chunk dispenser
-};
+int awfm_lane_prepare(awfm_gpu_ctx *c, Lane &L) {
+  (void)c;
+  if (L.ready) return AWFM_GPU_OK;
+  if (!L.sc.dWorkCounter) CU(cudaMalloc(&L.sc.dWorkCounter, 64));
+  if (!L.unpackDone) CU(cudaEventCreateWithFlags(&L.unpackDone, cudaEventDisableTiming));
+  for (auto &s : L.slots) {
+    if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (!s.offsetsDone) CU(cudaEventCreateWithFlags(&s.offsetsDone, cudaEventDisableTiming));
+    if (!s.sc.dWorkCounter) CU(cudaMalloc(&s.sc.dWorkCounter, 64));
+  }
+  L.ready = true;
+  return AWFM_GPU_OK;
+}
 
-struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grown on demand, one call at a time
-  uint64_t cap = 0;                       // queries the buffers hold
-  void *arena = nullptr;                  // one allocation carved into the buffers below
-  uint32_t *keys[2] = {nullptr, nullptr};  // seed-table index per query, radix-sort double buffer
-  uint64_t *vals[2] = {nullptr, nullptr};  // (remaining letters << 32) | query id
-  uint4 *recs[2][kSweepMaxArrays] = {};   // two generations x (2 | 10) double-ended arrays
-  int arrays = 0;                         // arrays per generation the arena was carved for
-  uint32_t *ctrl = nullptr;               // [kSweepMaxPasses][4] bucket counters, then the irregular-query counter
-  uint32_t *irregularIds = nullptr;
-  void *sortTemp = nullptr;
-  size_t sortTempBytes = 0;
-  cudaEvent_t done = nullptr;             // end of the last sweep: the next one (possibly on another stream) waits
-  cudaEvent_t stage[kSweepMaxPasses + 4];  // stage boundaries of the most recent call ("sweep_profile")
-  int numStages = 0, stagesRecorded = 0;
-  uint64_t bytes = 0;
-};
+LaneHold::LaneHold(awfm_gpu_ctx *ctx) : c(ctx) {
+  rc = awfm_set_device(c);
+  if (rc) return;
+  // host-facing calls use lanes 1..kLanes-1 (lane 0 belongs to the asynchronous device-buffer entry points)
+  for (int i = 1; i < awfm_gpu_ctx::kLanes && !lane; i++)
+    if (c->lanes[i].mu.try_lock()) lane = &c->lanes[i];
+  if (!lane) {
+    lane = &c->lanes[1];
+    lane->mu.lock();
+  }
+  rc = awfm_lane_prepare(c, *lane);
+  c->lastLane.store((int)(lane - c->lanes));
+}
+LaneHold::~LaneHold() {
+  if (lane) lane->mu.unlock();
+}
+AllLanesHold::AllLanesHold(awfm_gpu_ctx *ctx) : c(ctx) {
+  c->mu.lock();
+  for (auto &l : c->lanes) l.mu.lock();
+}
+AllLanesHold::~AllLanesHold() {
+  for (auto &l : c->lanes) l.mu.unlock();
+  c->mu.unlock();
+}
 
-struct PipeSlot {  // one in-flight chunk of the search-list engine
-  uint8_t *hLetters = nullptr, *dLetters = nullptr;
-  uint64_t lettersCap = 0, dLettersCap = 0;
-  uint64_t *hOffsets = nullptr, *dOffsets = nullptr;
-  uint32_t *hCounts = nullptr, *dCounts = nullptr;
-  uint4 *dRanges = nullptr;
-  uint64_t queryCap = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
-  uint64_t first = 0, n = 0;
-  bool busy = false;
-  bool ready = false;  // count engine: D2H complete, counts not scattered yet
-  // locate pipeline: hit offsets and positions of the chunk, both sides of the bus
-  LocateScratch sc;
-  uint64_t *hHit = nullptr, *dHit = nullptr, hitCap = 0;
-  uint64_t *hPos = nullptr, *dPos = nullptr, posCap = 0;
-  cudaEvent_t offsetsDone = nullptr;
-  uint64_t total = 0;
-  bool shipped = false, walked = false, big = false;
-};
-
-struct awfm_gpu_ctx {
-  int device = 0, numSMs = 0;
-  DevIndex ix{};
-  void *dLines = nullptr, *dXRel16 = nullptr, *dSuperC = nullptr, *dSeed = nullptr, *dSa = nullptr;
-  uint64_t *dSequenceEnds = nullptr;
-  void *dDeepSeed = nullptr, *dDenseSa = nullptr;  // derived structures (extend_seed_table / densify_suffix_array)
-  uint64_t deepSeedBytes = 0, denseSaBytes = 0;
-  uint32_t deepSeedKBuilt = 0;
-  const void *origSa = nullptr;                    // the index's own sampled SA, restored when the dense one is dropped
-  uint32_t origSaBitWidth = 0, origSaRatio = 0, origSaRatioShift = 0;
-  uint64_t deviceBytes = 0;
-  bool hasSa = false;
-  // tuning
-  int countLpq = 2, locateLpq = 2, countVariant = 1, locateVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
-  int64_t chunkQueries = 1 << 16;
-  int64_t locateChunkQueries = 1 << 18;
-  int64_t locateInlineHits = 1 << 22;  // a chunk with more hits than this is finished through windows of ...
-  int64_t locateWindowHits = 1 << 26;  // ... this many flat hit indices
-  LocateScratch sc;  // scratch of the device-/host-buffer calls (the list engine's slots have their own)
-  SweepScratch sweep;
-  int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
-  int64_t sweepMaxBatch = 1ll << 27;
-  int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
-  uint64_t *hBigPos = nullptr, *dBigPos = nullptr, bigPosCap = 0;  // windowed positions of a chunk with very many hits
-  std::vector<EventPair> kernelEvents;  // of the most recent call
-  size_t eventsUsed = 0;
-  awfm_gpu_stats stats{};
-  static constexpr int kSlots = 6;
-  PipeSlot slots[kSlots];
-  std::mutex mu;
-};
-
-static int setDevice(const awfm_gpu_ctx *c) {
+int awfm_set_device(const awfm_gpu_ctx *c) {
   CU(cudaSetDevice(c->device));
   return AWFM_GPU_OK;
 }
@@ -157,13 +124,13 @@ static uint64_t numSeedsOf(uint8_t alphabet, uint8_t k) {
 }
 
 static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view *v, bool fromDevice) {
-  if (!out || !v || !v->blocks || !v->prefixSums || !v->seedTable) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (v->alphabet < 1 || v->alphabet > 3) return fail(AWFM_GPU_ERR_ARG, "alphabetType must be 1 (amino), 2 (DNA) or 3 (RNA)");
-  if (v->bwtLength < 2 || v->numBlocks != 1 + (v->bwtLength - 1) / 256) return fail(AWFM_GPU_ERR_ARG, "numBlocks does not match bwtLength");
-  if (v->saBytes && (v->saRatio == 0 || v->saBitWidth == 0 || v->saBitWidth > 64)) return fail(AWFM_GPU_ERR_ARG, "bad SA ratio / bit width");
+  if (!out || !v || !v->blocks || !v->prefixSums || !v->seedTable) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (v->alphabet < 1 || v->alphabet > 3) return awfm_fail(AWFM_GPU_ERR_ARG, "alphabetType must be 1 (amino), 2 (DNA) or 3 (RNA)");
+  if (v->bwtLength < 2 || v->numBlocks != 1 + (v->bwtLength - 1) / 256) return awfm_fail(AWFM_GPU_ERR_ARG, "numBlocks does not match bwtLength");
+  if (v->saBytes && (v->saRatio == 0 || v->saBitWidth == 0 || v->saBitWidth > 64)) return awfm_fail(AWFM_GPU_ERR_ARG, "bad SA ratio / bit width");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return fail(AWFM_GPU_ERR_NO_DEVICE, "no such CUDA device");
+  if (device < 0 || device >= ndev) return awfm_fail(AWFM_GPU_ERR_NO_DEVICE, "no such CUDA device");
   CU(cudaSetDevice(device));
   awfm_gpu_ctx *c = new awfm_gpu_ctx();
   c->device = device;
@@ -183,7 +150,7 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
     cudaError_t e_ = (call);                                           \
     if (e_ != cudaSuccess) {                                           \
       cudaGetLastError();                                              \
-      return bail(fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, #call, cudaGetErrorString(e_))); \
+      return bail(awfm_fail(e_ == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, #call, cudaGetErrorString(e_))); \
     }                                                                  \
   } while (0)
 
@@ -290,13 +257,7 @@ static int ctxCreateCommon(awfm_gpu_ctx **out, int device, const awfm_index_view
   c->locateLpq = amino ? 4 : 1;
   ix.deepSeedTable = nullptr;
   ix.deepSeedK = ix.deepSeedWide = 0;
-  CUB_(cudaMalloc(&c->sc.dWorkCounter, 64));
-  for (auto &s : c->slots) {
-    CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    CUB_(cudaEventCreateWithFlags(&s.offsetsDone, cudaEventDisableTiming));
-    CUB_(cudaMalloc(&s.sc.dWorkCounter, 64));
-  }
+  if (int r = awfm_lane_prepare(c, c->lanes[0])) return bail(r);  // the other lanes are prepared on first use
 #undef CUB_
   *out = c;
   return AWFM_GPU_OK;
@@ -324,18 +285,18 @@ struct AwfmiSections {
 static int parseAwfmi(const uint8_t *f, uint64_t fileBytes, AwfmiSections *o) {
   memset(o, 0, sizeof *o);
   o->fileBytes = fileBytes;
-  if (fileBytes < 30 || memcmp(f, "AwFmIndex\n", 10) != 0) return fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (bad magic)");
+  if (fileBytes < 30 || memcmp(f, "AwFmIndex\n", 10) != 0) return awfm_fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (bad magic)");
   memcpy(&o->version, f + 10, 4);
   memcpy(&o->featureFlags, f + 14, 4);
-  if (o->version != 8) return fail(AWFM_GPU_ERR_ARG, "unsupported .awfmi version (this loader reads version 8)");
+  if (o->version != 8) return awfm_fail(AWFM_GPU_ERR_ARG, "unsupported .awfmi version (this loader reads version 8)");
   o->saRatio = f[18], o->seedK = f[19], o->alphabet = f[20], o->storesSequence = f[21];
   memcpy(&o->bwtLength, f + 22, 8);
-  if (o->alphabet < 1 || o->alphabet > 3 || o->saRatio == 0 || o->bwtLength < 2) return fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header");
+  if (o->alphabet < 1 || o->alphabet > 3 || o->saRatio == 0 || o->bwtLength < 2) return awfm_fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header");
   const bool amino = o->alphabet == 1;
   o->numBlocks = 1 + (o->bwtLength - 1) / 256;
   o->blockBytes = amino ? 352 : 160;
   o->numPrefix = amino ? 22 : 6;
-  if (o->seedK > (amino ? 14 : 31)) return fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header (seed length)");
+  if (o->seedK > (amino ? 14 : 31)) return awfm_fail(AWFM_GPU_ERR_ARG, "corrupt .awfmi header (seed length)");
   o->numSeeds = numSeedsOf(o->alphabet, o->seedK);
   o->blocksOff = 30;
   o->prefixOff = o->blocksOff + o->numBlocks * o->blockBytes;
@@ -345,33 +306,33 @@ static int parseAwfmi(const uint8_t *f, uint64_t fileBytes, AwfmiSections *o) {
   const uint64_t samples = (o->bwtLength + o->saRatio - 1) / o->saRatio;                     // :144-147
   o->saBytes = (samples * o->saBitWidth + 7) / 8 + 8;                                        // :41-53
   uint64_t end = o->saOff + o->saBytes;
-  if (end > fileBytes) return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file");
+  if (end > fileBytes) return awfm_fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file");
   if (o->featureFlags & 1u) {  // FastaVector section: header length, record count, header chars, record table
-    if (end + 16 > fileBytes) return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
+    if (end + 16 > fileBytes) return awfm_fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
     memcpy(&o->headerBytes, f + end, 8);
     memcpy(&o->numSequences, f + end + 8, 8);
     o->headerOff = end + 16;
     o->metaOff = o->headerOff + o->headerBytes;
     if (o->metaOff < o->headerOff || o->numSequences > (fileBytes - o->metaOff) / 16 || o->metaOff > fileBytes)
-      return fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
+      return awfm_fail(AWFM_GPU_ERR_ARG, "truncated .awfmi file (FastaVector section)");
   }
   return AWFM_GPU_OK;
 }
 
 extern "C" int awfm_gpu_ctx_create_from_file(awfm_gpu_ctx **ctx, int device, const char *path, int wantSuffixArray,
                                              awfm_file_info *info) {
-  if (!ctx || !path) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (!ctx || !path) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
   const int fd = open(path, O_RDONLY);
-  if (fd < 0) return fail(AWFM_GPU_ERR_ARG, "cannot open index file", path);
+  if (fd < 0) return awfm_fail(AWFM_GPU_ERR_ARG, "cannot open index file", path);
   struct stat st;
   if (fstat(fd, &st) != 0 || st.st_size < 30) {
     close(fd);
-    return fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (too short)", path);
+    return awfm_fail(AWFM_GPU_ERR_ARG, "not an .awfmi file (too short)", path);
   }
   const uint64_t bytes = (uint64_t)st.st_size;
   void *map = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
   close(fd);
-  if (map == MAP_FAILED) return fail(AWFM_GPU_ERR_ALLOC, "mmap of the index file failed", path);
+  if (map == MAP_FAILED) return awfm_fail(AWFM_GPU_ERR_ALLOC, "mmap of the index file failed", path);
   madvise(map, bytes, MADV_SEQUENTIAL);
   const uint8_t *f = (const uint8_t *)map;
   AwfmiSections sec;
@@ -420,7 +381,6 @@ extern "C" int awfm_gpu_ctx_create_from_file(awfm_gpu_ctx **ctx, int device, con
 
 static void freeScratch(LocateScratch &sc) {
   cudaFree(sc.scanTemp);
-  cudaFree(sc.dLengths);
   cudaFree(sc.dWorkCounter);
   sc = LocateScratch();
 }
@@ -453,14 +413,31 @@ static void freeSlot(PipeSlot &s) {
   s = PipeSlot();
 }
 
+static void freeLane(Lane &L) {
+  for (auto &s : L.slots) freeSlot(s);
+  for (auto &e : L.kernelEvents) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  L.kernelEvents.clear();
+  freeScratch(L.sc);
+  freeSweep(L.sweep);
+  if (L.hBigPos) cudaFreeHost(L.hBigPos);
+  cudaFree(L.dBigPos);
+  L.hBigPos = L.dBigPos = nullptr, L.bigPosCap = 0;
+  if (L.unpackDone) cudaEventDestroy(L.unpackDone);
+  L.unpackDone = nullptr;
+  for (GrowBuf *b : {&L.dLetters, &L.dOffsets, &L.dCounts, &L.dRanges, &L.dHits, &L.dPositions, &L.dUnpacked}) b->release();
+  L.ready = false;
+}
+
 extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto &s : c->slots) freeSlot(s);
-  for (auto &e : c->kernelEvents) {
-    cudaEventDestroy(e.a);
-    cudaEventDestroy(e.b);
+  {
+    AllLanesHold all(c);  // waits for calls still in flight on any lane
+    for (auto &l : c->lanes) freeLane(l);
   }
   cudaFree(c->dLines);
   cudaFree(c->dXRel16);
@@ -470,18 +447,14 @@ extern "C" void awfm_gpu_ctx_destroy(awfm_gpu_ctx *c) {
   cudaFree(c->dSequenceEnds);
   cudaFree(c->dDeepSeed);
   cudaFree(c->dDenseSa);
-  freeScratch(c->sc);
-  freeSweep(c->sweep);
-  if (c->hBigPos) cudaFreeHost(c->hBigPos);
-  cudaFree(c->dBigPos);
   cudaGetLastError();
   delete c;
 }
 
-extern "C" uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *c) { return c ? c->deviceBytes : 0; }
+extern "C" uint64_t awfm_gpu_ctx_device_bytes(const awfm_gpu_ctx *c) { return c ? c->deviceBytes.load() : 0; }
 
 extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t value) {
-  if (!c || !key) return fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (!c || !key) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
   const std::string k(key);
   auto lpqOk = [](int64_t v) { return v == 1 || v == 2 || v == 4 || v == 8; };
   if (k == "count_lpq" && lpqOk(value)) c->countLpq = (int)value;
@@ -505,37 +478,39 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
     c->ix.deepSeedTable = on ? c->dDeepSeed : nullptr;
     c->ix.deepSeedK = on ? c->deepSeedKBuilt : 0;
   }
-  else return fail(AWFM_GPU_ERR_ARG, "unknown tuning key or bad value", key);
+  else return awfm_fail(AWFM_GPU_ERR_ARG, "unknown tuning key or bad value", key);
   return AWFM_GPU_OK;
 }
 
 // ---- kernel event bookkeeping (device time of OUR kernels on the launching stream) ----
-static void beginCall(awfm_gpu_ctx *c) {
-  c->eventsUsed = 0;
-  c->stats = awfm_gpu_stats{};
+void awfm_begin_call(Lane &L) {
+  L.eventsUsed = 0;
+  L.stats = awfm_gpu_stats{};
 }
-static EventPair *nextEvents(awfm_gpu_ctx *c) {
-  if (c->eventsUsed == c->kernelEvents.size()) {
+static EventPair *nextEvents(Lane &L) {
+  if (L.eventsUsed == L.kernelEvents.size()) {
     EventPair p;
     if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return nullptr;
-    c->kernelEvents.push_back(p);
+    L.kernelEvents.push_back(p);
   }
-  return &c->kernelEvents[c->eventsUsed++];
+  return &L.kernelEvents[L.eventsUsed++];
 }
 
+// Stats of the most recent call on the context (the lane it ran on).  Not meaningful while another call is in flight.
 extern "C" int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *cc, awfm_gpu_stats *out) {
   awfm_gpu_ctx *c = const_cast<awfm_gpu_ctx *>(cc);
-  if (!c || !out) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (setDevice(c)) return AWFM_GPU_ERR_CUDA;
+  if (!c || !out) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (awfm_set_device(c)) return AWFM_GPU_ERR_CUDA;
+  Lane &L = c->lanes[c->lastLane.load()];
   double ms = 0;
-  for (size_t i = 0; i < c->eventsUsed; i++) {
-    CU(cudaEventSynchronize(c->kernelEvents[i].b));
+  for (size_t i = 0; i < L.eventsUsed; i++) {
+    CU(cudaEventSynchronize(L.kernelEvents[i].b));
     float f = 0;
-    CU(cudaEventElapsedTime(&f, c->kernelEvents[i].a, c->kernelEvents[i].b));
+    CU(cudaEventElapsedTime(&f, L.kernelEvents[i].a, L.kernelEvents[i].b));
     ms += f;
   }
-  c->stats.kernelMs = ms;
-  *out = c->stats;
+  L.stats.kernelMs = ms;
+  *out = L.stats;
   return AWFM_GPU_OK;
 }
 
@@ -623,7 +598,7 @@ static int launchLocate(awfm_gpu_ctx *c, LocateScratch &sc, const uint4 *dRanges
 
 static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st) {
   if (numHits == 0) return AWFM_GPU_OK;
-  return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, c->sc, numHits, dPos, st);
+  return DISPATCH_LOCATE(launchWalk, c->locateLpq, c->ix.amino != 0, c, c->lanes[0].sc, numHits, dPos, st);
 }
 
 // ---- sweep count path (awfm_sweep.cuh): large fixed-length nucleotide batches, counts only ----
@@ -657,8 +632,8 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
   return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : 8));
 }
 
-static int ensureSweep(awfm_gpu_ctx *c, uint64_t n, int arrays) {
-  SweepScratch &w = c->sweep;
+static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
+  SweepScratch &w = L.sweep;
   if (!w.done) CU(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   while (w.numStages < kSweepMaxPasses + 4) {
     CU(cudaEventCreate(&w.stage[w.numStages]));
@@ -677,7 +652,7 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n, int arrays) {
   if (cudaMalloc(&w.arena, bytes) != cudaSuccess) {
     cudaGetLastError();
     w.arena = nullptr;
-    return fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");
+    return awfm_fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");
   }
   uint8_t *p = static_cast<uint8_t *>(w.arena);
   for (int g = 0; g < 2; g++)
@@ -693,9 +668,9 @@ static int ensureSweep(awfm_gpu_ctx *c, uint64_t n, int arrays) {
 }
 
 template <bool AMINO>
-static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
-                           uint4 *dRanges, cudaStream_t st) {
-  SweepScratch &w = c->sweep;
+static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
+                           uint32_t *dCounts, uint4 *dRanges, cudaStream_t st) {
+  SweepScratch &w = L.sweep;
   const uint32_t k = sweepSeedK(c, len), steps = len - k;
   const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
   int stage = 0;
@@ -710,7 +685,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
   {
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
-    if (AMINO && len % 4 == 0 && len <= 12) {
+    if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
+      const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
+      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0]);
+    } else if (AMINO && len % 4 == 0 && len <= 12) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
         case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
@@ -727,7 +705,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
         AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
         AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
 #undef AWFM_PACK_CASE
-        default: return fail(AWFM_GPU_ERR_ARG, "sweep: query length out of range");
+        default: return awfm_fail(AWFM_GPU_ERR_ARG, "sweep: query length out of range");
       }
     } else {
       const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
@@ -810,56 +788,90 @@ static int sweepCountBatch(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t le
     if (int r = launchPassItems(std::false_type(), pass)) return r;
     mark();
   }
-  sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
-  CU(cudaGetLastError());
+  if (format == AWFM_QUERY_ASCII) {  // (the 2-bit format cannot express an irregular query)
+    sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
+    CU(cudaGetLastError());
+  }
   mark();
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
-  c->stats.launches += 3 + (steps > 1 ? steps - 1 : 0) + (endBit > beginBit ? 3 : 0);
+  L.stats.launches += 2 + (format == AWFM_QUERY_ASCII ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + (endBit > beginBit ? 3 : 0);
   return AWFM_GPU_OK;
 }
 
 // Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
 // slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
-static int sweepCount(awfm_gpu_ctx *c, const uint8_t *dLetters, uint32_t len, uint64_t n, uint32_t *dCounts,
-                      uint4 *dRanges, cudaStream_t st) {
+static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
+                      uint32_t *dCounts, uint4 *dRanges, cudaStream_t st) {
   const bool amino = c->ix.amino != 0;
   const uint64_t maxBatch = amino ? std::min<int64_t>(c->sweepMaxBatch, 1ll << 26) : c->sweepMaxBatch;
   const uint64_t slice = std::min<uint64_t>(n, maxBatch & ~255ull);  // slices start 16-B aligned
-  if (int r = ensureSweep(c, slice, amino ? 10 : 2)) return r;
+  const uint64_t queryBytes = awfm_query_bytes(format, len);
+  if (int r = ensureSweep(c, L, slice, amino ? 10 : 2)) return r;
   for (uint64_t first = 0; first < n; first += slice) {
     const uint64_t m = std::min(slice, n - first);
     uint4 *ranges = dRanges ? dRanges + first : nullptr;
-    const int r = amino ? sweepCountBatch<true>(c, dLetters + first * len, len, m, dCounts + first, ranges, st)
-                        : sweepCountBatch<false>(c, dLetters + first * len, len, m, dCounts + first, ranges, st);
+    const int r = amino ? sweepCountBatch<true>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, st)
+                        : sweepCountBatch<false>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, st);
     if (r) return r;
   }
   return AWFM_GPU_OK;
 }
 
-static int countDeviceImpl(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
-                           uint64_t n, uint32_t *dCounts, awfm_range *dRanges, cudaStream_t st) {
+// One batch of queries on the device: counts and (optionally) every query's final range.  2-/5-bit batches that do not
+// take the sweep path are first expanded to ASCII letters in the lane's scratch (unpackQueries).
+int awfm_count_device_impl(awfm_gpu_ctx *c, Lane &L, const PackedBatch &batch, uint32_t *dCounts, awfm_range *dRanges,
+                           cudaStream_t st) {
+  const uint64_t n = batch.numQueries;
   if (n == 0) return AWFM_GPU_OK;
-  QueryBatch qb{dLetters, dOffsets, n, fixedLen};
-  EventPair *ev = nextEvents(c);
-  if (ev) CU(cudaEventRecord(ev->a, st));
-  int r;
-  const bool sweep = sweepEligible(c, dLetters, dOffsets, fixedLen, n, dRanges);
-  r = sweep ? sweepCount(c, dLetters, fixedLen, n, dCounts, (uint4 *)dRanges, st) : AWFM_GPU_OK;
-  if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
-    c->sweep.stagesRecorded = 0;
-    r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
-    c->stats.launches += 1;
+  if (batch.format != AWFM_QUERY_ASCII && batch.format != AWFM_QUERY_2BIT && batch.format != AWFM_QUERY_5BIT)
+    return awfm_fail(AWFM_GPU_ERR_ARG, "unknown query format");
+  if (batch.format != AWFM_QUERY_ASCII) {
+    if (batch.offsets || batch.length == 0) return awfm_fail(AWFM_GPU_ERR_ARG, "2-/5-bit query batches are fixed-length");
+    if ((batch.format == AWFM_QUERY_5BIT) != (c->ix.amino != 0))
+      return awfm_fail(AWFM_GPU_ERR_ARG, "query format does not match the index alphabet (2-bit: nucleotide, 5-bit: amino)");
   }
+  EventPair *ev = nextEvents(L);
+  if (ev) CU(cudaEventRecord(ev->a, st));
+  const uint8_t *dLetters = batch.data;
+  uint32_t format = batch.format;
+  const uint32_t fixedLen = batch.length;
+  const bool directBits = format == AWFM_QUERY_2BIT && fixedLen <= 32 &&
+                          sweepEligible(c, dLetters, nullptr, fixedLen, n, dRanges);
+  const bool unpack = format != AWFM_QUERY_ASCII && !directBits;
+  if (unpack) {
+    CU(cudaStreamWaitEvent(st, L.unpackDone, 0));
+    if (L.dUnpacked.cap < n * (uint64_t)fixedLen + 16) CU(cudaDeviceSynchronize());  // about to be reallocated
+    if (int r = L.dUnpacked.ensure(n * (uint64_t)fixedLen + 16)) return r;
+    const uint64_t words = (n * (uint64_t)fixedLen + 3) / 4;
+    const int grid = (int)std::min<uint64_t>((words + 255) / 256, (uint64_t)c->numSMs * 16);
+    if (format == AWFM_QUERY_2BIT) unpackQueries<2><<<grid, 256, 0, st>>>(dLetters, n, fixedLen, (uint8_t *)L.dUnpacked.p);
+    else unpackQueries<5><<<grid, 256, 0, st>>>(dLetters, n, fixedLen, (uint8_t *)L.dUnpacked.p);
+    CU(cudaGetLastError());
+    L.stats.launches += 1;
+    dLetters = (const uint8_t *)L.dUnpacked.p;
+    format = AWFM_QUERY_ASCII;
+  }
+  QueryBatch qb{dLetters, batch.offsets, n, fixedLen};
+  int r;
+  const bool sweep = directBits || sweepEligible(c, dLetters, batch.offsets, fixedLen, n, dRanges);
+  r = sweep ? sweepCount(c, L, dLetters, format, fixedLen, n, dCounts, (uint4 *)dRanges, st) : AWFM_GPU_OK;
+  if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
+    L.sweep.stagesRecorded = 0;
+    if (format != AWFM_QUERY_ASCII) return awfm_fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");
+    r = DISPATCH_COUNT(launchCount, c->countLpq, c->ix.amino != 0, c, qb, dCounts, (uint4 *)dRanges, st);
+    L.stats.launches += 1;
+  }
+  if (unpack) CU(cudaEventRecord(L.unpackDone, st));
   if (ev) CU(cudaEventRecord(ev->b, st));
-  c->stats.queries += n;
+  L.stats.queries += n;
   return r;
 }
 
 extern "C" int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *c, double *ms, int capacity) {
-  if (!c || !ms) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (int r = setDevice(c)) return r;
-  SweepScratch &w = c->sweep;
+  if (!c || !ms) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  SweepScratch &w = c->lanes[c->lastLane.load()].sweep;
   int n = 0;
   for (int i = 0; i + 1 < w.stagesRecorded && n < capacity; i++, n++) {
     if (cudaEventSynchronize(w.stage[i + 1]) != cudaSuccess) break;
@@ -874,64 +886,74 @@ extern "C" int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *c, double *ms, int capa
 extern "C" int awfm_gpu_count_device(awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets,
                                      uint32_t fixedLen, uint64_t n, uint32_t *dCounts, awfm_range *dRanges,
                                      void *stream) {
-  if (!c || !dCounts || (n && !dLetters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (int r = setDevice(c)) return r;
-  beginCall(c);
-  return countDeviceImpl(c, dLetters, dOffsets, fixedLen, n, dCounts, dRanges, (cudaStream_t)stream);
+  return awfm_gpu_count_device_format(c, dLetters, AWFM_QUERY_ASCII, dOffsets, fixedLen, n, dCounts, dRanges, stream);
 }
 
-static int scanImpl(awfm_gpu_ctx *c, LocateScratch &sc, const awfm_range *dRanges, uint64_t n, uint64_t *dHitOffsets,
-                    cudaStream_t st) {
-  if (sc.lengthsCap < n + 1) {
-    cudaFree(sc.dLengths);
-    sc.dLengths = nullptr;
-    sc.lengthsCap = 0;
-    CU(cudaMalloc(&sc.dLengths, (n + 1) * 8));
-    sc.lengthsCap = n + 1;
-  }
-  size_t need = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, need, sc.dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
+extern "C" int awfm_gpu_count_device_format(awfm_gpu_ctx *c, const void *dQueries, uint32_t format,
+                                            const uint64_t *dOffsets, uint32_t fixedLen, uint64_t n, uint32_t *dCounts,
+                                            awfm_range *dRanges, void *stream) {
+  if (!c || !dCounts || (n && !dQueries)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  Lane &L = c->lanes[0];
+  c->lastLane.store(0);
+  awfm_begin_call(L);
+  PackedBatch b;
+  b.data = (const uint8_t *)dQueries, b.offsets = dOffsets, b.format = format, b.length = fixedLen, b.numQueries = n;
+  return awfm_count_device_impl(c, L, b, dCounts, dRanges, (cudaStream_t)stream);
+}
+
+// hitOffsets[q] = base + sum of the (u32-truncated) range lengths of the queries before q; hitOffsets[n] = base + total
+int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range *dRanges, uint64_t n,
+                   uint64_t *dHitOffsets, uint64_t base, cudaStream_t st) {
+  (void)c;
+  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+  const size_t need = (tiles + 1) * sizeof(uint64_t);
   if (need > sc.scanTempBytes) {
+    CU(cudaStreamSynchronize(st));
     cudaFree(sc.scanTemp);
     sc.scanTemp = nullptr;
     sc.scanTempBytes = 0;
-    CU(cudaMalloc(&sc.scanTemp, need));
-    sc.scanTempBytes = need;
+    CU(cudaMalloc(&sc.scanTemp, need + need / 4));
+    sc.scanTempBytes = need + need / 4;
   }
-  CU(cudaMemsetAsync(sc.dLengths + n, 0, 8, st));
-  if (n) rangeLengths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)dRanges, n, sc.dLengths);
+  uint64_t *tileSums = (uint64_t *)sc.scanTemp;
+  if (tiles) scanTileSums<<<(unsigned)tiles, 256, 0, st>>>((const uint4 *)dRanges, n, tileSums);
+  scanTileBases<<<1, 256, 0, st>>>(tileSums, tiles, base);
+  if (tiles) scanTileOffsets<<<(unsigned)tiles, 256, 0, st>>>((const uint4 *)dRanges, n, tileSums, dHitOffsets);
+  else CU(cudaMemcpyAsync(dHitOffsets, tileSums, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
   CU(cudaGetLastError());
-  CU(cub::DeviceScan::ExclusiveSum(sc.scanTemp, need, sc.dLengths, dHitOffsets, (unsigned long long)(n + 1), st));
-  c->stats.launches += 3;
+  L.stats.launches += tiles ? 3 : 1;
   return AWFM_GPU_OK;
 }
 
 extern "C" int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *c, const awfm_range *dRanges, uint64_t n,
                                            uint64_t *dHitOffsets, void *stream) {
-  if (!c || !dHitOffsets || (n && !dRanges)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (int r = setDevice(c)) return r;
-  return scanImpl(c, c->sc, dRanges, n, dHitOffsets, (cudaStream_t)stream);
+  if (!c || !dHitOffsets || (n && !dRanges)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  return awfm_scan_impl(c, c->lanes[0], c->lanes[0].sc, dRanges, n, dHitOffsets, 0, (cudaStream_t)stream);
 }
 
-static int locateDeviceImpl(awfm_gpu_ctx *c, LocateScratch &sc, const awfm_range *dRanges, const uint64_t *dHitOffsets,
-                            uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, cudaStream_t st) {
-  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+// Backtrace walk of the flat hit indices [hb, he) (in the numbering of dHitOffsets) into dPos[h - hb].
+int awfm_locate_device_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range *dRanges,
+                            const uint64_t *dHitOffsets, uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos,
+                            cudaStream_t st) {
+  if (!c->hasSa) return awfm_fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
   if (he <= hb) return AWFM_GPU_OK;
-  EventPair *ev = nextEvents(c);
+  EventPair *ev = nextEvents(L);
   if (ev) CU(cudaEventRecord(ev->a, st));
   int r = DISPATCH_LOCATE(launchLocate, c->locateLpq, c->ix.amino != 0, c, sc, (const uint4 *)dRanges, dHitOffsets, n,
                           hb, he, dPos, st);
   if (ev) CU(cudaEventRecord(ev->b, st));
-  c->stats.launches += 2;
-  c->stats.hits += he - hb;
+  L.stats.launches += 2;
+  L.stats.hits += he - hb;
   return r;
 }
 
 extern "C" int awfm_gpu_locate_device(awfm_gpu_ctx *c, const awfm_range *dRanges, const uint64_t *dHitOffsets,
                                       uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos, void *stream) {
-  if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (int r = setDevice(c)) return r;
-  return locateDeviceImpl(c, c->sc, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
+  if (!c || !dRanges || !dHitOffsets || (he > hb && !dPos)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  return awfm_locate_device_impl(c, c->lanes[0], c->lanes[0].sc, dRanges, dHitOffsets, n, hb, he, dPos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ derived structures
@@ -956,7 +978,7 @@ static int extendSeedLevels(awfm_gpu_ctx *c, uint32_t depth, bool wide) {
     if (e != cudaSuccess) {
       cudaGetLastError();
       cudaFree(prev);
-      return fail(AWFM_GPU_ERR_ALLOC, "derived seed table does not fit in device memory", cudaGetErrorString(e));
+      return awfm_fail(AWFM_GPU_ERR_ALLOC, "derived seed table does not fit in device memory", cudaGetErrorString(e));
     }
     const int grid = c->numSMs * 8;
     if (srcWide && wide) extendSeedTable<AMINO, true, true><<<grid, 256>>>(c->ix, src, numSrc, dst);
@@ -968,7 +990,7 @@ static int extendSeedLevels(awfm_gpu_ctx *c, uint32_t depth, bool wide) {
     if (e != cudaSuccess) {
       cudaGetLastError();
       cudaFree(dst);
-      return fail(AWFM_GPU_ERR_CUDA, "extendSeedTable", cudaGetErrorString(e));
+      return awfm_fail(AWFM_GPU_ERR_CUDA, "extendSeedTable", cudaGetErrorString(e));
     }
     prev = dst;
     src = dst;
@@ -981,9 +1003,9 @@ static int extendSeedLevels(awfm_gpu_ctx *c, uint32_t depth, bool wide) {
 }
 
 extern "C" int awfm_gpu_ctx_extend_seed_table(awfm_gpu_ctx *c, uint32_t depth, double *buildMs) {
-  if (!c) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
+  if (!c) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  AllLanesHold all(c);
+  if (int r = awfm_set_device(c)) return r;
   CU(cudaDeviceSynchronize());
   const double t0 = omp_get_wtime();
   if (buildMs) *buildMs = 0;
@@ -997,7 +1019,7 @@ extern "C" int awfm_gpu_ctx_extend_seed_table(awfm_gpu_ctx *c, uint32_t depth, d
   c->deepSeedKBuilt = 0;
   if (depth <= c->ix.seedK) return AWFM_GPU_OK;
   const bool amino = c->ix.amino != 0;
-  if (depth > (amino ? 9u : 20u)) return fail(AWFM_GPU_ERR_ARG, "seed table depth too large (max 20 nucleotide, 9 amino)");
+  if (depth > (amino ? 9u : 20u)) return awfm_fail(AWFM_GPU_ERR_ARG, "seed table depth too large (max 20 nucleotide, 9 amino)");
   const bool wide = c->ix.bwtLength > (1ull << 32);
   int rc = amino ? extendSeedLevels<true>(c, depth, wide) : extendSeedLevels<false>(c, depth, wide);
   if (rc) return rc;
@@ -1013,10 +1035,10 @@ extern "C" int awfm_gpu_ctx_extend_seed_table(awfm_gpu_ctx *c, uint32_t depth, d
 static int locateDeviceRaw(awfm_gpu_ctx *c, uint64_t numHits, uint64_t *dPos, cudaStream_t st);
 
 extern "C" int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *c, uint32_t newRatio, double *buildMs) {
-  if (!c) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  if (!c) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  AllLanesHold all(c);
+  if (int r = awfm_set_device(c)) return r;
+  if (!c->hasSa) return awfm_fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
   CU(cudaDeviceSynchronize());
   const double t0 = omp_get_wtime();
   if (buildMs) *buildMs = 0;
@@ -1043,10 +1065,10 @@ extern "C" int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *c, uint32_t newRa
     cudaGetLastError();
     cudaFree(dense);
     cudaFree(work);
-    return fail(AWFM_GPU_ERR_ALLOC, "dense suffix array does not fit in device memory");
+    return awfm_fail(AWFM_GPU_ERR_ALLOC, "dense suffix array does not fit in device memory");
   }
   cudaMemset(dense, 0, bytes);
-  cudaStream_t st = c->slots[0].stream;
+  cudaStream_t st = c->lanes[0].slots[0].stream;
   int rc = AWFM_GPU_OK;
   for (uint64_t first = 0; first < samples && rc == AWFM_GPU_OK; first += slab) {
     const uint64_t count = std::min(slab, samples - first);
@@ -1055,7 +1077,7 @@ extern "C" int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *c, uint32_t newRa
     if (rc == AWFM_GPU_OK) {
       if (width == 32) saNarrow<uint32_t><<<c->numSMs * 8, 256, 0, st>>>(work, count, (uint32_t *)dense + first);
       else saNarrow<uint64_t><<<c->numSMs * 8, 256, 0, st>>>(work, count, (uint64_t *)dense + first);
-      if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "densify suffix array", cudaGetErrorString(cudaGetLastError()));
+      if (cudaStreamSynchronize(st) != cudaSuccess) rc = awfm_fail(AWFM_GPU_ERR_CUDA, "densify suffix array", cudaGetErrorString(cudaGetLastError()));
     }
   }
   cudaFree(work);
@@ -1080,9 +1102,9 @@ extern "C" int awfm_gpu_ctx_densify_suffix_array(awfm_gpu_ctx *c, uint32_t newRa
 
 // ------------------------------------------------------------------------------------------------ contig mapping
 extern "C" int awfm_gpu_ctx_set_sequences(awfm_gpu_ctx *c, const void *metadata, uint64_t numSequences) {
-  if (!c || (numSequences && !metadata)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
+  if (!c || (numSequences && !metadata)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  AllLanesHold all(c);
+  if (int r = awfm_set_device(c)) return r;
   CU(cudaDeviceSynchronize());
   cudaFree(c->dSequenceEnds);
   c->dSequenceEnds = nullptr;
@@ -1094,7 +1116,7 @@ extern "C" int awfm_gpu_ctx_set_sequences(awfm_gpu_ctx *c, const void *metadata,
   const uint64_t *m = (const uint64_t *)metadata;
   for (uint64_t i = 0; i < numSequences; i++) {
     ends[i] = m[2 * i + 1];
-    if (i && ends[i] < ends[i - 1]) return fail(AWFM_GPU_ERR_ARG, "sequenceEndPosition must be non-decreasing");
+    if (i && ends[i] < ends[i - 1]) return awfm_fail(AWFM_GPU_ERR_ARG, "sequenceEndPosition must be non-decreasing");
   }
   CU(cudaMalloc(&c->dSequenceEnds, numSequences * 8));
   CU(cudaMemcpy(c->dSequenceEnds, ends.data(), numSequences * 8, cudaMemcpyHostToDevice));
@@ -1104,141 +1126,144 @@ extern "C" int awfm_gpu_ctx_set_sequences(awfm_gpu_ctx *c, const void *metadata,
   return AWFM_GPU_OK;
 }
 
-static int mapDeviceImpl(awfm_gpu_ctx *c, const uint64_t *dPos, uint64_t n, uint64_t *dSeq, uint64_t *dLocal,
+int awfm_map_device_impl(awfm_gpu_ctx *c, Lane &L, const uint64_t *dPos, uint64_t n, uint64_t *dSeq, uint64_t *dLocal,
                          cudaStream_t st) {
-  if (!c->ix.sequenceEnds) return fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
+  if (!c->ix.sequenceEnds) return awfm_fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
   if (n == 0) return AWFM_GPU_OK;
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8);
-  EventPair *ev = nextEvents(c);
+  EventPair *ev = nextEvents(L);
   if (ev) CU(cudaEventRecord(ev->a, st));
   mapPositionsKernel<<<grid, 256, 0, st>>>(c->ix.sequenceEnds, c->ix.numSequences, dPos, n, dSeq, dLocal);
   CU(cudaGetLastError());
   if (ev) CU(cudaEventRecord(ev->b, st));
-  c->stats.launches += 1;
+  L.stats.launches += 1;
   return AWFM_GPU_OK;
 }
 
 extern "C" int awfm_gpu_map_positions_device(awfm_gpu_ctx *c, const uint64_t *dPositions, uint64_t n,
                                              uint64_t *dSequenceIndex, uint64_t *dLocalPosition, void *stream) {
-  if (!c || (n && (!dPositions || !dSequenceIndex || !dLocalPosition))) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  if (int r = setDevice(c)) return r;
-  return mapDeviceImpl(c, dPositions, n, dSequenceIndex, dLocalPosition, (cudaStream_t)stream);
+  if (!c || (n && (!dPositions || !dSequenceIndex || !dLocalPosition))) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  return awfm_map_device_impl(c, c->lanes[0], dPositions, n, dSequenceIndex, dLocalPosition, (cudaStream_t)stream);
 }
 
 extern "C" int awfm_gpu_map_positions_host(awfm_gpu_ctx *c, const uint64_t *positions, uint64_t n,
                                            uint64_t *sequenceIndex, uint64_t *localPosition, uint64_t *numIllegal) {
-  if (!c || (n && (!positions || !sequenceIndex || !localPosition))) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  beginCall(c);
+  if (!c || (n && (!positions || !sequenceIndex || !localPosition))) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  LaneHold hold(c);
+  if (hold.rc) return hold.rc;
+  Lane &L = *hold;
+  awfm_begin_call(L);
   if (numIllegal) *numIllegal = 0;
-  if (!c->ix.sequenceEnds) return fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
+  if (!c->ix.sequenceEnds) return awfm_fail(AWFM_GPU_ERR_ARG, "context has no sequence table (awfm_gpu_ctx_set_sequences)");
   if (n == 0) return AWFM_GPU_OK;
-  cudaStream_t st = c->slots[0].stream;
+  cudaStream_t st = L.slots[0].stream;
   const uint64_t batch = std::min<uint64_t>(n, 1ull << 27);  // bounded staging: 3 x 1 GiB
-  uint64_t *d = nullptr;
-  CU(cudaMalloc(&d, batch * 24));
+  if (int r = L.dPositions.ensure(batch * 24)) return r;
+  uint64_t *d = (uint64_t *)L.dPositions.p;
   int rc = AWFM_GPU_OK;
   uint64_t illegal = 0;
   for (uint64_t b0 = 0; b0 < n && rc == AWFM_GPU_OK; b0 += batch) {
     const uint64_t nb = std::min(batch, n - b0);
     cudaError_t e = cudaMemcpyAsync(d, positions + b0, nb * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) rc = mapDeviceImpl(c, d, nb, d + batch, d + 2 * batch, st);
+    if (e == cudaSuccess) rc = awfm_map_device_impl(c, L, d, nb, d + batch, d + 2 * batch, st);
     if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaMemcpyAsync(sequenceIndex + b0, d + batch, nb * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaMemcpyAsync(localPosition + b0, d + 2 * batch, nb * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && rc == AWFM_GPU_OK) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "map positions", cudaGetErrorString(e));
+    if (e != cudaSuccess) rc = awfm_fail(AWFM_GPU_ERR_CUDA, "map positions", cudaGetErrorString(e));
     if (rc == AWFM_GPU_OK && numIllegal)
       for (uint64_t i = b0; i < b0 + nb; i++) illegal += sequenceIndex[i] == ~0ull;
   }
-  cudaFree(d);
   if (numIllegal) *numIllegal = illegal;
-  c->stats.h2dBytes = n * 8;
-  c->stats.d2hBytes = n * 16;
+  L.stats.h2dBytes = n * 8;
+  L.stats.d2hBytes = n * 16;
   return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer calls
-struct DevBuf {  // RAII device scratch
-  void *p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-};
-
+// Single-device, synchronous, one batch at a time; device buffers persist in the lane between calls.  (The pipelined,
+// multi-GPU engine for large host batches is awfm_gpu_group_* in awfm_multi.cu.)
 static uint64_t totalLetters(const uint64_t *offsets, uint32_t fixedLen, uint64_t n) {
   return offsets ? offsets[n] : n * (uint64_t)fixedLen;
 }
 
 extern "C" int awfm_gpu_count_host(awfm_gpu_ctx *c, const uint8_t *letters, const uint64_t *offsets,
                                    uint32_t fixedLen, uint64_t n, uint32_t *counts, awfm_range *ranges) {
-  if (!c || !counts || (n && !letters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  beginCall(c);
+  if (!c || !counts || (n && !letters)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  LaneHold hold(c);
+  if (hold.rc) return hold.rc;
+  Lane &L = *hold;
+  awfm_begin_call(L);
   if (n == 0) return AWFM_GPU_OK;
   const uint64_t nLetters = totalLetters(offsets, fixedLen, n);
-  DevBuf dL, dO, dC, dR;
-  CU(dL.alloc(nLetters + 16));
-  CU(dC.alloc(n * 4));
-  if (offsets) CU(dO.alloc((n + 1) * 8));
-  if (ranges) CU(dR.alloc(n * 16));
-  cudaStream_t st = c->slots[0].stream;
-  CU(cudaMemcpyAsync(dL.p, letters, nLetters, cudaMemcpyHostToDevice, st));
-  if (offsets) CU(cudaMemcpyAsync(dO.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (int r = countDeviceImpl(c, (const uint8_t *)dL.p, offsets ? (const uint64_t *)dO.p : nullptr, fixedLen, n,
-                              (uint32_t *)dC.p, ranges ? (awfm_range *)dR.p : nullptr, st))
+  if (int r = L.dLetters.ensure(nLetters + 16)) return r;
+  if (int r = L.dCounts.ensure(n * 4)) return r;
+  if (offsets)
+    if (int r = L.dOffsets.ensure((n + 1) * 8)) return r;
+  if (ranges)
+    if (int r = L.dRanges.ensure(n * 16)) return r;
+  cudaStream_t st = L.slots[0].stream;
+  CU(cudaMemcpyAsync(L.dLetters.p, letters, nLetters, cudaMemcpyHostToDevice, st));
+  if (offsets) CU(cudaMemcpyAsync(L.dOffsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  PackedBatch b;
+  b.data = (const uint8_t *)L.dLetters.p, b.offsets = offsets ? (const uint64_t *)L.dOffsets.p : nullptr;
+  b.length = fixedLen, b.numQueries = n;
+  if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)L.dCounts.p, ranges ? (awfm_range *)L.dRanges.p : nullptr, st))
     return r;
-  CU(cudaMemcpyAsync(counts, dC.p, n * 4, cudaMemcpyDeviceToHost, st));
-  if (ranges) CU(cudaMemcpyAsync(ranges, dR.p, n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(counts, L.dCounts.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (ranges) CU(cudaMemcpyAsync(ranges, L.dRanges.p, n * 16, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  c->stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
-  c->stats.d2hBytes = n * 4 + (ranges ? n * 16 : 0);
+  L.stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
+  L.stats.d2hBytes = n * 4 + (ranges ? n * 16 : 0);
   return AWFM_GPU_OK;
 }
 
 extern "C" int awfm_gpu_locate_host(awfm_gpu_ctx *c, const uint8_t *letters, const uint64_t *offsets,
                                     uint32_t fixedLen, uint64_t n, uint64_t *hitOffsets, uint64_t *positions,
                                     uint64_t positionsCapacity, awfm_range *ranges) {
-  if (!c || !hitOffsets || (n && !letters)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  if (!c->hasSa && positions) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
-  beginCall(c);
+  if (!c || !hitOffsets || (n && !letters)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  LaneHold hold(c);
+  if (hold.rc) return hold.rc;
+  Lane &L = *hold;
+  if (!c->hasSa && positions) return awfm_fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
+  awfm_begin_call(L);
   hitOffsets[0] = 0;
   if (n == 0) return AWFM_GPU_OK;
   const uint64_t nLetters = totalLetters(offsets, fixedLen, n);
-  DevBuf dL, dO, dC, dR, dH, dP;
-  CU(dL.alloc(nLetters + 16));
-  CU(dC.alloc(n * 4));
-  CU(dR.alloc(n * 16));
-  CU(dH.alloc((n + 1) * 8));
-  if (offsets) CU(dO.alloc((n + 1) * 8));
-  cudaStream_t st = c->slots[0].stream;
-  CU(cudaMemcpyAsync(dL.p, letters, nLetters, cudaMemcpyHostToDevice, st));
-  if (offsets) CU(cudaMemcpyAsync(dO.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (int r = countDeviceImpl(c, (const uint8_t *)dL.p, offsets ? (const uint64_t *)dO.p : nullptr, fixedLen, n,
-                              (uint32_t *)dC.p, (awfm_range *)dR.p, st))
-    return r;
-  if (int r = scanImpl(c, c->sc, (const awfm_range *)dR.p, n, (uint64_t *)dH.p, st)) return r;
-  CU(cudaMemcpyAsync(hitOffsets, dH.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-  if (ranges) CU(cudaMemcpyAsync(ranges, dR.p, n * 16, cudaMemcpyDeviceToHost, st));
+  if (int r = L.dLetters.ensure(nLetters + 16)) return r;
+  if (int r = L.dCounts.ensure(n * 4)) return r;
+  if (int r = L.dRanges.ensure(n * 16)) return r;
+  if (int r = L.dHits.ensure((n + 1) * 8)) return r;
+  if (offsets)
+    if (int r = L.dOffsets.ensure((n + 1) * 8)) return r;
+  cudaStream_t st = L.slots[0].stream;
+  CU(cudaMemcpyAsync(L.dLetters.p, letters, nLetters, cudaMemcpyHostToDevice, st));
+  if (offsets) CU(cudaMemcpyAsync(L.dOffsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  PackedBatch b;
+  b.data = (const uint8_t *)L.dLetters.p, b.offsets = offsets ? (const uint64_t *)L.dOffsets.p : nullptr;
+  b.length = fixedLen, b.numQueries = n;
+  if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)L.dCounts.p, (awfm_range *)L.dRanges.p, st)) return r;
+  if (int r = awfm_scan_impl(c, L, L.sc, (const awfm_range *)L.dRanges.p, n, (uint64_t *)L.dHits.p, 0, st)) return r;
+  CU(cudaMemcpyAsync(hitOffsets, L.dHits.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (ranges) CU(cudaMemcpyAsync(ranges, L.dRanges.p, n * 16, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   const uint64_t total = hitOffsets[n];
-  c->stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
-  c->stats.d2hBytes = (n + 1) * 8 + (ranges ? n * 16 : 0);
+  L.stats.h2dBytes = nLetters + (offsets ? (n + 1) * 8 : 0);
+  L.stats.d2hBytes = (n + 1) * 8 + (ranges ? n * 16 : 0);
   if (!positions || total == 0) return AWFM_GPU_OK;
-  if (positionsCapacity < total) return fail(AWFM_GPU_ERR_ARG, "positions buffer smaller than hitOffsets[numQueries]");
+  if (positionsCapacity < total) return awfm_fail(AWFM_GPU_ERR_ARG, "positions buffer smaller than hitOffsets[numQueries]");
   // bounded device staging: at most 1 Gi hits (8 GB) per launch
   const uint64_t batch = std::min<uint64_t>(total, 1ull << 30);
-  CU(dP.alloc(batch * 8));
+  if (int r = L.dPositions.ensure(batch * 8)) return r;
   for (uint64_t hb = 0; hb < total; hb += batch) {
     const uint64_t he = std::min(total, hb + batch);
-    if (int r = locateDeviceImpl(c, c->sc, (const awfm_range *)dR.p, (const uint64_t *)dH.p, n, hb, he, (uint64_t *)dP.p, st))
+    if (int r = awfm_locate_device_impl(c, L, L.sc, (const awfm_range *)L.dRanges.p, (const uint64_t *)L.dHits.p, n, hb, he,
+                                        (uint64_t *)L.dPositions.p, st))
       return r;
-    CU(cudaMemcpyAsync(positions + hb, dP.p, (he - hb) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(positions + hb, L.dPositions.p, (he - hb) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
-  c->stats.d2hBytes += total * 8;
+  L.stats.d2hBytes += total * 8;
   return AWFM_GPU_OK;
 }
 
@@ -1256,8 +1281,8 @@ static int ensureSlot(PipeSlot &s, uint64_t queries, uint64_t letterBytes, bool 
     cudaFree(s.dRanges);
     s.hOffsets = nullptr, s.hCounts = nullptr, s.dOffsets = nullptr, s.dCounts = nullptr, s.dRanges = nullptr;
     s.queryCap = 0;
-    CU(cudaHostAlloc(&s.hOffsets, (queries + 1) * 8, cudaHostAllocDefault));
-    CU(cudaHostAlloc(&s.hCounts, queries * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&s.hOffsets, (queries + 1) * 8, cudaHostAllocPortable));
+    CU(cudaHostAlloc(&s.hCounts, queries * 4, cudaHostAllocPortable));
     CU(cudaMalloc(&s.dOffsets, (queries + 1) * 8));
     CU(cudaMalloc(&s.dCounts, queries * 4));
     s.queryCap = queries;
@@ -1268,7 +1293,7 @@ static int ensureSlot(PipeSlot &s, uint64_t queries, uint64_t letterBytes, bool 
     s.hLetters = nullptr;
     s.lettersCap = 0;
     const uint64_t cap = letterBytes + letterBytes / 4 + 64;
-    CU(cudaHostAlloc(&s.hLetters, cap, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&s.hLetters, cap, cudaHostAllocPortable));
     s.lettersCap = cap;
   }
   return AWFM_GPU_OK;
@@ -1309,7 +1334,7 @@ struct Packed {
   const uint8_t *source = nullptr;  // where the H2D copy reads from: the slot's staging or the caller's own buffer
 };
 
-static bool isPinnedHost(const void *p) {
+bool awfm_is_pinned_host(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -1345,10 +1370,10 @@ static void teamPackPrepare(TeamPack &tp, PipeSlot &s, const awfm_kmer_search_da
   tp.direct = tp.optimistic && sourcePinned &&
               (const uint8_t *)d0[n - 1].kmerString == tp.base + (n - 1) * tp.len0 &&
               (const uint8_t *)d0[n / 2].kmerString == tp.base + (n / 2) * tp.len0;
-  if (tp.optimistic) {
-    tp.rc = ensureSlot(s, n, tp.direct ? 16 : n * tp.len0 + 16, wantRanges);
-    tp.staging = s.hLetters;
-  }
+  // every DEVICE buffer of the slot is sized here, by the thread that has the chunk's device current; the team may
+  // later only grow the (portable, page-locked) host staging
+  tp.rc = ensureSlot(s, n, (!tp.optimistic || tp.direct) ? 16 : n * tp.len0 + 16, wantRanges);
+  tp.staging = s.hLetters;
   tp.uniformAll = tp.contiguousAll = 1;
   tp.fallback = !tp.optimistic;
 }
@@ -1414,7 +1439,7 @@ static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
         tp.fallback = true;
       }
 #pragma omp barrier
-      if (tp.rc == AWFM_GPU_OK) {
+      if (worker && tp.rc == AWFM_GPU_OK) {
         uint64_t o = tp.partSum[t];
         uint64_t *offs = s.hOffsets;
         uint8_t *staging = tp.staging;
@@ -1441,15 +1466,16 @@ static Packed teamPackResult(TeamPack &tp, PipeSlot &s, int T) {
   return pk;
 }
 
-static int submitCount(awfm_gpu_ctx *c, PipeSlot &s, const Packed &pk, bool wantRanges) {
+static int submitCount(awfm_gpu_ctx *c, Lane &L, PipeSlot &s, const Packed &pk, bool wantRanges) {
   const bool fixed = pk.uniformLen != 0;
   if (int r = ensureDeviceLetters(s, pk.letterBytes)) return r;
   CU(cudaMemcpyAsync(s.dLetters, pk.source, pk.letterBytes, cudaMemcpyHostToDevice, s.stream));
   if (!fixed) CU(cudaMemcpyAsync(s.dOffsets, s.hOffsets, (s.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-  if (int r = countDeviceImpl(c, s.dLetters, fixed ? nullptr : s.dOffsets, pk.uniformLen, s.n, s.dCounts,
-                              wantRanges ? (awfm_range *)s.dRanges : nullptr, s.stream))
+  PackedBatch b;
+  b.data = s.dLetters, b.offsets = fixed ? nullptr : s.dOffsets, b.length = pk.uniformLen, b.numQueries = s.n;
+  if (int r = awfm_count_device_impl(c, L, b, s.dCounts, wantRanges ? (awfm_range *)s.dRanges : nullptr, s.stream))
     return r;
-  c->stats.h2dBytes += pk.letterBytes + (fixed ? 0 : (s.n + 1) * 8);
+  L.stats.h2dBytes += pk.letterBytes + (fixed ? 0 : (s.n + 1) * 8);
   return AWFM_GPU_OK;
 }
 
@@ -1457,372 +1483,7 @@ static int teamSize(uint32_t numThreads, uint64_t n, uint64_t chunk) {
   return (int)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(1, numThreads), std::min(n, chunk) / 64));
 }
 
-// awFmParallelSearchCount over the reference's list layout.  One persistent OpenMP region runs the whole call in
-// rounds, one chunk entering the pipeline per round, ONE team-wide synchronisation point per round besides the one
-// inside teamPack():
-//   workers (all threads but the calling one when the team has more than 4): scatter the counts of chunk r-LAG into the
-//            32-B entries (src/AwFmParallelSearch.c:187-190), then pack chunk r;
-//   driver  (the calling thread, the only one that talks to CUDA), meanwhile: ship chunk r-1 (H2D, kernel, D2H on the
-//            slot's stream), prepare the packing of chunk r+1, wait for the D2H of chunk r-LAG+1.
-// Nothing the driver does is on the workers' critical path unless the GPU falls LAG-2 rounds behind.  Chunks are small
-// (default 2^16 queries) so the entries written by the scatter are still in the packing thread's L2 from LAG rounds
-// earlier: the list is read from DRAM once and written back once (tools/host_list_floor.c measures that floor).
-extern "C" int awfm_gpu_search_list_count(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
-                                          uint32_t numThreads) {
-  if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  beginCall(c);
-  if (n == 0) return AWFM_GPU_OK;
-  const uint64_t chunk = (uint64_t)c->chunkQueries;
-  const uint64_t numChunks = (n + chunk - 1) / chunk;
-  const int T = teamSize(numThreads, n, chunk);
-  constexpr uint64_t LAG = 4;
-  constexpr int NS = awfm_gpu_ctx::kSlots;  // >= LAG + 2: a slot is prepared again only after its counts were scattered
-  static_assert(NS >= (int)LAG + 2, "count pipeline needs LAG + 2 slots");
-  const bool dual = T <= 4;                 // small teams: the calling thread drives the GPU and packs as well
-  const int W = dual ? T : T - 1;           // packing / scattering threads
-  const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
-  const double tStart = omp_get_wtime();
-  double tDriver = 0, tWait = 0, tWork = 0;
-
-  int rc = AWFM_GPU_OK;  // written by the driver only; workers act on per-slot / per-chunk state published at barriers
-  TeamPack tps[2];
-  tps[0].partSum.assign(W + 1, 0);
-  tps[1].partSum.assign(W + 1, 0);
-  for (auto &s : c->slots) s.busy = s.ready = false;
-  teamPackPrepare(tps[0], c->slots[0], data, std::min(chunk, n), sourcePinned, false);
-  if (tps[0].rc != AWFM_GPU_OK) return tps[0].rc;
-
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
-    const bool driver = t == 0, worker = dual || t > 0;
-    const int wi = dual ? t : t - 1;
-    for (uint64_t r = 0; r < numChunks + LAG; r++) {
-      TeamPack &tp = tps[r & 1];  // chunk r (tp.n == 0: none)
-      if (driver) {
-        const double d0 = omp_get_wtime();
-        if (r >= 1 && r - 1 < numChunks) {  // ship chunk r-1, packed in the previous round
-          TeamPack &done = tps[(r - 1) & 1];
-          PipeSlot &s = c->slots[(r - 1) % NS];
-          if (done.n && done.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = done.rc;
-          if (done.n && rc == AWFM_GPU_OK) {
-            const Packed pk = teamPackResult(done, s, W);
-            s.first = (r - 1) * chunk, s.n = done.n, s.ready = false;
-            rc = submitCount(c, s, pk, false);
-            if (rc == AWFM_GPU_OK) {
-              cudaError_t e = cudaMemcpyAsync(s.hCounts, s.dCounts, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
-              if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
-              if (e != cudaSuccess) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", cudaGetErrorString(e));
-              else {
-                c->stats.d2hBytes += s.n * 4;
-                s.busy = true;
-              }
-            }
-          }
-        }
-        TeamPack &next = tps[(r + 1) & 1];  // chunk r+1 is packed next round
-        next.n = 0;
-        if (r + 1 < numChunks && rc == AWFM_GPU_OK) {
-          const uint64_t first = (r + 1) * chunk;
-          teamPackPrepare(next, c->slots[(r + 1) % NS], data + first, std::min(chunk, n - first), sourcePinned, false);
-          if (next.rc != AWFM_GPU_OK) rc = next.rc, next.n = 0;
-        }
-        const double d1 = omp_get_wtime();
-        if (r + 1 >= LAG && r + 1 - LAG < numChunks) {  // chunk r+1-LAG is scattered next round: its D2H must be complete
-          PipeSlot &s = c->slots[(r + 1 - LAG) % NS];
-          if (s.busy) {
-            const bool ok = cudaEventSynchronize(s.done) == cudaSuccess;
-            if (!ok && rc == AWFM_GPU_OK) rc = fail(AWFM_GPU_ERR_CUDA, "count pipeline", "event synchronize failed");
-            s.busy = false;
-            s.ready = ok && rc == AWFM_GPU_OK;
-          }
-        }
-        tDriver += d1 - d0;
-        tWait += omp_get_wtime() - d1;
-      }
-      const double w0 = omp_get_wtime();
-      if (worker && r >= LAG) {  // src/AwFmParallelSearch.c:187-190: count = range length, stored as uint32
-        PipeSlot &s = c->slots[(r - LAG) % NS];
-        if (s.ready) {
-          awfm_kmer_search_data *dst = data + s.first;
-          const uint32_t *src = s.hCounts;
-          const uint64_t a = s.n * wi / W, b = s.n * (wi + 1) / W;
-          for (uint64_t i = a; i < b; i++) dst[i].count = src[i];
-        }
-      }
-      teamPack(tp, c->slots[r % NS], worker ? wi : -1, W);
-      if (t == T - 1) tWork += omp_get_wtime() - w0;
-#pragma omp barrier
-    }
-  }
-  for (auto &s : c->slots) {  // busy slots are only left behind with rc != OK: never leave a DMA in flight
-    if (s.busy) cudaStreamSynchronize(s.stream);
-    s.busy = s.ready = false;
-  }
-  if (getenv("AWFM_GPU_VERBOSE"))
-    fprintf(stderr, "[awfm_gpu] count list: %llu queries, %llu chunks, %d threads (%d packing), pinned=%d: total %.1f ms; driver: submit+prepare %.1f, wait %.1f; last worker: scatter/pack incl. barrier waits %.1f\n",
-            (unsigned long long)n, (unsigned long long)numChunks, T, W, (int)sourcePinned, 1e3 * (omp_get_wtime() - tStart),
-            1e3 * tDriver, 1e3 * tWait, 1e3 * tWork);
-  return rc;
-}
-
-// ---- awFmParallelSearchLocate over the reference's list layout ----
-static int ensureHitBuffers(PipeSlot &s, uint64_t queries) {
-  if (s.hitCap < queries + 1) {
-    if (s.hHit) cudaFreeHost(s.hHit);
-    cudaFree(s.dHit);
-    s.hHit = nullptr, s.dHit = nullptr, s.hitCap = 0;
-    CU(cudaHostAlloc(&s.hHit, (queries + 1) * 8, cudaHostAllocDefault));
-    CU(cudaMalloc(&s.dHit, (queries + 1) * 8));
-    s.hitCap = queries + 1;
-  }
-  return AWFM_GPU_OK;
-}
-
-static int ensurePositionBuffers(uint64_t **hPos, uint64_t **dPos, uint64_t *cap, uint64_t hits, uint64_t floorHits) {
-  if (*cap < hits) {
-    if (*hPos) cudaFreeHost(*hPos);
-    cudaFree(*dPos);
-    *hPos = nullptr, *dPos = nullptr, *cap = 0;
-    const uint64_t want = std::max(hits + hits / 4, floorHits);
-    CU(cudaHostAlloc(hPos, want * 8, cudaHostAllocDefault));
-    CU(cudaMalloc(dPos, want * 8));
-    *cap = want;
-  }
-  return AWFM_GPU_OK;
-}
-
-// A chunk goes through four stations, one round apart or more, so neither side of the bus waits for the other:
-//   pack   (team)    round r                     letters of the chunk into staging (or nothing when copy-free)
-//   ship   (master)  round r+1                   H2D, search with ranges, scan of the range lengths, hit offsets D2H
-//   walk   (master)  round r+1+kWalkLag          the hit total is on the host: expand + backtrace walk, positions D2H
-//   finish (team)    round r+1+kWalkLag+kFinLag  count / capacity semantics of src/AwFmParallelSearch.c:367-387
-//                                                (realloc to exactly `count` when the list is too small) and the
-//                                                positions of SA[sp..ep] in that order into each positionList
-// A chunk with more hits than kInlineHits (a very short or very repetitive query) is finished through a window of
-// flat hit indices instead, by the same team, with the pipeline behind it waiting.
-extern "C" int awfm_gpu_search_list_locate(awfm_gpu_ctx *c, awfm_kmer_search_data *data, uint64_t n,
-                                           uint32_t numThreads) {
-  if (!c || (n && !data)) return fail(AWFM_GPU_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (int r = setDevice(c)) return r;
-  if (!c->hasSa) return fail(AWFM_GPU_ERR_NO_SA, "context was created without a sampled suffix array");
-  beginCall(c);
-  if (n == 0) return AWFM_GPU_OK;
-  constexpr int64_t kWalkLag = 2, kFinLag = 2, NS = awfm_gpu_ctx::kSlots;
-  static_assert(NS >= 2 + kWalkLag + kFinLag, "a slot is reused only after its chunk is finished");
-  const uint64_t kInlineHits = (uint64_t)c->locateInlineHits, kWindowHits = (uint64_t)c->locateWindowHits;
-  const uint64_t chunk = (uint64_t)c->locateChunkQueries;
-  const int64_t numChunks = (int64_t)((n + chunk - 1) / chunk);
-  const int T = teamSize(numThreads, n, chunk);
-  const bool sourcePinned = data[0].kmerString && isPinnedHost(data[0].kmerString);
-  const double tStart = omp_get_wtime();
-  double tShip = 0, tWalkWait = 0, tWalk = 0, tFinWait = 0, tTeam = 0, tWindows = 0;
-
-  // state shared by the team (written by the calling thread between barriers)
-  int rc = AWFM_GPU_OK;
-  int allocFailed = 0;
-  TeamPack tp;
-  tp.partSum.assign(T + 1, 0);
-  bool packed = false;  // tp holds the chunk packed in the previous round
-  struct {
-    awfm_kmer_search_data *dst = nullptr;
-    uint64_t n = 0, total = 0;
-    const uint64_t *hit = nullptr, *pos = nullptr;
-    bool big = false;
-    PipeSlot *slot = nullptr;
-  } fin;
-  struct {
-    uint64_t hb = 0, he = 0, q0 = 0, q1 = 0, cursor = 0;
-    bool ok = false;
-  } win;
-
-  auto cudaFailed = [&](cudaError_t e, const char *what) {
-    if (e == cudaSuccess) return false;
-    cudaGetLastError();
-    if (rc == AWFM_GPU_OK)
-      rc = fail(e == cudaErrorMemoryAllocation ? AWFM_GPU_ERR_ALLOC : AWFM_GPU_ERR_CUDA, what, cudaGetErrorString(e));
-    return true;
-  };
-
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
-    for (int64_t r = 0; r <= numChunks + kWalkLag + kFinLag; r++) {
-#pragma omp master
-      {
-        double t0 = omp_get_wtime();
-        // ---- ship the chunk packed in the previous round ----
-        if (packed && tp.rc != AWFM_GPU_OK && rc == AWFM_GPU_OK) rc = tp.rc;
-        if (packed && rc == AWFM_GPU_OK) {
-          PipeSlot &s = c->slots[(r - 1) % NS];
-          const Packed pk = teamPackResult(tp, s, T);
-          s.first = (uint64_t)(r - 1) * chunk, s.n = tp.n;
-          s.total = 0, s.walked = s.big = false;
-          if (rc == AWFM_GPU_OK) rc = ensureHitBuffers(s, s.n);
-          if (rc == AWFM_GPU_OK) rc = submitCount(c, s, pk, true);
-          if (rc == AWFM_GPU_OK) rc = scanImpl(c, s.sc, (const awfm_range *)s.dRanges, s.n, s.dHit, s.stream);
-          if (rc == AWFM_GPU_OK &&
-              !cudaFailed(cudaMemcpyAsync(s.hHit, s.dHit, (s.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream), "hit offsets D2H") &&
-              !cudaFailed(cudaEventRecord(s.offsetsDone, s.stream), "event record")) {
-            c->stats.d2hBytes += (s.n + 1) * 8;
-            s.busy = true;
-          }
-        }
-        packed = false;
-        double t1 = omp_get_wtime();
-        tShip += t1 - t0;
-        // ---- the chunk shipped kWalkLag rounds ago: its hit total is on the host, walk it ----
-        const int64_t w = r - 1 - kWalkLag;
-        if (w >= 0 && w < numChunks && c->slots[w % NS].busy && rc == AWFM_GPU_OK) {
-          PipeSlot &s = c->slots[w % NS];
-          if (!cudaFailed(cudaEventSynchronize(s.offsetsDone), "hit offsets")) {
-            const double t2 = omp_get_wtime();
-            tWalkWait += t2 - t1;
-            s.total = s.hHit[s.n];
-            if (s.total > kInlineHits) s.big = true;
-            else if (s.total) {
-              rc = ensurePositionBuffers(&s.hPos, &s.dPos, &s.posCap, s.total, std::max<uint64_t>(chunk, 1 << 16));
-              if (rc == AWFM_GPU_OK)
-                rc = locateDeviceImpl(c, s.sc, (const awfm_range *)s.dRanges, s.dHit, s.n, 0, s.total, s.dPos, s.stream);
-              if (rc == AWFM_GPU_OK &&
-                  !cudaFailed(cudaMemcpyAsync(s.hPos, s.dPos, s.total * 8, cudaMemcpyDeviceToHost, s.stream), "positions D2H") &&
-                  !cudaFailed(cudaEventRecord(s.done, s.stream), "event record")) {
-                c->stats.d2hBytes += s.total * 8;
-                s.walked = true;
-              }
-            }
-            tWalk += omp_get_wtime() - t2;
-          }
-        }
-        t1 = omp_get_wtime();
-        // ---- the chunk walked kFinLag rounds ago: its positions are on the host, the team finishes it ----
-        fin.n = 0;
-        const int64_t f = w - kFinLag;
-        if (f >= 0 && f < numChunks && c->slots[f % NS].busy) {
-          PipeSlot &s = c->slots[f % NS];
-          if (s.walked) cudaFailed(cudaEventSynchronize(s.done), "positions");
-          if (rc == AWFM_GPU_OK) {
-            fin.dst = data + s.first, fin.n = s.n, fin.total = s.total, fin.hit = s.hHit, fin.pos = s.hPos;
-            fin.big = s.big, fin.slot = &s;
-            if (s.big) {
-              rc = ensurePositionBuffers(&c->hBigPos, &c->dBigPos, &c->bigPosCap, std::min(s.total, kWindowHits), 0);
-              if (rc != AWFM_GPU_OK) fin.n = 0;
-              win.cursor = 0;
-            }
-          }
-          if (!s.walked || rc != AWFM_GPU_OK) cudaStreamSynchronize(s.stream);
-          s.busy = false;
-        }
-        tFinWait += omp_get_wtime() - t1;
-        // ---- the chunk the team packs this round ----
-        tp.n = 0;
-        if (r < numChunks && rc == AWFM_GPU_OK) {
-          const uint64_t first = (uint64_t)r * chunk;
-          teamPackPrepare(tp, c->slots[r % NS], data + first, std::min(chunk, n - first), sourcePinned, true);
-          if (tp.rc != AWFM_GPU_OK) rc = tp.rc;
-          else packed = true;
-        }
-      }
-#pragma omp barrier
-      const double w0 = omp_get_wtime();
-      // read now: the master rewrites `fin` in the next round's block, which it may reach before this thread is done
-      const bool windowed = fin.n && fin.big;
-      const uint64_t windowTotal = fin.total, windowHits = c->bigPosCap;
-      if (fin.n) {
-        awfm_kmer_search_data *dst = fin.dst;
-        const uint64_t *hit = fin.hit, *pos = fin.pos;
-        const bool copyNow = !fin.big;
-        const uint64_t a = fin.n * t / T, b = fin.n * (t + 1) / T;
-        bool failed = false;
-        for (uint64_t i = a; i < b; i++) {
-          const uint64_t h0 = hit[i];
-          const uint32_t count = (uint32_t)(hit[i + 1] - h0);
-          if (dst[i].capacity < count) {
-            void *p = realloc(dst[i].positionList, (size_t)count * sizeof(uint64_t));
-            if (!p) {
-              fprintf(stderr, "Critical memory failure: could not allocate memory for position list.\n");
-              dst[i].count = 0;  // never write past the old allocation
-              failed = true;
-              continue;
-            }
-            dst[i].positionList = (uint64_t *)p;
-            dst[i].capacity = count;
-          }
-          dst[i].count = count;
-          if (copyNow) {
-            if (count == 1) dst[i].positionList[0] = pos[h0];
-            else if (count) memcpy(dst[i].positionList, pos + h0, (size_t)count * 8);
-          }
-        }
-        if (failed) {
-#pragma omp atomic write
-          allocFailed = 1;
-        }
-      }
-      teamPack(tp, c->slots[r % NS], t, T);
-#pragma omp barrier
-      const double w1 = omp_get_wtime();
-      if (windowed) {  // positions in windows of flat hit indices [hb, he)
-        for (uint64_t hb = 0; hb < windowTotal; hb += windowHits) {
-#pragma omp master
-          {
-            PipeSlot &s = *fin.slot;
-            win.hb = hb, win.he = std::min(fin.total, hb + c->bigPosCap), win.ok = false;
-            if (rc == AWFM_GPU_OK)
-              rc = locateDeviceImpl(c, s.sc, (const awfm_range *)s.dRanges, s.dHit, s.n, win.hb, win.he, c->dBigPos, s.stream);
-            if (rc == AWFM_GPU_OK &&
-                !cudaFailed(cudaMemcpyAsync(c->hBigPos, c->dBigPos, (win.he - win.hb) * 8, cudaMemcpyDeviceToHost, s.stream), "positions D2H") &&
-                !cudaFailed(cudaStreamSynchronize(s.stream), "positions")) {
-              c->stats.d2hBytes += (win.he - win.hb) * 8;
-              while (win.cursor < fin.n && fin.hit[win.cursor + 1] <= win.hb) win.cursor++;
-              win.q0 = win.q1 = win.cursor;
-              while (win.q1 < fin.n && fin.hit[win.q1] < win.he) win.q1++;
-              win.ok = true;
-            }
-          }
-#pragma omp barrier
-          if (win.ok) {
-            awfm_kmer_search_data *dst = fin.dst;
-            const uint64_t *hit = fin.hit, *pos = c->hBigPos;
-            const uint64_t span = win.q1 - win.q0;
-            const uint64_t q0 = win.q0 + span * t / T, q1 = win.q0 + span * (t + 1) / T;
-            for (uint64_t i = q0; i < q1; i++) {
-              if (dst[i].count == 0) continue;
-              const uint64_t lo = std::max(hit[i], win.hb), hi = std::min(hit[i] + dst[i].count, win.he);
-              if (lo < hi) memcpy(dst[i].positionList + (lo - hit[i]), pos + (lo - win.hb), (hi - lo) * 8);
-            }
-          }
-#pragma omp barrier
-        }
-      }
-#pragma omp master
-      {
-        tTeam += w1 - w0;
-        tWindows += omp_get_wtime() - w1;
-      }
-    }
-  }
-  for (auto &s : c->slots)  // only reachable with rc != OK: never leave a DMA in flight
-    if (s.busy) {
-      cudaStreamSynchronize(s.stream);
-      s.busy = false;
-    }
-  if (c->bigPosCap) {  // the window is not worth keeping between calls
-    cudaFreeHost(c->hBigPos);
-    cudaFree(c->dBigPos);
-    c->hBigPos = c->dBigPos = nullptr, c->bigPosCap = 0;
-  }
-  if (getenv("AWFM_GPU_VERBOSE"))
-    fprintf(stderr, "[awfm_gpu] locate list: %llu queries, %lld chunks, %d threads, pinned=%d, %llu hits: total %.1f ms = ship %.1f + "
-            "wait(offsets) %.1f + walk submit %.1f + wait(positions) %.1f + team pack/finish %.1f + windows %.1f\n",
-            (unsigned long long)n, (long long)numChunks, T, (int)sourcePinned, (unsigned long long)c->stats.hits,
-            1e3 * (omp_get_wtime() - tStart), 1e3 * tShip, 1e3 * tWalkWait, 1e3 * tWalk, 1e3 * tFinWait, 1e3 * tTeam, 1e3 * tWindows);
-  if (rc == AWFM_GPU_OK && allocFailed) return fail(AWFM_GPU_ERR_ALLOC, "realloc of a position list failed");
-  return rc;
-}
+#include "awfm_list_engine.inc"
 
 // ------------------------------------------------------------------------------------------------ gather probe
 template <int BYTES>
@@ -1832,7 +1493,7 @@ static int runGather(int lanes, const uint4 *d, uint64_t numRecords, uint64_t nu
     case 2: gatherProbe<BYTES, 2><<<grid, 256>>>(d, numRecords, numReads, sink); break;
     case 4: gatherProbe<BYTES, 4><<<grid, 256>>>(d, numRecords, numReads, sink); break;
     case 8: gatherProbe<BYTES, 8><<<grid, 256>>>(d, numRecords, numReads, sink); break;
-    default: return fail(AWFM_GPU_ERR_ARG, "lanesPerRead must be 1, 2, 4 or 8");
+    default: return awfm_fail(AWFM_GPU_ERR_ARG, "lanesPerRead must be 1, 2, 4 or 8");
   }
   CU(cudaGetLastError());
   return AWFM_GPU_OK;
@@ -1850,13 +1511,17 @@ extern "C" int awfm_gpu_set_l2_fetch_granularity(int device, int bytes, int *act
 
 extern "C" int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32_t bytesPerRead, uint64_t numReads,
                                          int lanesPerRead, double *gbps) {
-  if (!gbps || arrayBytes < 4096) return fail(AWFM_GPU_ERR_ARG, "bad argument");
+  if (!gbps || arrayBytes < 4096) return awfm_fail(AWFM_GPU_ERR_ARG, "bad argument");
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
-  DevBuf data, sink;
-  CU(data.alloc(arrayBytes));
-  CU(sink.alloc(64));
+  GrowBuf data, sink;
+  struct Release {
+    GrowBuf &a, &b;
+    ~Release() { a.release(), b.release(); }
+  } release{data, sink};
+  if (int r = data.ensure(arrayBytes)) return r;
+  if (int r = sink.ensure(64)) return r;
   CU(cudaMemset(data.p, 1, arrayBytes));
   const uint64_t numRecords = arrayBytes / bytesPerRead;
   const int grid = prop.multiProcessorCount * 8;
@@ -1873,7 +1538,7 @@ extern "C" int awfm_gpu_gather_bandwidth(int device, uint64_t arrayBytes, uint32
       case 64: r = runGather<64>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
       case 128: r = runGather<128>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
       case 256: r = runGather<256>(lanesPerRead, (const uint4 *)data.p, numRecords, numReads, (uint64_t *)sink.p, grid); break;
-      default: r = fail(AWFM_GPU_ERR_ARG, "bytesPerRead must be 16, 32, 64, 128 or 256");
+      default: r = awfm_fail(AWFM_GPU_ERR_ARG, "bytesPerRead must be 16, 32, 64, 128 or 256");
     }
     if (r) return r;
     CU(cudaEventRecord(b));

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256)
 // Step 1, expandHits: positions[h - hitBegin] = sp(q) + (h - hitOffsets[q]) for every flat hit index h of the
 // window, written by one warp per 32 queries (lanes stride over a query's hits, so a query with millions of hits
 // is as cheap per hit as one with a single hit).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     expandHits(const uint4 *__restrict__ ranges, const uint64_t *__restrict__ hitOffsets, uint64_t numQueries,
                uint64_t hitBegin, uint64_t hitEnd, uint64_t *__restrict__ positions) {
   const unsigned lane = threadIdx.x & 31u;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256)
 
 // densify the sampled SA: out[j] = SA[j * newRatio] for j in [first, first + count), by the locate walk itself
 // (src/AwFmParallelSearch.c:333-361).  `work` holds j*newRatio on entry (iota kernel) and text positions on exit.
-__global__ void saIota(uint64_t *__restrict__ work, uint64_t first, uint64_t count, uint64_t newRatio) {
+static __global__ void saIota(uint64_t *__restrict__ work, uint64_t first, uint64_t count, uint64_t newRatio) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
     work[i] = (first + i) * newRatio;
 }
@@ -434,7 +434,7 @@ __global__ void saNarrow(const uint64_t *__restrict__ work, uint64_t count, T *_
 // (16 B x 10 k contigs for BASELINE cfg 5) stays L1/L2-resident.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMapSample = 256;
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     mapPositionsKernel(const uint64_t *__restrict__ ends, uint64_t numSequences, const uint64_t *__restrict__ positions,
                        uint64_t n, uint64_t *__restrict__ sequenceIndex, uint64_t *__restrict__ localPosition) {
   __shared__ uint64_t sample[kMapSample];  // sample[j] = E[min((j+1)*stride, numSequences) - 1]
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------
 // Nucleotide: first the superblock rows (one thread per 2^16-position superblock = 256 reference blocks), then one
 // thread per reference block (256 positions) -> four 32-B sectors with 16-bit counts relative to the superblock row.
-__global__ void sectorSuperRows(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+static __global__ void sectorSuperRows(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
                                 const uint64_t *__restrict__ prefixSums /* device copy, 6 entries */,
                                 uint64_t *__restrict__ superCounts, uint64_t *__restrict__ superC) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // superblock inside this slab
@@ -489,7 +489,7 @@ __global__ void sectorSuperRows(const uint8_t *__restrict__ raw, uint64_t numBlo
     superC[row * kSectorSuperStride + c] = c < 5 ? v + prefixSums[c] : 0;
   }
 }
-__global__ void relayoutNucleotideSectors(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+static __global__ void relayoutNucleotideSectors(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
                                           const uint64_t *__restrict__ superCounts, uint4 *__restrict__ sectors,
                                           uint16_t *__restrict__ xRel16) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,7 +530,7 @@ __global__ void relayoutNucleotideSectors(const uint8_t *__restrict__ raw, uint6
 // One thread per reference block (256 positions) -> four quarter-lines (see awfm_device.cuh).  The count of letter c
 // at the start of quarter q = baseOccurrences[c] (block start) + popcount of c's selector over the 2q words before
 // it, made relative to the enclosing superblock.
-__global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
+static __global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlocks, uint64_t firstBlock,
                               const uint64_t *__restrict__ superCounts /* [numSuper][24] */,
                               uint4 *__restrict__ lines) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,8 +575,137 @@ __global__ void relayoutAmino(const uint8_t *__restrict__ raw, uint64_t numBlock
   }
 }
 
+// Packed query formats of include/awfm_gpu.h -> the ASCII letters the search kernels take.  AWFM_QUERY_2BIT: codes 0..3
+// = A,C,G,T; AWFM_QUERY_5BIT: codes 0..19 = the amino letters in the reference's index order (src/AwFmLetter.c:55-67),
+// anything above = the ambiguity letter (written as 'X', which both the sanitizer and the ambiguity predicate treat as
+// such, src/AwFmLetter.c:69-79,98-125).  Query i occupies bytes [i*B, (i+1)*B), B = ceil(len*bits/8), letter j in bits
+// [j*bits, (j+1)*bits) of that little-endian byte string.  One thread per four output letters.
+template <int BITS>
+__global__ void __launch_bounds__(256)
+    unpackQueries(const uint8_t *__restrict__ packed, uint64_t numQueries, uint32_t len, uint8_t *__restrict__ ascii) {
+  const uint64_t totalLetters = numQueries * (uint64_t)len;
+  const uint32_t B = (len * BITS + 7u) >> 3;
+  const uint64_t totalBytes = numQueries * (uint64_t)B;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; 4 * w < totalLetters;
+       w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t out = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+      const uint64_t i = 4 * w + t;
+      if (i >= totalLetters) break;
+      const uint64_t q = i / len;
+      const uint32_t bit = (uint32_t)(i - q * len) * BITS;
+      const uint64_t byte = q * B + (bit >> 3);
+      uint32_t window = __ldg(packed + byte);
+      if (byte + 1 < totalBytes) window |= (uint32_t)__ldg(packed + byte + 1) << 8;
+      const uint32_t code = (window >> (bit & 7u)) & ((1u << BITS) - 1u);
+      uint32_t ch;
+      if (BITS == 2) ch = (0x54474341u >> (8u * code)) & 0xFFu;  // "ACGT"
+      else ch = code < 20u ? (uint32_t)"ACDEFGHIKLMNPQRSTVWY"[code] : (uint32_t)'X';
+      out |= ch << (8u * t);
+    }
+    if (4 * w + 4 <= totalLetters) reinterpret_cast<uint32_t *>(ascii)[w] = out;
+    else
+      for (uint32_t t = 0; 4 * w + t < totalLetters; t++) ascii[4 * w + t] = (uint8_t)(out >> (8u * t));
+  }
+}
+
+// ---- range-length scan (src/AwFmParallelSearch.c:328,367: lengths are u32-truncated) in three launches of our own:
+// per-tile sums, one CTA scanning the tile sums, per-tile exclusive scan + tile base.  hitOffsets[n] = base + total. ----
+constexpr int kScanTile = 2048;  // queries per CTA: 256 threads x 8
+__device__ __forceinline__ uint64_t rangeLengthOf(const uint4 r) {
+  const uint64_t sp = (uint64_t)r.x | ((uint64_t)r.y << 32), ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
+  return (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
+}
+__device__ __forceinline__ uint64_t blockSum256(uint64_t v, uint64_t *warpSums /* [8] shared */) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31u) == 0) warpSums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint64_t total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) total += warpSums[w];
+  __syncthreads();
+  return total;
+}
+static __global__ void __launch_bounds__(256)
+    scanTileSums(const uint4 *__restrict__ ranges, uint64_t n, uint64_t *__restrict__ tileSums) {
+  __shared__ uint64_t warpSums[8];
+  const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile;
+  uint64_t mine = 0;
+#pragma unroll
+  for (int it = 0; it < kScanTile / 256; it++) {
+    const uint64_t q = q0 + it * 256 + threadIdx.x;
+    if (q < n) mine += rangeLengthOf(__ldg(ranges + q));
+  }
+  const uint64_t total = blockSum256(mine, warpSums);
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+// one CTA: exclusive scan of the tile sums in place (numTiles is small: n / 2048), grand total to tileSums[numTiles]
+static __global__ void __launch_bounds__(256) scanTileBases(uint64_t *__restrict__ tileSums, uint64_t numTiles, uint64_t base) {
+  __shared__ uint64_t warpSums[8];
+  __shared__ uint64_t carry;
+  if (threadIdx.x == 0) carry = base;
+  __syncthreads();
+  for (uint64_t t0 = 0; t0 < numTiles; t0 += 256) {
+    const uint64_t t = t0 + threadIdx.x;
+    const uint64_t v = t < numTiles ? tileSums[t] : 0;
+    uint64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((threadIdx.x & 31u) >= (unsigned)d) incl += up;
+    }
+    if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint64_t before = carry;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); w++) before += warpSums[w];
+    if (t < numTiles) tileSums[t] = before + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = before + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tileSums[numTiles] = carry;
+}
+static __global__ void __launch_bounds__(256)
+    scanTileOffsets(const uint4 *__restrict__ ranges, uint64_t n, const uint64_t *__restrict__ tileBases,
+                    uint64_t *__restrict__ hitOffsets) {
+  __shared__ uint64_t warpSums[8];
+  const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // thread t owns the 8 consecutive queries q0 + 8t .. q0 + 8t + 7
+  uint64_t len[kScanTile / 256], mine = 0;
+#pragma unroll
+  for (int j = 0; j < kScanTile / 256; j++) {
+    const uint64_t q = q0 + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
+    len[j] = q < n ? rangeLengthOf(__ldg(ranges + q)) : 0;
+    mine += len[j];
+  }
+  uint64_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= (unsigned)d) incl += up;
+  }
+  if (lane == 31u) warpSums[warp] = incl;
+  __syncthreads();
+  uint64_t run = __ldg(tileBases + blockIdx.x) + incl - mine;
+  for (unsigned w = 0; w < warp; w++) run += warpSums[w];
+#pragma unroll
+  for (int j = 0; j < kScanTile / 256; j++) {
+    const uint64_t q = q0 + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
+    if (q < n) hitOffsets[q] = run;
+    run += len[j];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) hitOffsets[n] = __ldg(tileBases + gridDim.x);
+}
+static __global__ void addHitBase(uint64_t *__restrict__ hitOffsets, uint64_t count, uint64_t base) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    hitOffsets[i] += base;
+}
+
 // range lengths (u32-truncated, src/AwFmParallelSearch.c:328,367) for the exclusive scan that builds hitOffsets
-__global__ void rangeLengths(const uint4 *__restrict__ ranges, uint64_t n, uint64_t *__restrict__ lengths) {
+static __global__ void rangeLengths(const uint4 *__restrict__ ranges, uint64_t n, uint64_t *__restrict__ lengths) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4 r = ranges[i];

@@ -199,6 +199,54 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// sweepPackBits: the 2-bit packed query format of include/awfm_gpu.h (AWFM_QUERY_2BIT): query i occupies bytes
+// [i*B, (i+1)*B), B = ceil(len/4), letter j in bits [2j, 2j+2) of that little-endian byte string, codes 0..3 = A,C,G,T
+// (the reference's letter indices, src/AwFmLetter.c:4-22).  len <= 32.  A tile of 256 queries is staged through shared
+// memory with coalesced 128-bit loads; one bit reversal + one swap of neighbouring bits turns the query into the same
+// number Q sweepPackWords builds (first letter most significant).  The format has no ambiguity codes, so there are no
+// irregular queries.
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+    sweepPackBits(const uint8_t *__restrict__ packed, uint64_t numQueries, uint32_t len, uint32_t k,
+                  uint32_t *__restrict__ keys, uint64_t *__restrict__ vals) {
+  extern __shared__ __align__(16) uint8_t sPacked[];  // 256 * B bytes, rounded up to 16
+  const uint32_t B = (len + 3u) >> 2;
+  const uint64_t numTiles = (numQueries + 255) / 256;
+  const uint64_t totalBytes = numQueries * (uint64_t)B;
+  const uint64_t keyMask = (k >= 16) ? 0xFFFFFFFFull : ((1ull << (2 * k)) - 1ull);
+  for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    const uint64_t q0 = tile * 256;
+    const uint32_t nq = (uint32_t)min((uint64_t)256, numQueries - q0);
+    const uint64_t byte0 = q0 * (uint64_t)B;  // multiple of 256
+    const uint32_t bytes = nq * B;
+    __syncthreads();  // previous tile consumed
+    for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) {
+      const uint64_t g = byte0 + 16ull * i;
+      uint4 v;
+      if (g + 16 <= totalBytes) {
+        v = __ldg(reinterpret_cast<const uint4 *>(packed + g));
+      } else {  // never read past the batch's final byte
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (uint32_t b = 0; g + b < totalBytes; b++) w[b >> 2] |= (uint32_t)__ldg(packed + g + b) << (8 * (b & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      reinterpret_cast<uint4 *>(sPacked)[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nq) {
+      const uint8_t *s = sPacked + threadIdx.x * B;
+      uint64_t raw = 0;
+      for (uint32_t b = 0; b < B; b++) raw |= (uint64_t)s[b] << (8u * b);
+      uint64_t r = __brevll(raw);  // letter j: bits (2j, 2j+1) -> (63-2j, 62-2j)
+      r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);  // ... -> (62-2j, 63-2j)
+      const uint64_t Q = r >> (64u - 2u * len);  // first letter most significant, 2 bits per letter
+      keys[q0 + threadIdx.x] = (uint32_t)(Q & keyMask);
+      vals[q0 + threadIdx.x] = ((Q >> (2 * k)) << 32) | (uint32_t)(q0 + threadIdx.x);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // sweepStep: one pass.  FIRST: input = sorted (key, payload) pairs, range from the seed table; else input = the
 // previous generation's buckets in letter order.  `steps` = LF steps the queries of this pass still have to do
 // INCLUDING this pass's (0 only for FIRST with len == k).

@@ -119,6 +119,29 @@ class IndexArrays:
         return (bits << np.arange(w, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
 
 
+def section_digests(ix: "IndexArrays", chunk_bytes=1 << 26):
+    """SHA-256 of every section of an index as the `.awfmi` file stores it (blocks, prefix sums, seed table, packed
+    sampled SA), plus a short digest per 64-MiB chunk so that a mismatch can be localised.  Used to prove that a
+    device-built index equals the one the reference's awFmCreateIndex builds (tools/ref_index_hashes.py)."""
+    import hashlib
+
+    def one(a):
+        b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        whole = hashlib.sha256()
+        chunks = []
+        for o in range(0, len(b), chunk_bytes):
+            part = b[o:o + chunk_bytes]
+            whole.update(part)
+            chunks.append(hashlib.sha256(part).hexdigest()[:16])
+        return {"bytes": int(len(b)), "sha256": whole.hexdigest(), "chunk_bytes": chunk_bytes, "chunks": chunks}
+
+    out = {"blocks": one(ix.blocks), "prefix_sums": one(ix.prefix_sums.astype("<u8")),
+           "seed_table": one(ix.seed_table.astype("<u8"))}
+    if ix.sa_bytes is not None:
+        out["suffix_array"] = one(ix.sa_bytes)
+    return out
+
+
 def read_awfmi(path, keep_suffix_array=True):
     with open(path, "rb") as f:
         data = f.read()

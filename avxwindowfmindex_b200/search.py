@@ -173,6 +173,172 @@ class GpuIndex:
                                                    d_positions, stream or None))
 
 
+QUERY_ASCII, QUERY_2BIT, QUERY_5BIT = 0, 2, 5  # include/awfm_gpu.h: awfm_query_format
+
+
+def pack_queries_bits(letters, length, amino=False):
+    """ASCII fixed-length queries -> the 2-bit (nucleotide) / 5-bit (amino) packed format of include/awfm_gpu.h:
+    query i occupies bytes [i*B, (i+1)*B), B = ceil(length*bits/8), letter j in bits [j*bits, (j+1)*bits) of that
+    little-endian byte string.  Nucleotide letters must be A/C/G/T/U (either case); amino letters outside the 20
+    standard ones become code 20 (ambiguity).  Test/bench helper (numpy), not on the product path."""
+    letters = np.ascontiguousarray(letters, dtype=np.uint8).reshape(-1, length)
+    n = letters.shape[0]
+    if amino:
+        bits = 5
+        table = np.full(256, 20, dtype=np.uint8)
+        for i, ch in enumerate(b"ACDEFGHIKLMNPQRSTVWY"):
+            table[ch] = i
+            table[ch | 0x20] = i
+    else:
+        bits = 2
+        table = np.full(256, 255, dtype=np.uint8)
+        for i, chs in enumerate((b"Aa", b"Cc", b"Gg", b"TtUu")):
+            for ch in chs:
+                table[ch] = i
+    codes = table[letters]
+    if not amino and (codes == 255).any():
+        raise ValueError("the 2-bit format holds A/C/G/T(U) only")
+    nbytes = (length * bits + 7) // 8
+    out = np.zeros((n, nbytes), dtype=np.uint8)
+    step = max(1, (1 << 22) // max(length, 1))
+    for a in range(0, n, step):  # bounded temporaries
+        c = codes[a:a + step].astype(np.uint64)
+        acc = np.zeros((c.shape[0], (length * bits + 63) // 64), dtype=np.uint64)
+        for j in range(length):
+            bit = j * bits
+            w, sh = bit // 64, bit % 64
+            acc[:, w] |= c[:, j] << np.uint64(sh)
+            if sh + bits > 64:
+                acc[:, w + 1] |= c[:, j] >> np.uint64(64 - sh)
+        out[a:a + step] = acc.view(np.uint8).reshape(c.shape[0], -1)[:, :nbytes]
+    return out.reshape(-1)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from awfm_gpu_host_alloc (every GPU of the box can DMA from / to it)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = capi.load()
+        self.dtype = np.dtype(dtype)
+        self.shape = (shape,) if np.isscalar(shape) else tuple(shape)
+        nbytes = max(16, int(np.prod(self.shape)) * self.dtype.itemsize)
+        p = C.c_void_p()
+        capi.check(self.lib.awfm_gpu_host_alloc(C.byref(p), nbytes))
+        self.ptr = p.value
+        buf = (C.c_uint8 * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.awfm_gpu_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GpuGroup:
+    """A device group (awfm_gpu_group): one call fanned out over several GPUs from this process, and the pipelined
+    packed-batch engine.  Built from host arrays (replicated onto `devices`) or from existing GpuIndex objects."""
+
+    def __init__(self, arrays: IndexArrays = None, devices=None, indexes=None):
+        self.lib = capi.load()
+        self._g = C.c_void_p()
+        self._keep = indexes
+        if indexes is not None:
+            ctxs = (C.c_void_p * len(indexes))(*[ix.ctx for ix in indexes])
+            capi.check(self.lib.awfm_gpu_group_create_from_contexts(C.byref(self._g), ctxs, len(indexes)))
+        else:
+            view = arrays.view()
+            self._arrays = arrays
+            if devices is None:
+                capi.check(self.lib.awfm_gpu_group_create(C.byref(self._g), None, 0, C.byref(view)))
+            else:
+                devs = (C.c_int * len(devices))(*devices)
+                capi.check(self.lib.awfm_gpu_group_create(C.byref(self._g), devs, len(devices), C.byref(view)))
+            if arrays.fasta_metadata is not None and len(arrays.fasta_metadata):
+                self.set_sequences(arrays.fasta_metadata)
+
+    @property
+    def handle(self):
+        return self._g
+
+    @property
+    def size(self):
+        return int(self.lib.awfm_gpu_group_size(self._g))
+
+    def close(self):
+        if self._g:
+            self.lib.awfm_gpu_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_sequences(self, fasta_metadata):
+        meta = np.ascontiguousarray(fasta_metadata, dtype=np.uint64).reshape(-1, 2)
+        capi.check(self.lib.awfm_gpu_group_set_sequences(self._g, _ptr(meta), len(meta)))
+
+    def set_tuning(self, **kv):
+        for k, v in kv.items():
+            capi.check(self.lib.awfm_gpu_group_set_tuning(self._g, k.encode(), int(v)))
+
+    def stats(self):
+        s = abi.awfm_gpu_stats()
+        capi.check(self.lib.awfm_gpu_group_get_stats(self._g, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    @staticmethod
+    def _n(queries, fmt, offsets, fixed_len):
+        if offsets is not None:
+            return len(offsets) - 1
+        bits = {QUERY_ASCII: 8, QUERY_2BIT: 2, QUERY_5BIT: 5}[fmt]
+        qb = (fixed_len * bits + 7) // 8
+        return len(queries) // qb if qb else 0
+
+    def count(self, queries, fmt=QUERY_ASCII, offsets=None, fixed_len=0, out=None):
+        """awfm_gpu_group_count: `queries` uint8 (numpy, page-locked or not), returns uint32 counts (`out` if given)."""
+        n = self._n(queries, fmt, offsets, fixed_len)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        counts = out if out is not None else np.zeros(n, dtype=np.uint32)
+        capi.check(self.lib.awfm_gpu_group_count(self._g, queries.ctypes.data, fmt, _ptr(offsets), fixed_len, n,
+                                                 counts.ctypes.data))
+        return counts
+
+    def locate(self, queries, fmt=QUERY_ASCII, offsets=None, fixed_len=0, mapped=False, out=None):
+        """awfm_gpu_group_locate: (hit_offsets, positions[, sequence_index, local_position]).  `out` = (hit_offsets,
+        positions[, seq, loc]) preallocated arrays (e.g. page-locked) to be filled instead of fresh ones."""
+        n = self._n(queries, fmt, offsets, fixed_len)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        total = C.c_uint64()
+        if out is None:
+            hit = np.zeros(n + 1, dtype=np.uint64)
+            capi.check(self.lib.awfm_gpu_group_locate(self._g, queries.ctypes.data, fmt, _ptr(offsets), fixed_len, n,
+                                                      hit.ctypes.data, None, 0, None, None, C.byref(total)))
+            pos = np.zeros(int(total.value), dtype=np.uint64)
+            seq = np.zeros(int(total.value), dtype=np.uint64) if mapped else None
+            loc = np.zeros(int(total.value), dtype=np.uint64) if mapped else None
+            if total.value == 0:
+                return (hit, pos, seq, loc) if mapped else (hit, pos)
+        else:
+            hit, pos = out[0], out[1]
+            seq, loc = (out[2], out[3]) if mapped else (None, None)
+        capi.check(self.lib.awfm_gpu_group_locate(self._g, queries.ctypes.data, fmt, _ptr(offsets), fixed_len, n,
+                                                  hit.ctypes.data, pos.ctypes.data, len(pos), _ptr(seq), _ptr(loc),
+                                                  C.byref(total)))
+        self.last_total = int(total.value)
+        return (hit, pos, seq, loc) if mapped else (hit, pos)
+
+
 class KmerSearchList:
     """The reference's AwFmKmerSearchList, allocated and freed by `lib` itself (awFmCreateKmerSearchList /
     awFmDeallocKmerSearchList), filled the way README.md's example does: set kmerString/kmerLength per entry and

@@ -178,6 +178,38 @@ enum AwFmReturnCode awFmGpuGetLocalSequencePositions(const struct AwFmIndex *ind
                                                      size_t count, size_t *sequenceNumbers,
                                                      size_t *localSequencePositions);
 
+/* Number of GPUs the batched calls on `index` are fanned out over (AWFM_GPU_DEVICES = "all" | "0,1,..." selects them;
+ * default one GPU, AWFM_GPU_DEVICE or 0); uploads the index if it is not resident yet.  0 on failure. */
+int awFmGpuNumDevices(const struct AwFmIndex *index);
+
+/* ---- the packed-batch API: the same two searches without the per-query 32-B structs and
+ *      pointers of src/AwFmIndex.h:111-123 — contiguous k-mers in, flat arrays out.  With page-locked buffers
+ *      (awFmGpuHostAlloc) the GPUs' copy engines read and write the caller's memory in place, chunk-pipelined with the
+ *      search, every selected GPU working on its own contiguous shard of the batch. ---- */
+enum AwFmGpuKmerFormat {
+  AwFmGpuKmerAscii = 0, /* one byte per letter, what kmerString holds in the reference API                          */
+  AwFmGpuKmer2Bit = 2,  /* nucleotide: letter j of k-mer i in bits [2j,2j+2) of bytes [i*B,(i+1)*B), B = ceil(L/4);
+                           codes 0..3 = A,C,G,T — the reference's letter indices (src/AwFmLetter.c:4-22)            */
+  AwFmGpuKmer5Bit = 5   /* amino: 5 bits per letter, B = ceil(5L/8); codes 0..19 in the reference's letter-index order
+                           (src/AwFmLetter.c:55-67), >= 20 = ambiguity                                              */
+};
+/* counts[i] = what awFmParallelSearchCount stores in kmerSearchData[i].count.  kmerOffsets (numKmers+1 entries) is for
+ * variable-length ASCII batches; NULL = every k-mer has kmerLength letters. */
+enum AwFmReturnCode awFmGpuCountPacked(const struct AwFmIndex *index, const void *kmers, enum AwFmGpuKmerFormat format,
+                                       const uint64_t *kmerOffsets, uint32_t kmerLength, uint64_t numKmers,
+                                       uint32_t *counts);
+/* CSR form of awFmParallelSearchLocate: positions[hitOffsets[i] .. hitOffsets[i+1]) = kmerSearchData[i].positionList
+ * (same order).  *totalHits = hitOffsets[numKmers].  With positions == NULL or positionsCapacity < *totalHits only
+ * hitOffsets and *totalHits are produced (size the buffer, call again).  sequenceNumbers / localSequencePositions (both
+ * or neither) receive awFmGetLocalSequencePositionFromIndexPosition's answer for every hit. */
+enum AwFmReturnCode awFmGpuLocatePacked(const struct AwFmIndex *index, const void *kmers, enum AwFmGpuKmerFormat format,
+                                        const uint64_t *kmerOffsets, uint32_t kmerLength, uint64_t numKmers,
+                                        uint64_t *hitOffsets, uint64_t *positions, uint64_t positionsCapacity,
+                                        uint64_t *sequenceNumbers, uint64_t *localSequencePositions,
+                                        uint64_t *totalHits);
+void *awFmGpuHostAlloc(size_t bytes); /* page-locked, visible to every GPU; NULL on failure */
+void awFmGpuHostFree(void *p);
+
 #ifndef __cplusplus
 _Static_assert(sizeof(struct AwFmNucleotideBlock) == 160, "nucleotide block is 160 B");
 _Static_assert(sizeof(struct AwFmAminoBlock) == 352, "amino block is 352 B");

@@ -76,6 +76,18 @@ typedef struct awfm_kmer_search_data { /* == struct AwFmKmerSearchData, 32 B (sr
 
 typedef struct awfm_gpu_ctx awfm_gpu_ctx;
 
+/* How a batch of queries is stored (awfm_gpu_count_device_format, awfm_gpu_group_*):
+ *   AWFM_QUERY_ASCII  one byte per letter, the raw bytes the reference API would be given (any case, ambiguity codes);
+ *                     fixed length, or variable length through an offsets array;
+ *   AWFM_QUERY_2BIT   nucleotide indexes, fixed length L: query i occupies bytes [i*B, (i+1)*B) with B = ceil(L/4),
+ *                     letter j in bits [2j, 2j+2) of that little-endian byte string; codes 0,1,2,3 = A,C,G,T(U) — the
+ *                     reference's own letter indices (src/AwFmLetter.c:4-22).  No ambiguity codes.
+ *   AWFM_QUERY_5BIT   amino indexes, fixed length L: B = ceil(5L/8), letter j in bits [5j, 5j+5); codes 0..19 = the
+ *                     letters A C D E F G H I K L M N P Q R S T V W Y in the reference's index order
+ *                     (src/AwFmLetter.c:55-67), any code >= 20 = the ambiguity letter.
+ * A 20-mer costs 5 bytes on the bus instead of 20; an amino 8-mer 5 instead of 8. */
+typedef enum awfm_query_format { AWFM_QUERY_ASCII = 0, AWFM_QUERY_2BIT = 2, AWFM_QUERY_5BIT = 5 } awfm_query_format;
+
 /* Kernel-only timing and work counters of the most recent call on a context (device time from CUDA events). */
 typedef struct awfm_gpu_stats {
   double kernelMs;        /* sum over launches of the search / backtrace kernels          */
@@ -161,6 +173,10 @@ int awfm_gpu_locate_host(awfm_gpu_ctx *ctx, const uint8_t *letters, const uint64
 int awfm_gpu_count_device(awfm_gpu_ctx *ctx, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t fixedLen,
                           uint64_t numQueries, uint32_t *dCounts, awfm_range *dRanges /* may be NULL */,
                           void *stream);
+/* Same for any awfm_query_format (dOffsets must be NULL unless format is AWFM_QUERY_ASCII). */
+int awfm_gpu_count_device_format(awfm_gpu_ctx *ctx, const void *dQueries, uint32_t format, const uint64_t *dOffsets,
+                                 uint32_t fixedLen, uint64_t numQueries, uint32_t *dCounts,
+                                 awfm_range *dRanges /* may be NULL */, void *stream);
 /* dRanges (in) come from awfm_gpu_count_device; dHitOffsets (out, numQueries+1) is their exclusive scan. */
 int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, uint64_t numQueries,
                                 uint64_t *dHitOffsets, void *stream);
@@ -193,6 +209,72 @@ int awfm_gpu_search_list_count(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, u
  * Chunks of the list are pipelined: pack (host team) -> H2D + search + scan -> walk + D2H -> scatter (host team). */
 int awfm_gpu_search_list_locate(awfm_gpu_ctx *ctx, awfm_kmer_search_data *data, uint64_t numQueries,
                                 uint32_t numThreads);
+
+/* ---- device groups: ONE call fanned out over several GPUs of the box (single process, index
+ *      replicated in every GPU's HBM, query i -> GPU floor(i*G/N) in contiguous shards, one DMA stream set per GPU).
+ *      Results land in the caller's HOST arrays directly, so no device-to-device gather exists on this path.
+ *      The reference's parallel axis is inside the call as well (`omp parallel for`, src/AwFmParallelSearch.c:103-106,
+ *      167-170).  A group of one device is the pipelined single-GPU engine. ---- */
+typedef struct awfm_gpu_group awfm_gpu_group;
+/* Replicates the index (HOST arrays in `view`) onto every listed device; numDevices = 0 / devices = NULL = all visible. */
+int awfm_gpu_group_create(awfm_gpu_group **group, const int *devices, int numDevices, const awfm_index_view *view);
+/* Groups contexts that already exist (distinct contexts holding the same index, e.g. one built on the device);
+ * the group does not own them. */
+int awfm_gpu_group_create_from_contexts(awfm_gpu_group **group, awfm_gpu_ctx *const *contexts, int numContexts);
+void awfm_gpu_group_destroy(awfm_gpu_group *group);
+int awfm_gpu_group_size(const awfm_gpu_group *group);
+awfm_gpu_ctx *awfm_gpu_group_context(awfm_gpu_group *group, int i);
+int awfm_gpu_group_set_sequences(awfm_gpu_group *group, const void *metadata, uint64_t numSequences);
+/* keys: "packed_chunk_queries" (queries per pipeline chunk of awfm_gpu_group_count/_locate, multiple of 256; default
+ * 2^24), "packed_min_shard" (a device is only given a shard of at least this many queries; default 2^16),
+ * "packed_window_hits" (hits per walk window of awfm_gpu_group_locate; default 2^24); any other key is forwarded to
+ * every context (awfm_gpu_ctx_set_tuning). */
+int awfm_gpu_group_set_tuning(awfm_gpu_group *group, const char *key, int64_t value);
+int awfm_gpu_group_get_stats(awfm_gpu_group *group, awfm_gpu_stats *out); /* summed over the devices, last call */
+
+/* SURVEY.md §8 row f1 — the additive packed-batch API: contiguous queries in HOST memory (ASCII, 2-bit or 5-bit, see
+ * awfm_query_format) in, flat arrays out; escapes the reference's per-query 32-B structs with pointers
+ * (src/AwFmIndex.h:111-123; list setup src/AwFmParallelSearch.c:36-84).  Every device works through its shard in
+ * chunks on three streams: the H2D copy of chunk i+1, the search of chunk i and the D2H copy of chunk i-1 overlap.
+ * Buffers that are page-locked (awfm_gpu_host_alloc / awfm_gpu_host_register / cudaHostAlloc) are read and written by
+ * the DMA engines in place; pageable ones go through page-locked staging.  `offsets` (numQueries+1 letter offsets) is
+ * for variable-length ASCII batches, else NULL with every query `fixedLen` letters long. */
+int awfm_gpu_group_count(awfm_gpu_group *group, const void *queries, uint32_t format, const uint64_t *offsets,
+                         uint32_t fixedLen, uint64_t numQueries, uint32_t *counts /* out, numQueries */);
+/* Locate, CSR output as awfm_gpu_locate_host: hitOffsets[numQueries+1], positions[hitOffsets[numQueries]] in SA order
+ * within each query.  *totalHits (may be NULL) always receives hitOffsets[numQueries].  If positions is NULL or
+ * positionsCapacity is smaller than that total, only hitOffsets are produced and the call returns AWFM_GPU_OK — size
+ * the buffer and call again.  sequenceIndex / localPosition (both or neither; same length as positions) additionally
+ * receive awFmGetLocalSequencePositionFromIndexPosition's answer for every hit (src/AwFmSearch.c:284-301), computed on
+ * the device right after the walk (needs awfm_gpu_group_set_sequences). */
+int awfm_gpu_group_locate(awfm_gpu_group *group, const void *queries, uint32_t format, const uint64_t *offsets,
+                          uint32_t fixedLen, uint64_t numQueries, uint64_t *hitOffsets, uint64_t *positions,
+                          uint64_t positionsCapacity, uint64_t *sequenceIndex, uint64_t *localPosition,
+                          uint64_t *totalHits);
+/* The reference's list layout over all devices of the group: chunk r of the list is searched on device r mod G. */
+int awfm_gpu_group_search_list_count(awfm_gpu_group *group, awfm_kmer_search_data *data, uint64_t numQueries,
+                                     uint32_t numThreads);
+int awfm_gpu_group_search_list_locate(awfm_gpu_group *group, awfm_kmer_search_data *data, uint64_t numQueries,
+                                      uint32_t numThreads);
+
+/* page-locked host memory every device of the box can DMA from / to */
+int awfm_gpu_host_alloc(void **p, uint64_t bytes);
+void awfm_gpu_host_free(void *p);
+int awfm_gpu_host_register(void *p, uint64_t bytes);
+int awfm_gpu_host_unregister(void *p);
+
+/* ---- result gather between PROCESSES over NVLink without a collective (one process per GPU): the root
+ *      exports a device buffer, every other rank opens it and writes its shard of the results into its slot with a
+ *      copy-engine peer copy on its own stream — no SM of either GPU is involved (an NCCL gather's channel CTAs share
+ *      the SMs with the persistent search kernels).  handle = 64 bytes (cudaIpcMemHandle_t), to be passed between the
+ *      processes by any means. ---- */
+int awfm_gpu_device_malloc(int device, void **dPtr, uint64_t bytes);
+int awfm_gpu_device_free(int device, void *dPtr);
+int awfm_gpu_ipc_export(int device, const void *dPtr, void *handle64);
+int awfm_gpu_ipc_open(int device, const void *handle64, void **dPtr);
+int awfm_gpu_ipc_close(int device, void *dPtr);
+/* dst/src: device pointers valid in this process (local, peer-mapped or IPC-opened); asynchronous on `stream` */
+int awfm_gpu_peer_copy_async(int device, void *dst, const void *src, uint64_t bytes, void *stream);
 
 /* ---- index construction on the device (replaces awFmCreateIndex, src/AwFmCreate.c:31-137,
  *      for texts with bwtLength < 2^32).  Output arrays are in the reference's own formats (raw 160/352-B blocks,

@@ -1,5 +1,6 @@
 import os
 import sys
+import zlib
 
 import numpy as np
 import pytest
@@ -14,6 +15,23 @@ from oracle import harness  # noqa: E402
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are SKIPPED (not failed) on a box without a usable CUDA device, so a plain `pytest` is green on
+    the CPU box and the GPU box runs everything.  The product itself still fails loudly without a device
+    (tests/test_library_symbols.py::test_no_device_means_loud_failure)."""
+    try:
+        from avxwindowfmindex_b200 import capi
+        have_gpu = capi.load().awfm_gpu_device_count() > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box (run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -100,6 +118,6 @@ def small_indexes(reference, tmp_path_factory):
     ]
     out = {}
     for name, amino, n, k, ratio, amb, mixed in specs:
-        text = make_text(n, amino, seed=hash(name) % 10007, ambiguity_every=amb, mixed_case=mixed)
+        text = make_text(n, amino, seed=zlib.crc32(name.encode()) % 10007, ambiguity_every=amb, mixed_case=mixed)  # stable across runs
         out[name] = BuiltIndex(reference, tmp, name, text, amino, k, ratio)
     return out

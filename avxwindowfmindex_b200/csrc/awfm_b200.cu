@@ -795,6 +795,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   mark();
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
+  w.lastSteps = steps, w.lastBuckets = AMINO ? 20 : 4, w.lastQueries = n;
   L.stats.launches += 2 + (format == AWFM_QUERY_ASCII ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + (endBit > beginBit ? 3 : 0);
   return AWFM_GPU_OK;
 }
@@ -880,6 +881,28 @@ extern "C" int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *c, double *ms, int capa
     ms[n] = f;
   }
   cudaGetLastError();
+  return n;
+}
+
+// Live records after every pass of the most recent sweep count call (what the compulsory-traffic model of the bench is
+// computed from): live[0] = queries of the batch, live[p] = records appended by pass p (still searching after LF step
+// p), p = 1 .. passes-1 (the last pass appends nothing).  *irregular = queries answered by sweepIrregular.
+extern "C" int awfm_gpu_ctx_sweep_live(awfm_gpu_ctx *c, uint64_t *live, int capacity, uint64_t *irregular) {
+  if (!c || !live || capacity < 1) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  SweepScratch &w = c->lanes[c->lastLane.load()].sweep;
+  if (!w.ctrl || w.stagesRecorded == 0 && w.lastQueries == 0) return 0;
+  CU(cudaDeviceSynchronize());
+  std::vector<uint32_t> ctrl(kSweepMaxPasses * kSweepCtrlStride + 4);
+  CU(cudaMemcpy(ctrl.data(), w.ctrl, ctrl.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  int n = 0;
+  live[n++] = w.lastQueries;
+  for (uint32_t p = 0; p + 1 < w.lastSteps && n < capacity; p++) {
+    uint64_t sum = 0;
+    for (uint32_t b = 0; b < w.lastBuckets; b++) sum += ctrl[p * kSweepCtrlStride + b];
+    live[n++] = sum;
+  }
+  if (irregular) *irregular = ctrl[kSweepMaxPasses * kSweepCtrlStride];
   return n;
 }
 

@@ -63,6 +63,8 @@ struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grow
   cudaEvent_t stage[awfm::kSweepMaxPasses + 4];  // stage boundaries of the most recent call ("sweep_profile")
   int numStages = 0, stagesRecorded = 0;
   uint64_t bytes = 0;
+  uint32_t lastSteps = 0, lastBuckets = 0;  // passes and buckets of the most recent sweep (for awfm_gpu_ctx_sweep_live)
+  uint64_t lastQueries = 0;
 };
 
 struct PipeSlot {  // one in-flight chunk of the search-list engine

@@ -119,7 +119,7 @@ class IndexArrays:
         return (bits << np.arange(w, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
 
 
-def section_digests(ix: "IndexArrays", chunk_bytes=1 << 26):
+def section_digests(ix: "IndexArrays", chunk_bytes=1 << 26, with_chunks=True):
     """SHA-256 of every section of an index as the `.awfmi` file stores it (blocks, prefix sums, seed table, packed
     sampled SA), plus a short digest per 64-MiB chunk so that a mismatch can be localised.  Used to prove that a
     device-built index equals the one the reference's awFmCreateIndex builds (tools/ref_index_hashes.py)."""
@@ -132,8 +132,12 @@ def section_digests(ix: "IndexArrays", chunk_bytes=1 << 26):
         for o in range(0, len(b), chunk_bytes):
             part = b[o:o + chunk_bytes]
             whole.update(part)
-            chunks.append(hashlib.sha256(part).hexdigest()[:16])
-        return {"bytes": int(len(b)), "sha256": whole.hexdigest(), "chunk_bytes": chunk_bytes, "chunks": chunks}
+            if with_chunks:
+                chunks.append(hashlib.sha256(part).hexdigest()[:16])
+        out = {"bytes": int(len(b)), "sha256": whole.hexdigest()}
+        if with_chunks:
+            out.update({"chunk_bytes": chunk_bytes, "chunks": chunks})
+        return out
 
     out = {"blocks": one(ix.blocks), "prefix_sums": one(ix.prefix_sums.astype("<u8")),
            "seed_table": one(ix.seed_table.astype("<u8"))}

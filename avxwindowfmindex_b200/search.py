@@ -123,6 +123,18 @@ class GpuIndex:
         n = self.lib.awfm_gpu_ctx_sweep_stage_ms(self._ctx, ms, 32)
         return [ms[i] for i in range(max(n, 0))]
 
+    def sweep_live(self):
+        """(live, irregular): live[0] = queries, live[p] = queries still searching after LF step p, of the most recent
+        sweep count call ([] when it took the tile kernel)."""
+        live = (C.c_uint64 * 32)()
+        irregular = C.c_uint64()
+        n = self.lib.awfm_gpu_ctx_sweep_live(self._ctx, live, 32, C.byref(irregular))
+        return [int(live[i]) for i in range(max(n, 0))], int(irregular.value)
+
+    def count_device_format(self, d_queries, fmt, fixed_len, n, d_counts, d_ranges=None, stream=0):
+        capi.check(self.lib.awfm_gpu_count_device_format(self._ctx, d_queries, fmt, None, fixed_len, n, d_counts,
+                                                         d_ranges or None, stream or None))
+
     def device_bytes(self):
         return int(self.lib.awfm_gpu_ctx_device_bytes(self._ctx))
 

@@ -141,6 +141,10 @@ int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
  * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.
  * Returns the number of entries written (<= capacity), 0 when the last count call did not take the sweep path. */
 int awfm_gpu_ctx_sweep_stage_ms(awfm_gpu_ctx *ctx, double *ms, int capacity);
+/* Live records of the most recent sweep count call: live[0] = queries of the batch, live[p] = queries still searching
+ * after LF step p (the records pass p appended).  Returns the number of entries written, 0 when the last count call did
+ * not take the sweep path.  The bench's compulsory-traffic model for the sweep is computed from these. */
+int awfm_gpu_ctx_sweep_live(awfm_gpu_ctx *ctx, uint64_t *live, int capacity, uint64_t *irregular /* may be NULL */);
 
 /* ---- derived structures: spend HBM (180 GB per B200) to remove dependent DRAM round trips.  Both are computed on
  *      the device from the unchanged index with the search kernels' own primitives, hold exactly the values the

@@ -246,20 +246,31 @@ def pack_bits_device(env, d_letters, n, L, amino=False):
     torch = env.torch
     bits = 5 if amino else 2
     nbytes = (L * bits + 7) // 8
-    assert L * bits <= 62
+    per = 56 // bits  # letters per 64-bit accumulator (whole bytes' worth of headroom is not needed: see below)
+    span = per * bits
     out = torch.empty((n, nbytes), dtype=torch.uint8, device=env.dev)
-    shifts = bits * torch.arange(L, device=env.dev, dtype=torch.int64)
     if amino:
         table = torch.full((256,), 20, dtype=torch.int64, device=env.dev)
         for i, ch in enumerate(b"ACDEFGHIKLMNPQRSTVWY"):
             table[ch] = i
-    step = 1 << 23
+    step = 1 << 22
     for a in range(0, n, step):
         m = min(step, n - a)
         w = d_letters[a * L:(a + m) * L].view(m, L).to(torch.int64)
         code = table[w] if amino else ((w >> 1) ^ (w >> 2)) & 3
-        acc = (code << shifts).sum(dim=1)
-        out[a:a + m] = torch.stack([(acc >> (8 * i)) & 0xFF for i in range(nbytes)], dim=1).to(torch.uint8)
+        accs = []  # accumulator c holds letters [c*per, (c+1)*per) in its low `span` bits
+        for c0 in range(0, L, per):
+            c1 = min(L, c0 + per)
+            shifts = bits * torch.arange(c1 - c0, device=env.dev, dtype=torch.int64)
+            accs.append((code[:, c0:c1] << shifts).sum(dim=1))
+        cols = []
+        for i in range(nbytes):
+            c, o = divmod(8 * i, span)
+            b = accs[c] >> o
+            if o + 8 > span and c + 1 < len(accs):
+                b = b | (accs[c + 1] << (span - o))
+            cols.append(b & 0xFF)
+        out[a:a + m] = torch.stack(cols, dim=1).to(torch.uint8)
     return out.reshape(-1)
 
 
@@ -1248,18 +1259,30 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     # ---- the other BASELINE configs ----
+    def guarded(fn, *a):
+        """a secondary leg that breaks (out of memory on a small box, ...) is reported, it does not take the headline
+        with it; a parity failure (SystemExit) is never swallowed"""
+        if world > 1:
+            return fn(*a)  # ranks must fail together
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            torch.cuda.empty_cache()
+            return {"error": repr(e), "traceback": traceback.format_exc()[-1500:]}
+
     if world == 1:
         if "cfg1" not in args.skip:
-            result["cfg1"] = leg_cfg1(env)
+            result["cfg1"] = guarded(leg_cfg1, env)
         if "cfg3" not in args.skip and nl > 0:
             result["cfg3"] = {"ratio_%d" % args.sa_ratio: "see `locate`"}
             for ratio in (1, 16):
                 if ratio != args.sa_ratio:
-                    result["cfg3"]["ratio_%d" % ratio] = leg_cfg3_ratio(env, ratio)
+                    result["cfg3"]["ratio_%d" % ratio] = guarded(leg_cfg3_ratio, env, ratio)
         if "cfg4" not in args.skip:
-            result["cfg4"] = leg_cfg4(env)
+            result["cfg4"] = guarded(leg_cfg4, env)
     if "cfg5" not in args.skip:
-        result["cfg5"] = leg_cfg5(env)
+        result["cfg5"] = guarded(leg_cfg5, env)
 
     if rank != 0:
         if world > 1:

@@ -174,6 +174,9 @@ class Env:
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.dev)
+            # a second, CPU-side group: a rank waiting in an NCCL barrier keeps a spinning kernel on its GPU, which
+            # time-slices against any other process using that GPU (the single-process fan-out leg does)
+            self.cpu_group = dist.new_group(backend="gloo")
         self.lib = capi.load()  # raises if the CUDA library is missing: there is no fallback
         self.stream = torch.cuda.current_stream()
         self.cores = os.cpu_count() or 1
@@ -182,6 +185,12 @@ class Env:
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
+
+    def cpu_barrier(self):
+        """waits on the host only: the waiting ranks' GPUs stay idle"""
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x):
         if self.world == 1:
@@ -1247,11 +1256,11 @@ def run_ours(args):
     device_bytes = gpu.device_bytes()
     # ---- N>1: one process, all GPUs (rank 0; the other ranks' GPUs are idle meanwhile) ----
     if world > 1 and "fanout" not in args.skip and h_bits is not None:
-        env.barrier()
+        env.cpu_barrier()
         if rank == 0:
             full = d_counts.cpu().numpy().astype(np.uint32)
             result["single_process_fanout"] = leg_fanout(env, arrays, h_bits.array, full)
-        env.barrier()
+        env.cpu_barrier()
     if h_bits is not None:
         h_bits.close()
     gpu.close()

@@ -29,6 +29,9 @@ def build(ref=True):
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     if ref and os.path.isdir(os.path.join(REFERENCE_TREE, "src")):
         subprocess.run(["make", "-s", "-C", HERE, "ref", f"REF={REFERENCE_TREE}"], check=True)
+        dropin = os.path.join(HERE, "..", "avxwindowfmindex_b200", "csrc", "libawfm_b200.so")
+        if os.path.exists(dropin):  # the C consumer of tests/test_c_consumer.py (needs the reference's header)
+            subprocess.run(["make", "-s", "-C", HERE, "consumers", f"REF={REFERENCE_TREE}"], check=True)
 
 
 def have_reference():

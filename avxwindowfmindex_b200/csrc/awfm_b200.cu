@@ -388,6 +388,7 @@ static void freeScratch(LocateScratch &sc) {
 static void freeSweep(SweepScratch &w) {
   cudaFree(w.arena);
   cudaFree(w.ctrl);
+  cudaFree(w.sortCtrl);
   cudaFree(w.sortTemp);
   if (w.done) cudaEventDestroy(w.done);
   for (int i = 0; i < w.numStages; i++) cudaEventDestroy(w.stage[i]);
@@ -466,6 +467,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_max_batch" && value >= 256 && value <= (1ll << 30)) c->sweepMaxBatch = value;
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
+  else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
@@ -516,9 +518,9 @@ extern "C" int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *cc, awfm_gpu_stats *ou
 
 // ------------------------------------------------------------------------------------------------ launches
 template <typename K>
-static int gridFor(awfm_gpu_ctx *c, K kernel, int threads, int *grid) {
+static int gridFor(awfm_gpu_ctx *c, K kernel, int threads, int *grid, size_t dynamicSmem = 0) {
   int perSm = c->blocksPerSm;
-  if (perSm == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0));
+  if (perSm == 0 || dynamicSmem) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, dynamicSmem));
   if (perSm < 1) perSm = 1;
   *grid = c->numSMs * perSm;  // whole multiples of the SM count: persistent grid-stride CTAs
   return AWFM_GPU_OK;
@@ -640,6 +642,7 @@ static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
     w.numStages++;
   }
   if (!w.ctrl) CU(cudaMalloc(&w.ctrl, (kSweepMaxPasses * kSweepCtrlStride + 4) * sizeof(uint32_t)));
+  if (!w.sortCtrl) CU(cudaMalloc(&w.sortCtrl, sizeof(SortCtrl) + 2 * (sizeof(uint32_t) << (2 * kSortMaxDigitBits))));
   if (w.cap >= n && w.arrays == arrays) return AWFM_GPU_OK;
   CU(cudaDeviceSynchronize());
   cudaFree(w.arena);
@@ -682,40 +685,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   CU(cudaMemsetAsync(dCounts, 0, n * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(w.ctrl, 0, (kSweepMaxPasses * kSweepCtrlStride + 4) * sizeof(uint32_t), st));
   uint32_t *irregularCount = w.ctrl + kSweepMaxPasses * kSweepCtrlStride;
-  {
-    const uint64_t tiles = (n + 255) / 256;
-    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
-    if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
-      const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
-      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0]);
-    } else if (AMINO && len % 4 == 0 && len <= 12) {
-      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
-      switch (len / 4) {
-        case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
-        case 2: sweepPackWordsAmino<2><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
-        default: sweepPackWordsAmino<3><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); break;
-      }
-    } else if (!AMINO && len % 4 == 0) {
-      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
-      switch (len / 4) {
-#define AWFM_PACK_CASE(W)                                                                                         \
-  case W:                                                                                                         \
-    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount); \
-    break;
-        AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
-        AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
-#undef AWFM_PACK_CASE
-        default: return awfm_fail(AWFM_GPU_ERR_ARG, "sweep: query length out of range");
-      }
-    } else {
-      const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
-      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount);
-    }
-    CU(cudaGetLastError());
-  }
-  mark();
-  int cur = 0;
-  // the radix sort orders the key's top bits; the first pass finishes up to 8 more inside each tile (shared memory)
+  // ---- how the pairs get ordered: the top bits of the key globally, up to 8 more inside each tile of the first pass ----
   const int endBit = (int)sweepKeyBits(c, k);
   // Low key bits left to the first pass's tile-local sort.  Automatic: as many as keep a group of equal upper bits
   // within about two 1024-pair tiles (beyond that the tiles of a group interleave too many runs for the warps to
@@ -730,7 +700,69 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   }
   const uint32_t localBits = (uint32_t)std::min({wantLocal, endBit, 8});
   const int beginBit = std::max(0, endBit - std::min(c->sweepSortBits, endBit - (int)localBits));
-  if (endBit > beginBit) {
+  const int sortedBits = endBit - beginBit;
+  // our own two bucket passes (awfm_sort.cuh) order up to 16 bits; deeper seed tables go through CUB
+  const bool ownSort = c->sweepOwnSort && sortedBits >= 1 && sortedBits <= 2 * kSortMaxDigitBits;
+  const uint32_t dA = ownSort ? (uint32_t)(sortedBits <= kSortMaxDigitBits ? sortedBits : sortedBits - sortedBits / 2) : 0u;
+  const uint32_t dB = ownSort ? (uint32_t)sortedBits - dA : 0u;
+  const uint32_t shiftA = (uint32_t)endBit - dA, shiftB = (uint32_t)beginBit;
+  SortCtrl *sortCtrl = ownSort ? reinterpret_cast<SortCtrl *>(w.sortCtrl) : nullptr;
+  uint32_t *countB = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.sortCtrl) + sizeof(SortCtrl));
+  uint32_t *cursorB = countB + (1u << (2 * kSortMaxDigitBits));
+  if (ownSort) CU(cudaMemsetAsync(w.sortCtrl, 0, sizeof(SortCtrl) + (dB ? sizeof(uint32_t) << (dA + dB) : 0), st));
+  {
+    const uint64_t tiles = (n + 255) / 256;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
+    if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
+      const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
+      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA);
+    } else if (AMINO && len % 4 == 0 && len <= 12) {
+      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
+      switch (len / 4) {
+        case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
+        case 2: sweepPackWordsAmino<2><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
+        default: sweepPackWordsAmino<3><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
+      }
+    } else if (!AMINO && len % 4 == 0) {
+      const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
+      switch (len / 4) {
+#define AWFM_PACK_CASE(W)                                                                                         \
+  case W:                                                                                                         \
+    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); \
+    break;
+        AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
+        AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
+#undef AWFM_PACK_CASE
+        default: return awfm_fail(AWFM_GPU_ERR_ARG, "sweep: query length out of range");
+      }
+    } else {
+      const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
+      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA);
+    }
+    CU(cudaGetLastError());
+  }
+  mark();
+  int cur = 0;
+  uint32_t sortLaunches = 0;
+  if (ownSort) {
+    int grid = 0;
+    if (int r = gridFor(c, sortPass<false>, kSortThreads, &grid, kSortSmemBytes)) return r;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSortTile - 1) / kSortTile);
+    sortBases<0><<<1, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+    sortPass<false><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[0], w.vals[0], w.keys[1], w.vals[1], (uint32_t)n, sortCtrl,
+                                                               cursorB, dA, dB, shiftA);
+    cur = 1;
+    sortLaunches = 2;
+    if (dB) {
+      sortDigitCounts<<<grid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
+      sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+      sortPass<true><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[1], w.vals[1], w.keys[0], w.vals[0], (uint32_t)n, sortCtrl,
+                                                                cursorB, dA, dB, shiftB);
+      cur = 0;
+      sortLaunches = 5;
+    }
+    CU(cudaGetLastError());
+  } else if (endBit > beginBit) {
     cub::DoubleBuffer<uint32_t> dk(w.keys[0], w.keys[1]);
     cub::DoubleBuffer<uint64_t> dv(w.vals[0], w.vals[1]);
     size_t need = 0;
@@ -746,6 +778,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     size_t have = w.sortTempBytes;
     CU(cub::DeviceRadixSort::SortPairs(w.sortTemp, have, dk, dv, (int)n, beginBit, endBit, st));
     cur = dk.selector;
+    sortLaunches = 3;
   }
   mark();
   auto gen = [&](int g, int pass) {
@@ -796,7 +829,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
   w.lastSteps = steps, w.lastBuckets = AMINO ? 20 : 4, w.lastQueries = n;
-  L.stats.launches += 2 + (format == AWFM_QUERY_ASCII ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + (endBit > beginBit ? 3 : 0);
+  L.stats.launches += 2 + (format == AWFM_QUERY_ASCII ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
   return AWFM_GPU_OK;
 }
 

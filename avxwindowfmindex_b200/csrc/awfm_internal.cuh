@@ -57,7 +57,8 @@ struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grow
   int arrays = 0;                          // arrays per generation the arena was carved for
   uint32_t *ctrl = nullptr;                // [kSweepMaxPasses][stride] bucket counters, then the irregular-query counter
   uint32_t *irregularIds = nullptr;
-  void *sortTemp = nullptr;
+  void *sortCtrl = nullptr;                // awfm_sort.cuh: SortCtrl + group counts + group cursors
+  void *sortTemp = nullptr;                // CUB's temporary storage (seed tables deeper than 2^24 entries)
   size_t sortTempBytes = 0;
   cudaEvent_t done = nullptr;              // end of the last sweep: the next one (possibly on another stream) waits
   cudaEvent_t stage[awfm::kSweepMaxPasses + 4];  // stage boundaries of the most recent call ("sweep_profile")
@@ -129,7 +130,7 @@ struct awfm_gpu_ctx {
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
   int64_t sweepMaxBatch = 1ll << 27;
   int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
-  int sweepOwnSort = 0;  // 1 = the hand-written stable radix passes (awfm_sort.cuh), 0 = CUB (cross-check)
+  int sweepOwnSort = 1;  // 1 = the hand-written stable radix passes (awfm_sort.cuh), 0 = CUB (cross-check)
   static constexpr int kLanes = 3;
   Lane lanes[kLanes];
   std::atomic<int> lastLane{0};  // lane of the most recent call: what get_stats / sweep_stage_ms report

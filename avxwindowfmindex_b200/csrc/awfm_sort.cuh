@@ -1,0 +1,226 @@
+// awfm_sort.cuh — the ordering step of the sweep count path (awfm_sweep.cuh), hand-written for sm_100a.
+//
+// What the sweep needs is weaker than a sort: the (key, payload) pairs GROUPED by the top S bits of the key, groups in
+// ascending order, any order inside a group (the first sweep pass finishes the low bits inside each of its tiles, and a
+// query's result does not depend on the processing order).  No stability is required, so there is no look-back chain
+// and no spinning anywhere: two most-significant-digit-first bucket passes of up to 8 bits each,
+//
+//   pack kernel        also counts the top digit A (shared-memory histogram per CTA, 2^dA atomics per CTA at the end)
+//   sortBases<0>       exclusive scan of the 2^dA bucket counts -> bucket bases, append cursors, tile map of pass B
+//   sortPass<false>    tiles of kSortTile pairs in input order: counting sort by digit A in shared memory (rank = one
+//                      shared atomic per pair), ONE global atomicAdd per tile and bucket claims room behind the
+//                      bucket's cursor, pairs leave the tile bucket by bucket (runs of ~kSortTile/2^dA neighbours)
+//   sortDigitCounts    tiles inside the bucket regions: shared histogram of digit B, 2^dB atomics per tile
+//   sortBases<1>       exclusive scan of the 2^(dA+dB) group counts (one CTA per bucket)
+//   sortPass<true>     the same tile body on digit B, tiles cut so that none straddles two buckets
+//
+// against CUB's onesweep (round 1: 1.68 ms for 100 M pairs, 3.0 TB/s, profiles/r01_ncu_sweep_cub_onesweep.json) the pairs
+// are moved the same two times, but the passes carry no decoupled look-back and no per-tile status polling.  CUB stays
+// as the path for S > 16 (seed tables deeper than 2^24 entries) and as a cross-check ("sweep_own_sort" = 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace awfm {
+
+constexpr int kSortThreads = 256;
+#ifndef AWFM_SORT_ITEMS
+#define AWFM_SORT_ITEMS 12
+#endif
+constexpr int kSortItems = AWFM_SORT_ITEMS;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kSortMaxDigitBits = 8;
+constexpr int kSortBins = 1 << kSortMaxDigitBits;
+
+// control block of one sort (device memory, zeroed before the pack kernel)
+struct SortCtrl {
+  uint32_t countA[kSortBins];       // pairs per top-digit bucket (pack kernel)
+  uint32_t baseA[kSortBins + 1];    // first slot of every bucket (+ total)
+  uint32_t cursorA[kSortBins];      // append cursor of pass A
+  uint32_t tilesBefore[kSortBins + 1];  // pass B: tiles in the buckets before a (+ total)
+  uint32_t ticket[4];               // tile tickets of pass A, the digit count, pass B
+};
+// followed in the same allocation by countB[2^(dA+dB)] and cursorB[2^(dA+dB)]
+
+template <int LEVEL>  // 0: bucket bases from countA; 1: group bases from countB (grid = 2^dA CTAs)
+__global__ void __launch_bounds__(kSortThreads)
+    sortBases(SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB, uint32_t *__restrict__ cursorB, uint32_t dA,
+              uint32_t dB) {
+  __shared__ uint32_t warpSums[kSortThreads / 32];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  auto blockExclusive = [&](uint32_t v, uint32_t &total) {  // exclusive scan over the CTA's 256 threads
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= (unsigned)d) incl += up;
+    }
+    __syncthreads();
+    if (lane == 31u) warpSums[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (unsigned w = 0; w < kSortThreads / 32; w++) {
+      const uint32_t s = warpSums[w];
+      before += w < warp ? s : 0u;
+      all += s;
+    }
+    total = all;
+    return before + incl - v;
+  };
+  if (LEVEL == 0) {
+    const uint32_t bins = 1u << dA;
+    const uint32_t c = threadIdx.x < bins ? ctrl->countA[threadIdx.x] : 0u;
+    uint32_t total, tilesTotal;
+    const uint32_t base = blockExclusive(c, total);
+    const uint32_t tiles = (c + kSortTile - 1) / kSortTile;
+    const uint32_t tb = blockExclusive(tiles, tilesTotal);
+    if (threadIdx.x < bins) {
+      ctrl->baseA[threadIdx.x] = base;
+      ctrl->cursorA[threadIdx.x] = base;
+      ctrl->tilesBefore[threadIdx.x] = tb;
+    }
+    if (threadIdx.x == 0) {
+      ctrl->baseA[bins] = total;
+      ctrl->tilesBefore[bins] = tilesTotal;
+    }
+  } else {
+    const uint32_t a = blockIdx.x, bins = 1u << dB;
+    const uint32_t c = threadIdx.x < bins ? countB[(a << dB) + threadIdx.x] : 0u;
+    uint32_t total;
+    const uint32_t local = blockExclusive(c, total);
+    if (threadIdx.x < bins) cursorB[(a << dB) + threadIdx.x] = ctrl->baseA[a] + local;
+  }
+}
+
+// pass B's tile t -> (bucket a, first pair, number of pairs); tiles never straddle two buckets
+__device__ __forceinline__ void sortTileOfBucket(const SortCtrl *__restrict__ ctrl, uint32_t numBuckets, uint32_t tile,
+                                                 uint32_t &a, uint32_t &first, uint32_t &count) {
+  uint32_t lo = 0, hi = numBuckets;  // last a with tilesBefore[a] <= tile
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (ctrl->tilesBefore[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  a = lo;
+  const uint32_t j = tile - ctrl->tilesBefore[a];
+  const uint32_t begin = ctrl->baseA[a], end = ctrl->baseA[a + 1];
+  first = begin + j * kSortTile;
+  count = min((uint32_t)kSortTile, end - first);
+}
+
+// histogram of digit B inside the bucket regions (keys only: 4 B per pair)
+static __global__ void __launch_bounds__(kSortThreads)
+    sortDigitCounts(const uint32_t *__restrict__ keys, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB,
+                    uint32_t dA, uint32_t dB, uint32_t shiftB) {
+  __shared__ uint32_t bins[kSortBins];
+  __shared__ uint32_t tileShared;
+  const uint32_t numBuckets = 1u << dA, maskB = (1u << dB) - 1u;
+  const uint32_t totalTiles = ctrl->tilesBefore[numBuckets];
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) tileShared = atomicAdd(&ctrl->ticket[1], 1u);
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = tileShared;
+    if (tile >= totalTiles) break;
+    uint32_t a, first, count;
+    sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) atomicAdd(&bins[(__ldg(keys + first + i) >> shiftB) & maskB], 1u);
+    }
+    __syncthreads();
+    const uint32_t c = bins[threadIdx.x];
+    if (c) atomicAdd(countB + (a << dB) + threadIdx.x, c);
+  }
+}
+
+// One bucket pass.  SECOND = false: tiles in input order, digit A, cursors ctrl->cursorA.  SECOND = true: tiles inside
+// the bucket regions of pass A's output, digit B, cursors cursorB[a << dB | digit].
+template <bool SECOND>
+__global__ void __launch_bounds__(kSortThreads)
+    sortPass(const uint32_t *__restrict__ keysIn, const uint64_t *__restrict__ valsIn, uint32_t *__restrict__ keysOut,
+             uint64_t *__restrict__ valsOut, uint32_t numPairs, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ cursorB,
+             uint32_t dA, uint32_t dB, uint32_t shift) {
+  extern __shared__ __align__(16) uint8_t sortSmem[];
+  uint64_t *sVal = reinterpret_cast<uint64_t *>(sortSmem);                        // kSortTile
+  uint32_t *sKey = reinterpret_cast<uint32_t *>(sortSmem + 8 * (size_t)kSortTile);  // kSortTile
+  __shared__ uint32_t bins[kSortBins], localBase[kSortBins], globalBase[kSortBins];
+  __shared__ uint32_t warpSums[kSortThreads / 32];
+  __shared__ uint32_t tileShared;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t digitBits = SECOND ? dB : dA, mask = (1u << digitBits) - 1u;
+  const uint32_t numBuckets = 1u << dA;
+  const uint32_t totalTiles = SECOND ? ctrl->tilesBefore[numBuckets] : (numPairs + kSortTile - 1) / kSortTile;
+  for (;;) {
+    __syncthreads();  // previous tile's staging consumed
+    if (threadIdx.x == 0) tileShared = atomicAdd(&ctrl->ticket[SECOND ? 2 : 0], 1u);
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = tileShared;
+    if (tile >= totalTiles) break;
+    uint32_t a = 0, first, count;
+    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
+    else first = tile * kSortTile, count = min((uint32_t)kSortTile, numPairs - first);
+    uint32_t key[kSortItems], rank[kSortItems];
+    uint64_t val[kSortItems];
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      const uint32_t src = first + min(i, count - 1u);
+      key[it] = __ldg(keysIn + src);
+      val[it] = __ldg(valsIn + src);
+    }
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) rank[it] = atomicAdd(&bins[(key[it] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    {  // exclusive scan of the tile's bin counts; room behind the global cursors
+      const uint32_t c = bins[threadIdx.x];
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (unsigned)d) incl += up;
+      }
+      if (lane == 31u) warpSums[warp] = incl;
+      __syncthreads();
+      uint32_t before = 0;
+#pragma unroll
+      for (unsigned w = 0; w < kSortThreads / 32; w++) before += w < warp ? warpSums[w] : 0u;
+      localBase[threadIdx.x] = before + incl - c;
+      uint32_t *cursor = SECOND ? cursorB + (a << dB) + threadIdx.x : ctrl->cursorA + threadIdx.x;
+      globalBase[threadIdx.x] = c ? atomicAdd(cursor, c) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) {
+        const uint32_t dst = localBase[(key[it] >> shift) & mask] + rank[it];
+        sKey[dst] = key[it];
+        sVal[dst] = val[it];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) {
+        const uint32_t k = sKey[i];
+        const uint32_t d = (k >> shift) & mask;
+        const uint32_t dst = globalBase[d] + (i - localBase[d]);
+        keysOut[dst] = k;
+        valsOut[dst] = sVal[i];
+      }
+    }
+  }
+}
+
+constexpr size_t kSortSmemBytes = 12 * (size_t)kSortTile;
+
+}  // namespace awfm

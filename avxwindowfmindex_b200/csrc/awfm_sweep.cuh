@@ -37,6 +37,7 @@
 // variable-length batches, bwtLength > 2^32, len - k > 16 (amino: 6), k > 16 (amino: 7).
 #pragma once
 #include "awfm_kernels.cuh"
+#include "awfm_sort.cuh"
 
 namespace awfm {
 
@@ -72,6 +73,28 @@ struct SweepAlphabet {
 // the last k letters (src/AwFmKmerTable.c:21-51) is Q mod 4^k, and Q >> 2k has the letter prepended next in its low
 // bits.
 // ---------------------------------------------------------------------------------------------------------------
+// Top-digit histogram of the ordering step (awfm_sort.cuh), kept per CTA in shared memory by the pack kernels and
+// flushed with one atomic per bin and CTA.  sortCtrl == nullptr: the caller orders the pairs some other way.
+struct PackHistogram {
+  uint32_t *bins;  // [kSortBins] shared
+  __device__ __forceinline__ void begin(uint32_t *shared, const SortCtrl *ctrl) {
+    bins = shared;
+    if (ctrl) {
+      for (uint32_t b = threadIdx.x; b < (uint32_t)kSortBins; b += blockDim.x) bins[b] = 0;
+      __syncthreads();
+    }
+  }
+  __device__ __forceinline__ void add(const SortCtrl *ctrl, uint32_t key, uint32_t shiftA) {
+    if (ctrl) atomicAdd(&bins[key >> shiftA], 1u);
+  }
+  __device__ __forceinline__ void flush(SortCtrl *ctrl) {
+    if (ctrl) {
+      __syncthreads();
+      for (uint32_t b = threadIdx.x; b < (uint32_t)kSortBins; b += blockDim.x)
+        if (bins[b]) atomicAdd(&ctrl->countA[b], bins[b]);
+    }
+  }
+};
 __device__ __forceinline__ uint32_t packFourLetters(uint32_t w, uint32_t &bad) {
   const uint32_t code = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
   const uint32_t b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u, both = b0 & b1;
@@ -85,7 +108,10 @@ template <int WORDS>  // words per query (len / 4), fully unrolled
 __global__ void __launch_bounds__(256)
     sweepPackWords(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
                    uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-                   uint32_t *__restrict__ irregularCount) {
+                   uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+  __shared__ uint32_t histShared[kSortBins];
+  PackHistogram hist;
+  hist.begin(histShared, sortCtrl);
   const uint64_t keyMask = (k >= 16) ? 0xFFFFFFFFull : ((1ull << (2 * k)) - 1ull);
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
        q += (uint64_t)gridDim.x * blockDim.x) {
@@ -104,7 +130,9 @@ __global__ void __launch_bounds__(256)
     }
     keys[q] = (uint32_t)(Q & keyMask);
     vals[q] = ((Q >> (2 * k)) << 32) | id;
+    hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
   }
+  hist.flush(sortCtrl);
 }
 
 // Amino counterpart (len % 4 == 0): the query's words straight from global memory, letters translated one by one
@@ -114,7 +142,10 @@ template <int WORDS>
 __global__ void __launch_bounds__(256)
     sweepPackWordsAmino(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
                         uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-                        uint32_t *__restrict__ irregularCount) {
+                        uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+  __shared__ uint32_t histShared[kSortBins];
+  PackHistogram hist;
+  hist.begin(histShared, sortCtrl);
   constexpr uint32_t LEN = 4 * WORDS;
   const uint32_t rest = LEN - k;
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
@@ -139,7 +170,9 @@ __global__ void __launch_bounds__(256)
     }
     keys[q] = key;
     vals[q] = ((uint64_t)packed << 32) | id;
+    hist.add(sortCtrl, key, shiftA);
   }
+  hist.flush(sortCtrl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -149,9 +182,12 @@ template <bool AMINO>  // amino: key = mixed-radix seed index (radix 20), 5 bits
 __global__ void __launch_bounds__(256)
     sweepPack(const uint8_t *__restrict__ letters, uint64_t numQueries, uint32_t len, uint32_t k,
               uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-              uint32_t *__restrict__ irregularCount) {
+              uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
   constexpr uint32_t CARD = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   extern __shared__ __align__(16) uint8_t sLetters[];  // 256 * len bytes, rounded up to 16
+  __shared__ uint32_t histShared[kSortBins];
+  PackHistogram hist;
+  hist.begin(histShared, sortCtrl);
   const uint64_t numTiles = (numQueries + 255) / 256;
   const uint64_t totalBytes = numQueries * (uint64_t)len;
   const uint32_t rest = len - k;
@@ -194,8 +230,10 @@ __global__ void __launch_bounds__(256)
       }
       keys[q0 + threadIdx.x] = key;
       vals[q0 + threadIdx.x] = ((uint64_t)packed << 32) | id;
+      hist.add(sortCtrl, key, shiftA);
     }
   }
+  hist.flush(sortCtrl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -208,8 +246,12 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256)
     sweepPackBits(const uint8_t *__restrict__ packed, uint64_t numQueries, uint32_t len, uint32_t k,
-                  uint32_t *__restrict__ keys, uint64_t *__restrict__ vals) {
+                  uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, SortCtrl *__restrict__ sortCtrl,
+                  uint32_t shiftA) {
   extern __shared__ __align__(16) uint8_t sPacked[];  // 256 * B bytes, rounded up to 16
+  __shared__ uint32_t histShared[kSortBins];
+  PackHistogram hist;
+  hist.begin(histShared, sortCtrl);
   const uint32_t B = (len + 3u) >> 2;
   const uint64_t numTiles = (numQueries + 255) / 256;
   const uint64_t totalBytes = numQueries * (uint64_t)B;
@@ -242,8 +284,10 @@ static __global__ void __launch_bounds__(256)
       const uint64_t Q = r >> (64u - 2u * len);  // first letter most significant, 2 bits per letter
       keys[q0 + threadIdx.x] = (uint32_t)(Q & keyMask);
       vals[q0 + threadIdx.x] = ((Q >> (2 * k)) << 32) | (uint32_t)(q0 + threadIdx.x);
+      hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
     }
   }
+  hist.flush(sortCtrl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

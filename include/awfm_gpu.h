@@ -135,7 +135,9 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * "sweep_first_items" (records per thread and tile of the later passes / of the first pass: 1, 2, 4, 8; default 4),
  * "sweep_max_batch" (queries per slice of the scratch — 92 B per query, 348 B for amino indexes —, default 2^27; when
  * even that does not fit the call is answered by the tile kernel), "sweep_profile" (0/1: record an event after every
- * stage of the next calls). */
+ * stage of the next calls), "sweep_own_sort" (1, the default: the hand-written bucket passes of csrc/awfm_sort.cuh order
+ * the pairs whenever at most 16 key bits have to be ordered globally; 0: CUB's radix sort, kept as cross-check and for
+ * deeper seed tables). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 /* Device time of every stage of the most recent sweep count call made with "sweep_profile" = 1, in launch order:
  * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.

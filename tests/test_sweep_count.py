@@ -182,3 +182,26 @@ def test_sweep_repeated_calls_and_streams(small_indexes):
         o_counts, _, _ = oracle.count(letters, fixed_len=k + 6)
         assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), o_counts)
     gpu.close()
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r16", "amino_r8"])
+def test_own_bucket_passes_and_cub_order_alike(small_indexes, name):
+    """The ordering step (csrc/awfm_sort.cuh: two unstable most-significant-digit-first bucket passes) against CUB's
+    radix sort on the same batches: counts and ranges identical to the oracle either way, for one- and two-digit splits
+    and for batches smaller and larger than one sort tile."""
+    b = small_indexes[name]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    for length, num in ((k + 1, 3), (k + 3, 3071), (k + 2, 3073), (k + 4, 50000), (k, 9000)):
+        letters = fixed_batch(b, length, num, seed=num + length)
+        o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
+        for own in (1, 0):
+            for bits, local in ((32, -1), (32, 0), (5, 3), (9, 2), (16, 0), (1, 8)):
+                gpu.set_tuning(sweep_min_queries=1, sweep_own_sort=own, sweep_sort_bits=bits, sweep_local_bits=local,
+                               sweep_profile=1)
+                counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+                assert gpu.sweep_stage_ms(), "the batch did not take the sweep path"
+                assert np.array_equal(counts, o_counts), (name, length, num, own, bits, local)
+                assert np.array_equal(ranges, o_ranges), (name, length, num, own, bits, local)
+    gpu.close()

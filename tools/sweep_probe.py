@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--first-items", type=int, default=4)
     ap.add_argument("--no-tile", action="store_true")
     ap.add_argument("--amino", action="store_true", help="cfg 4 shape: pass --bp 1000000000 --queries 50000000 --kmer 8 --seed-k 5")
+    ap.add_argument("--own-sort", type=str, default="1,0", help="ordering step: 1 = csrc/awfm_sort.cuh, 0 = CUB")
     ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
     lib = capi.load()
@@ -70,12 +71,14 @@ def main():
     ms = 0.0 if args.no_tile else timed(n, d_ref)
     emit({"variant": "tile", "queries": n, "ms": ms, "Gq_per_s": n / max(ms, 1e-9) / 1e6, "hits": int(d_ref.sum(dtype=torch.int64))})
     gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
-    for items, bits, local in [(int(i), int(x), int(l)) for i in args.items.split(",") for x in args.bits.split(",") if x
-                               for l in args.local.split(",")]:
-        gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items, sweep_local_bits=local, sweep_first_items=args.first_items)
+    for own, items, bits, local in [(int(o), int(i), int(x), int(l)) for o in args.own_sort.split(",")
+                                    for i in args.items.split(",") for x in args.bits.split(",") if x
+                                    for l in args.local.split(",")]:
+        gpu.set_tuning(sweep_sort_bits=bits, sweep_items=items, sweep_local_bits=local, sweep_first_items=args.first_items,
+                       sweep_own_sort=own)
         d_counts.fill_(-1)
         ms = timed(n, d_counts)
-        emit({"variant": "sweep", "amino": args.amino, "sort_bits": bits, "local_bits": local, "items": items, "first_items": args.first_items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+        emit({"variant": "sweep", "own_sort": own, "amino": args.amino, "sort_bits": bits, "local_bits": local, "items": items, "first_items": args.first_items, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
               "device_bytes": gpu.device_bytes()})
@@ -86,7 +89,7 @@ def main():
         gpu.count_device(d_letters.data_ptr(), None, L, n, d_counts.data_ptr(), None, stream.cuda_stream)
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_pop()
-    gpu.set_tuning(sweep_sort_bits=32)
+    gpu.set_tuning(sweep_sort_bits=32, sweep_own_sort=1)
     for nq in [int(x) for x in args.sizes.split(",") if x]:
         gpu.set_tuning(sweep_min_queries=-1)
         t_tile = timed(nq, d_ref, reps=2)

@@ -754,7 +754,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     cur = 1;
     sortLaunches = 2;
     if (dB) {
-      sortDigitCounts<<<grid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
+      int countGrid = 0;
+      if (int r = gridFor(c, sortDigitCounts, kSortThreads, &countGrid)) return r;
+      countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + kSortTile - 1) / kSortTile + (1u << dA));
+      sortDigitCounts<<<countGrid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
       sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
       sortPass<true><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[1], w.vals[1], w.keys[0], w.vals[0], (uint32_t)n, sortCtrl,
                                                                 cursorB, dA, dB, shiftB);

@@ -48,6 +48,7 @@ struct GroupDevice {
   PackSlot slots[kSlots];
   GrowBuf dRanges, dHit;  // locate: the shard's ranges and hit offsets stay on the device between the two phases
   uint64_t *hTotal = nullptr;  // page-locked
+  cudaEvent_t rebased = nullptr;  // locate phase B: the shard's hit offsets carry their global base
   uint64_t total = 0, base = 0;
   int rc = AWFM_GPU_OK;
   std::string err;
@@ -58,7 +59,7 @@ struct GroupDevice {
 
 struct awfm_gpu_group {
   std::vector<std::unique_ptr<GroupDevice>> dev;
-  int64_t chunkQueries = 1ll << 24, minShard = 1ll << 16, windowHits = 1ll << 24;
+  int64_t chunkQueries = 1ll << 24, minShard = 1ll << 16, windowHits = 1ll << 22;
   std::mutex mu;  // one packed-batch call at a time per group
 };
 
@@ -73,6 +74,7 @@ int prepareDevice(GroupDevice &D) {
     if (!s.sc.dWorkCounter) CU(cudaMalloc(&s.sc.dWorkCounter, 64));
   }
   if (!D.hTotal) CU(cudaHostAlloc(&D.hTotal, 64, cudaHostAllocPortable));
+  if (!D.rebased) CU(cudaEventCreateWithFlags(&D.rebased, cudaEventDisableTiming));
   D.ready = true;
   return AWFM_GPU_OK;
 }
@@ -96,6 +98,8 @@ void releaseDevice(GroupDevice &D) {
   D.dHit.release();
   if (D.hTotal) cudaFreeHost(D.hTotal);
   D.hTotal = nullptr;
+  if (D.rebased) cudaEventDestroy(D.rebased);
+  D.rebased = nullptr;
   cudaGetLastError();
   if (D.owned) awfm_gpu_ctx_destroy(D.ctx);
   D.ctx = nullptr;
@@ -185,6 +189,29 @@ void addStats(awfm_gpu_stats &into, const awfm_gpu_stats &s) {
   into.kernelMs += s.kernelMs;
 }
 
+// Chunk boundaries of a shard.  The first and the last chunk are half-sized: the pipeline's fill (H2D of the first chunk,
+// nothing to overlap it with) and drain (D2H of the last chunk's results) shrink, while the chunks in between stay large
+// enough for the sweep path's per-call cost (the index is streamed once per LF step whatever the batch size).
+std::vector<uint64_t> chunkStarts(uint64_t qa, uint64_t qb, uint64_t chunk) {
+  std::vector<uint64_t> starts{qa};
+  const uint64_t half = std::max<uint64_t>(256, (chunk / 2 + 255) & ~255ull);
+  if (chunk < 1024) {  // too small to be worth a ramp (tests): plain chunks
+    for (uint64_t pos = qa + chunk; pos < qb; pos += chunk) starts.push_back(pos);
+  } else if (qb - qa <= chunk + half) {
+    if (qb - qa > chunk) starts.push_back(qa + (((qb - qa) / 2 + 255) & ~255ull));
+  } else {
+    uint64_t pos = qa + half;
+    while (qb - pos > chunk + half) {
+      starts.push_back(pos);
+      pos += chunk;
+    }
+    starts.push_back(pos);
+    if (qb - pos > chunk) starts.push_back(qb - half - ((qb - half - pos) & 255ull));
+  }
+  starts.push_back(qb);
+  return starts;
+}
+
 // ---- count: one device's shard [qa, qb) ----
 int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, uint64_t qb) {
   awfm_gpu_ctx *c = D.ctx;
@@ -193,12 +220,12 @@ int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, u
   Lane &L = *hold;
   awfm_begin_call(L);
   if (int r = prepareDevice(D)) return r;
-  const uint64_t chunk = (uint64_t)g->chunkQueries;
-  uint64_t k = 0, h2d = 0, d2h = 0;
+  const std::vector<uint64_t> starts = chunkStarts(qa, qb, (uint64_t)g->chunkQueries);
+  uint64_t h2d = 0, d2h = 0;
   int rc = AWFM_GPU_OK;
-  for (uint64_t q0 = qa; q0 < qb && rc == AWFM_GPU_OK; q0 += chunk, k++) {
+  for (size_t k = 0; k + 1 < starts.size() && rc == AWFM_GPU_OK; k++) {
     PackSlot &s = D.slots[k % GroupDevice::kSlots];
-    const uint64_t m = std::min(chunk, qb - q0);
+    const uint64_t q0 = starts[k], m = starts[k + 1] - q0;
     if ((rc = finishSlot(s))) break;
     PackedBatch b;
     if ((rc = shipChunk(job, s, q0, m, &b, &h2d))) break;
@@ -238,11 +265,11 @@ int locateShardRanges(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_
   if (shard == 0) return AWFM_GPU_OK;
   if (int r = D.dRanges.ensure(shard * 16)) return r;
   if (int r = D.dHit.ensure((shard + 1) * 8)) return r;
-  const uint64_t chunk = (uint64_t)g->chunkQueries;
-  uint64_t k = 0, h2d = 0;
-  for (uint64_t q0 = qa; q0 < qb; q0 += chunk, k++) {
+  const std::vector<uint64_t> starts = chunkStarts(qa, qb, (uint64_t)g->chunkQueries);
+  uint64_t h2d = 0;
+  for (size_t k = 0; k + 1 < starts.size(); k++) {
     PackSlot &s = D.slots[k % GroupDevice::kSlots];
-    const uint64_t m = std::min(chunk, qb - q0);
+    const uint64_t q0 = starts[k], m = starts[k + 1] - q0;
     if (k >= GroupDevice::kSlots) CU(cudaStreamSynchronize(s.stream));  // the slot's input buffer is about to be rewritten
     PackedBatch b;
     if (int r = shipChunk(job, s, q0, m, &b, &h2d)) return r;
@@ -281,14 +308,15 @@ int locateShardWalk(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t 
     L.stats.launches += 1;
   }
   {  // hitOffsets[qa .. qb) (+ the final entry from the last shard)
+    // the walk windows below run on other streams: they must see the rebased offsets, but need not wait for the copy
+    CU(cudaEventRecord(D.rebased, s0.stream));
+    for (int i = 1; i < GroupDevice::kSlots; i++) CU(cudaStreamWaitEvent(D.slots[i].stream, D.rebased, 0));
     const uint64_t entries = shard + (lastShard ? 1 : 0);
     if (!job.hitPinned && (rc = s0.hOut.ensure(entries * 8))) return rc;
     if ((rc = copyOut(s0, s0.hOut, 0, job.hitOffsets + qa, job.hitPinned, dHit, entries * 8))) return rc;
     CU(cudaEventRecord(s0.done, s0.stream));
     s0.busy = true;
     d2h += entries * 8;
-    // the walk windows below run on other streams: they must see the rebased offsets
-    for (int i = 1; i < GroupDevice::kSlots; i++) CU(cudaStreamWaitEvent(D.slots[i].stream, s0.done, 0));
   }
   if (job.walk && D.total) {
     const uint64_t window = (uint64_t)g->windowHits;

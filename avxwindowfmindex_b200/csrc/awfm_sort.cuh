@@ -25,10 +25,13 @@ namespace awfm {
 
 constexpr int kSortThreads = 256;
 #ifndef AWFM_SORT_ITEMS
-#define AWFM_SORT_ITEMS 12
+#define AWFM_SORT_ITEMS 8
 #endif
 constexpr int kSortItems = AWFM_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;
+#ifndef AWFM_SORT_MIN_CTAS
+#define AWFM_SORT_MIN_CTAS 5
+#endif
 constexpr int kSortMaxDigitBits = 8;
 constexpr int kSortBins = 1 << kSortMaxDigitBits;
 
@@ -126,10 +129,16 @@ static __global__ void __launch_bounds__(kSortThreads)
     if (tile >= totalTiles) break;
     uint32_t a, first, count;
     sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
+    uint32_t key[kSortItems];  // every load is issued before the first shared atomic waits on one
 #pragma unroll
     for (int it = 0; it < kSortItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
-      if (i < count) atomicAdd(&bins[(__ldg(keys + first + i) >> shiftB) & maskB], 1u);
+      key[it] = __ldg(keys + first + min(i, count - 1u));
+    }
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) atomicAdd(&bins[(key[it] >> shiftB) & maskB], 1u);
     }
     __syncthreads();
     const uint32_t c = bins[threadIdx.x];
@@ -140,7 +149,7 @@ static __global__ void __launch_bounds__(kSortThreads)
 // One bucket pass.  SECOND = false: tiles in input order, digit A, cursors ctrl->cursorA.  SECOND = true: tiles inside
 // the bucket regions of pass A's output, digit B, cursors cursorB[a << dB | digit].
 template <bool SECOND>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
     sortPass(const uint32_t *__restrict__ keysIn, const uint64_t *__restrict__ valsIn, uint32_t *__restrict__ keysOut,
              uint64_t *__restrict__ valsOut, uint32_t numPairs, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ cursorB,
              uint32_t dA, uint32_t dB, uint32_t shift) {

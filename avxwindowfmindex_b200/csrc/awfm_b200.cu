@@ -746,6 +746,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   uint32_t sortLaunches = 0;
   if (ownSort) {
     int grid = 0;
+    if (kSortSmemBytes + 6 * 1024 > 48 * 1024) {  // more than the default dynamic shared memory: opt in (once per device is enough)
+      CU(cudaFuncSetAttribute(sortPass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
+      CU(cudaFuncSetAttribute(sortPass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
+    }
     if (int r = gridFor(c, sortPass<false>, kSortThreads, &grid, kSortSmemBytes)) return r;
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSortTile - 1) / kSortTile);
     sortBases<0><<<1, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);

@@ -25,12 +25,12 @@ namespace awfm {
 
 constexpr int kSortThreads = 256;
 #ifndef AWFM_SORT_ITEMS
-#define AWFM_SORT_ITEMS 8
+#define AWFM_SORT_ITEMS 12
 #endif
 constexpr int kSortItems = AWFM_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;
 #ifndef AWFM_SORT_MIN_CTAS
-#define AWFM_SORT_MIN_CTAS 5
+#define AWFM_SORT_MIN_CTAS 4
 #endif
 constexpr int kSortMaxDigitBits = 8;
 constexpr int kSortBins = 1 << kSortMaxDigitBits;

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <thread>
@@ -223,10 +224,17 @@ int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, u
   const std::vector<uint64_t> starts = chunkStarts(qa, qb, (uint64_t)g->chunkQueries);
   uint64_t h2d = 0, d2h = 0;
   int rc = AWFM_GPU_OK;
+  const bool verbose = getenv("AWFM_GPU_VERBOSE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   for (size_t k = 0; k + 1 < starts.size() && rc == AWFM_GPU_OK; k++) {
     PackSlot &s = D.slots[k % GroupDevice::kSlots];
     const uint64_t q0 = starts[k], m = starts[k + 1] - q0;
+    const double tw = ms();
     if ((rc = finishSlot(s))) break;
+    if (verbose)
+      fprintf(stderr, "[awfm_gpu] packed count dev %d chunk %zu (%llu queries): waited for its slot %.3f -> %.3f ms\n",
+              c->device, k, (unsigned long long)m, tw, ms());
     PackedBatch b;
     if ((rc = shipChunk(job, s, q0, m, &b, &h2d))) break;
     if ((rc = s.dCounts.ensure(m * 4))) break;
@@ -240,11 +248,13 @@ int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, u
     }
     s.busy = true;
     d2h += m * 4;
+    if (verbose) fprintf(stderr, "[awfm_gpu] packed count dev %d chunk %zu enqueued at %.3f ms\n", c->device, k, ms());
   }
   for (auto &s : D.slots) {  // drain (also on errors: never leave a DMA into the caller's memory in flight)
     const int r = finishSlot(s);
     if (rc == AWFM_GPU_OK) rc = r;
     if (r) cudaStreamSynchronize(s.stream), s.busy = false, s.pending.clear();
+    if (verbose) fprintf(stderr, "[awfm_gpu] packed count dev %d: a slot drained at %.3f ms\n", c->device, ms());
   }
   L.stats.h2dBytes = h2d;
   L.stats.d2hBytes = d2h;

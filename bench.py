@@ -890,6 +890,42 @@ def leg_cfg5(env):
     return out
 
 
+def leg_hostlink(env):
+    """What the box's host<->device links deliver with all N GPUs copying at once from / to page-locked memory: H2D
+    alone, D2H alone, both directions together (aggregate GB/s, max-over-ranks time).  The end-to-end numbers are bound
+    by these: a packed count query costs 5 B in and 4 B out."""
+    torch = env.torch
+    nbytes = 1 << 28
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_in.fill_(1)
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out.fill_(2)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
+    s1, s2 = torch.cuda.Stream(device=env.dev), torch.cuda.Stream(device=env.dev)
+    out = {}
+    for name in ("h2d", "d2h", "both"):
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            env.cpu_barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                if name in ("h2d", "both"):
+                    with torch.cuda.stream(s1):
+                        d_a.copy_(h_in, non_blocking=True)
+                if name in ("d2h", "both"):
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_b, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = env.max_over_ranks(time.perf_counter() - t0)
+            best = max(best, 4 * nbytes * env.world * (2 if name == "both" else 1) / dt / 1e9)
+        out[name + "_GBps"] = best
+    out["what"] = (f"aggregate over {env.world} GPU(s) copying at once, 4 x 256 MiB per direction and GPU, page-locked host "
+                   "memory, best of 3; `both` counts the bytes of both directions")
+    return out
+
+
 def leg_fanout(env, arrays, h_bits_rank0, want_counts_rank0):
     """N>1, rank 0 alone (the other ranks wait): ONE process drives all N GPUs through the library's own fan-out
     (awfm_gpu_group_create over all devices).  N x 100 M 2-bit packed 20-mers in page-locked host memory,
@@ -1225,6 +1261,13 @@ def run_ours(args):
             ha.close()
         pout.close()
         group.close()
+
+    if e2e_packed is not None:
+        link = leg_hostlink(env)
+        result["host_link"] = link
+        bytes_per_step = world * (e2e_packed["h2d_bytes_per_step"] + e2e_packed["d2h_bytes_per_step"])
+        e2e_packed["host_link_GBps"] = bytes_per_step / (e2e_packed["ms_per_step"] * 1e-3) / 1e9
+        e2e_packed["frac_of_host_link_both_directions"] = e2e_packed["host_link_GBps"] / link["both_GBps"]
 
     # ---- cpu baseline (rank 0, N=1): the unmodified reference on the host cores, bounded sample ----
     cpu = None

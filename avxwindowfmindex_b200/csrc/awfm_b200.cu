@@ -468,6 +468,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_sort_bits" && value >= 0 && value <= 32) c->sweepSortBits = (int)value;
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
+  else if (k == "sweep_record12" && (value == 0 || value == 1)) c->sweepRecord12 = (int)value;
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
@@ -795,31 +796,37 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     r.cap = w.cap;
     return r;
   };
-  auto launchPass = [&](auto first, auto items, uint32_t pass) -> int {
+  // 12-byte records (nucleotide, at most 8 letters left of the seed table's k-mer): see sweepStep
+  const bool rec12 = !AMINO && steps <= 8 && c->sweepRecord12;
+  auto launchPass = [&](auto first, auto items, auto small, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
-    auto kf = sweepStep<FIRST, ITEMS, AMINO>;
+    constexpr bool REC12 = decltype(small)::value && !AMINO;
+    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12>;
     int grid = 0;
     if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
     const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
-                                         steps, localBits, dCounts, dRanges);
+                                         steps, localBits, dCounts, dRanges, w.irregularIds, irregularCount);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
-                                         gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges);
+                                         gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges, w.irregularIds, irregularCount);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   };
+  auto launchPassRec = [&](auto first, auto items, uint32_t pass) -> int {
+    return rec12 ? launchPass(first, items, std::true_type(), pass) : launchPass(first, items, std::false_type(), pass);
+  };
   auto launchPassItems = [&](auto first, uint32_t pass) -> int {
     switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
-      case 1: return launchPass(first, std::integral_constant<int, 1>(), pass);
-      case 2: return launchPass(first, std::integral_constant<int, 2>(), pass);
+      case 1: return launchPassRec(first, std::integral_constant<int, 1>(), pass);
+      case 2: return launchPassRec(first, std::integral_constant<int, 2>(), pass);
 #if AWFM_SWEEP_THREADS <= 256  // 8 records per thread of a 512-thread CTA would need more than 48 KB of static shared memory
-      case 8: return launchPass(first, std::integral_constant<int, 8>(), pass);
+      case 8: return launchPassRec(first, std::integral_constant<int, 8>(), pass);
 #endif
-      default: return launchPass(first, std::integral_constant<int, 4>(), pass);
+      default: return launchPassRec(first, std::integral_constant<int, 4>(), pass);
     }
   };
   if (int r = launchPassItems(std::true_type(), 0)) return r;
@@ -828,15 +835,18 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     if (int r = launchPassItems(std::false_type(), pass)) return r;
     mark();
   }
-  if (format == AWFM_QUERY_ASCII) {  // (the 2-bit format cannot express an irregular query)
+  if (format == AWFM_QUERY_ASCII) {
     sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
+    CU(cudaGetLastError());
+  } else if (rec12) {  // the 2-bit format has no irregular letters, but a seed range may be too wide for 12-byte records
+    sweepIrregularBits<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
     CU(cudaGetLastError());
   }
   mark();
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
   w.lastSteps = steps, w.lastBuckets = AMINO ? 20 : 4, w.lastQueries = n;
-  L.stats.launches += 2 + (format == AWFM_QUERY_ASCII ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
+  L.stats.launches += 2 + ((format == AWFM_QUERY_ASCII || rec12) ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
   return AWFM_GPU_OK;
 }
 

@@ -357,12 +357,18 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
   return super + rel + __popc(lo) + __popc(hi);
 }
 
-template <bool FIRST, int kSweepItems, bool AMINO = false>
+// REC12 (nucleotide, at most 8 letters left of the seed): live records travel as 12 bytes instead of 16 —
+// {sp, id} (8 B) in the first cap*8 bytes of a double-ended array, {range width : 16 | remaining letters : 16} (4 B)
+// behind them.  A range can only narrow from step to step, so the 16-bit width is checked once: a query whose SEED
+// range is wider than 65534 goes to the irregular list (sweepIrregular answers it with the generic per-query search).
+template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false>
 __global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
-              uint4 *__restrict__ ranges /* or nullptr: every query's final (sp, ep) as the reference leaves it */) {
+              uint4 *__restrict__ ranges /* or nullptr: every query's final (sp, ep) as the reference leaves it */,
+              uint32_t *__restrict__ irregularIds, uint32_t *__restrict__ irregularCount) {
+  static_assert(!(REC12 && AMINO), "12-byte records are a nucleotide format");
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   constexpr uint32_t kLetterMask = (1u << LB) - 1u;
@@ -452,11 +458,22 @@ __global__ void __launch_bounds__(kSweepThreads)
         const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
         const bool odd = ge1 != ge2 || ge3;  // bucket 1 or 3
         const uint32_t r = i - first;
-        const uint4 rec = __ldg((ge2 ? in1 : in0) + (odd ? inLast - r : r));
-        sp[it] = rec.x;
-        ep[it] = rec.x + rec.y;
-        id[it] = rec.z;
-        rest[it] = rec.w;
+        const uint32_t slot = odd ? inLast - r : r;
+        if constexpr (REC12) {
+          const uint4 *base = ge2 ? in1 : in0;
+          const uint2 a = __ldg(reinterpret_cast<const uint2 *>(base) + slot);
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint2 *>(base) + in.cap) + slot);
+          sp[it] = a.x;
+          ep[it] = a.x + (w & 0xFFFFu);
+          id[it] = a.y;
+          rest[it] = w >> 16;
+        } else {
+          const uint4 rec = __ldg((ge2 ? in1 : in0) + slot);
+          sp[it] = rec.x;
+          ep[it] = rec.x + rec.y;
+          id[it] = rec.z;
+          rest[it] = rec.w;
+        }
       }
       if (want >= total) id[it] = kSweepNoId;
     }
@@ -526,6 +543,10 @@ __global__ void __launch_bounds__(kSweepThreads)
         if (s64[it] > e64[it]) {  // empty seed range: count stays 0, the stored pair is the query's final range
           if (ranges && id[it] != kSweepNoId)
             ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
+          id[it] = kSweepNoId;
+        }
+        if (REC12 && id[it] != kSweepNoId && e64[it] - s64[it] >= 0xFFFFull) {  // width does not fit the 16-bit field
+          irregularIds[atomicAdd(irregularCount, 1u)] = id[it];
           id[it] = kSweepNoId;
         }
         if (id[it] != kSweepNoId) sp[it] = (uint32_t)s64[it], ep[it] = (uint32_t)e64[it];
@@ -617,7 +638,13 @@ __global__ void __launch_bounds__(kSweepThreads)
       if (b < NB) {
         const uint32_t r = bucketBase[b] + warpCount[it][warp][b] + rank[it];
         uint4 *dst = AMINO ? out.arr[b >> 1] : ((b & 2u) ? out1 : out0);
-        dst[(b & 1u) ? outLast - r : r] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
+        const uint32_t slot = (b & 1u) ? outLast - r : r;
+        if constexpr (REC12) {
+          reinterpret_cast<uint2 *>(dst)[slot] = make_uint2(sp[it], id[it]);
+          reinterpret_cast<uint32_t *>(reinterpret_cast<uint2 *>(dst) + out.cap)[slot] = (ep[it] - sp[it]) | (rest[it] << 16);
+        } else {
+          dst[slot] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
+        }
       }
     }
   }
@@ -644,6 +671,29 @@ __global__ void __launch_bounds__(256)
         break;
       }
       lfStep<1, AMINO>(ix, sp, ep, letter, 0u, 0xFFFFFFFFu);
+      next--;
+    }
+    counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
+    if (ranges) ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
+  }
+}
+
+// The same for the 2-bit packed format (AWFM_QUERY_2BIT): only reached by queries whose seed range is too wide for the
+// 12-byte records.  The query's letters are unpacked into letter indices and searched like any other query.
+static __global__ void __launch_bounds__(256)
+    sweepIrregularBits(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ packed, uint32_t len,
+                       const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
+                       uint32_t *__restrict__ counts, uint4 *__restrict__ ranges) {
+  const uint32_t n = *numIds, B = (len + 3u) >> 2;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = ids[i];
+    const uint8_t *src = packed + (uint64_t)q * B;
+    uint8_t letters[32];
+    for (uint32_t j = 0; j < len && j < 32u; j++) letters[j] = (__ldg(src + (j >> 2)) >> (2u * (j & 3u))) & 3u;
+    uint64_t sp, ep;
+    uint64_t next = openRange<false, true>(ix, letters, len, sp, ep);
+    while (next > 0 && sp <= ep) {
+      lfStep<1, false>(ix, sp, ep, letters[next - 1], 0u, 0xFFFFFFFFu);
       next--;
     }
     counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);

@@ -205,3 +205,36 @@ def test_own_bucket_passes_and_cub_order_alike(small_indexes, name):
                 assert np.array_equal(counts, o_counts), (name, length, num, own, bits, local)
                 assert np.array_equal(ranges, o_ranges), (name, length, num, own, bits, local)
     gpu.close()
+
+
+def test_twelve_byte_records_and_the_wide_range_escape(reference, tmp_path):
+    """Nucleotide batches with at most 8 letters left of the seed travel as 12-byte records with a 16-bit range width;
+    a query whose SEED range is wider than 65534 positions leaves the sweep for the generic per-query search.  With a
+    2-letter seed table over 1.2 Mbp every seed range is ~75 k wide, so every query takes the escape; with k = 6 only
+    some do.  ASCII and 2-bit packed input, against the oracle, with the 16-byte records as cross-check."""
+    from avxwindowfmindex_b200 import GpuGroup, abi, pack_queries_bits
+    from avxwindowfmindex_b200.search import QUERY_2BIT
+    rng = np.random.default_rng(5)
+    text = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 1_200_000)]
+    text[:400_000] = ord("A")  # a long run: the seed ranges of AAAAAA... are very wide
+    for k in (2, 6):
+        ptr = reference.create_index(text.tobytes(), str(tmp_path / f"wide{k}.awfmi"), abi.AwFmAlphabetDna, k, 16)
+        arrays = reference.arrays(ptr)
+        oracle = harness.Oracle(arrays)
+        gpu = GpuIndex(arrays)
+        group = GpuGroup(indexes=[gpu])
+        for length in (k, k + 1, k + 5, k + 8):
+            starts = rng.integers(0, len(text) - length, 6000)
+            letters = np.ascontiguousarray(text[starts[:, None] + np.arange(length)[None, :]].reshape(-1))
+            letters.reshape(-1, length)[::3] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (2000, length))]
+            o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
+            for rec12 in (1, 0):
+                gpu.set_tuning(sweep_min_queries=1, sweep_record12=rec12, sweep_profile=1)
+                counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+                assert gpu.sweep_stage_ms(), "the batch did not take the sweep path"
+                assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (k, length, rec12)
+                packed = pack_queries_bits(letters, length)
+                assert np.array_equal(group.count(packed, QUERY_2BIT, fixed_len=length), o_counts), (k, length, rec12, "2bit")
+        group.close()
+        gpu.close()
+        reference.dealloc_index(ptr)

@@ -130,7 +130,7 @@ struct awfm_gpu_ctx {
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
   int64_t sweepMaxBatch = 1ll << 27;
   int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
-  int sweepRecord12 = 1;  // 12-byte live records when the batch allows it (nucleotide, <= 8 letters left of the seed)
+  int sweepRecord12 = 0;  // 12-byte live records when the batch allows it (nucleotide, <= 8 letters left of the seed)
   int sweepOwnSort = 1;  // 1 = the hand-written stable radix passes (awfm_sort.cuh), 0 = CUB (cross-check)
   static constexpr int kLanes = 3;
   Lane lanes[kLanes];

@@ -361,11 +361,10 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // {sp, id} (8 B) in the first cap*8 bytes of a double-ended array, {range width : 16 | remaining letters : 16} (4 B)
 // behind them.  A range can only narrow from step to step, so the 16-bit width is checked once: a query whose SEED
 // range is wider than 65534 goes to the irregular list (sweepIrregular answers it with the generic per-query search).
-#ifndef AWFM_SWEEP_MIN_CTAS
-#define AWFM_SWEEP_MIN_CTAS 1
-#endif
+// (forcing more resident CTAs per SM through __launch_bounds__ was measured: 5, 6 and 8 CTAs spill and run 20-30 %
+// slower than the 64 registers / 4 CTAs the compiler picks on its own, profiles/r02_sweep_probe.jsonl)
 template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false>
-__global__ void __launch_bounds__(kSweepThreads, AWFM_SWEEP_MIN_CTAS)
+__global__ void __launch_bounds__(kSweepThreads)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,

@@ -44,9 +44,10 @@ def main():
         launches.append(d)
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv"] + extra))))
     mix, stalls, total_inst, total_samples = Counter(), [], 0, 0
-    if len(src) > 2:
-        h = src[1]
-        i_src, i_ex, i_smp = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
+    h = src[1] if len(src) > 2 else []
+    smp = next((c for c in h if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"), None)
+    if len(src) > 2 and smp and "Source" in h and "Instructions Executed" in h:
+        i_src, i_ex, i_smp = h.index("Source"), h.index("Instructions Executed"), h.index(smp)
         for r in src[2:]:
             if r and r[0] == "Kernel Name":
                 break

@@ -354,7 +354,13 @@ __device__ __forceinline__ AminoSweepSelector aminoSweepSelector(uint32_t codeCa
 __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t p, uint32_t letter,
                                                    const AminoSweepSelector &s) {
   const uint4 *line = ix.lines + (uint64_t)(p >> 6) * kAminoLineU4;
-  const uint4 v0 = __ldg(line), v1 = __ldg(line + 1);
+  uint4 v0, v1;
+  {  // b0..b3 of all 64 positions in one 256-bit request (see sweepRank)
+    uint64_t a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(line));
+    v0 = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+  }
   const uint2 b4 = __ldg(reinterpret_cast<const uint2 *>(line + 2));
   const uint32_t rel = __ldg(reinterpret_cast<const uint32_t *>(line) + kAminoRelWord + letter);
   const uint32_t super = (uint32_t)__ldg(ix.superC + (uint64_t)(p >> kSuperShift) * kAminoSuperStride + letter);

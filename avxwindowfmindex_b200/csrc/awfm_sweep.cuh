@@ -355,12 +355,16 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
                                                    const AminoSweepSelector &s) {
   const uint4 *line = ix.lines + (uint64_t)(p >> 6) * kAminoLineU4;
   uint4 v0, v1;
+#ifdef AWFM_AMINO_NO_LDG256
+  v0 = __ldg(line), v1 = __ldg(line + 1);
+#else
   {  // b0..b3 of all 64 positions in one 256-bit request (see sweepRank)
     uint64_t a, b, c, d;
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(line));
     v0 = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
     v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
   }
+#endif
   const uint2 b4 = __ldg(reinterpret_cast<const uint2 *>(line + 2));
   const uint32_t rel = __ldg(reinterpret_cast<const uint32_t *>(line) + kAminoRelWord + letter);
   const uint32_t super = (uint32_t)__ldg(ix.superC + (uint64_t)(p >> kSuperShift) * kAminoSuperStride + letter);
@@ -380,7 +384,7 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // (forcing more resident CTAs per SM through __launch_bounds__ was measured: 5, 6 and 8 CTAs spill and run 20-30 %
 // slower than the 64 registers / 4 CTAs the compiler picks on its own, profiles/r02_sweep_probe.jsonl)
 template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false>
-__global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 1)
+__global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
@@ -574,15 +578,14 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
     for (int it = 0; it < kSweepItems; it++)
       if (id[it] == kSweepNoId) sp[it] = 1, ep[it] = 0;  // disabled items rank position 0: a valid address
     // ---- stage B: pull the two sectors of every item towards L1 (no registers, no scoreboard held) ----
-    // Nucleotide: ONE prefetch per item — sp-1 and ep of a sorted query mostly share a 128-B line, and the pass is bound
-    // by the L1/LSU pipe (75 % busy, profiles/r02_ncu_sweep_kernels.json), so the second request costs more than it
-    // hides: 6.82 ms per 100 M 20-mers with one, 7.10 with two, 7.10 with none (profiles/r02_sweep_probe.jsonl).
+    // ONE prefetch per item — sp-1 and ep of a sorted query mostly share a 128-B line (or neighbouring ones), and the
+    // pass is bound by the L1/LSU pipe (75 % busy, profiles/r02_ncu_sweep_kernels.json), so the second request costs
+    // more than it hides: 100 M nucleotide 20-mers 6.82 ms with one, 7.10 with two, 7.10 with none; 50 M amino 8-mers
+    // 3.30 with one, 3.39 with two (profiles/r02_sweep_probe.jsonl).
     if (steps > 0) {
 #pragma unroll
-      for (int it = 0; it < kSweepItems; it++) {
+      for (int it = 0; it < kSweepItems; it++)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kLineU4));
-        if (AMINO) asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)(ep[it] >> 6) * kLineU4));
-      }
     }
     // ---- stage C: the LF steps (src/AwFmSearch.c:42-103) ----
 #pragma unroll

@@ -628,11 +628,12 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
     return false;
   }
   if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
-  // automatic: pays off once the batch puts about one query on every 128-B line of the index (measured break-even
-  // at 3.1 Gbp: 12 M queries, profiles/r01_sweep_probe.jsonl).  With a derived deep seed table most of the LF steps
-  // the sweep would stream for are gone already and the tile kernel is the faster of the two.
+  // automatic: pays off once the batch puts about one query on every second 128-B line of the index (measured
+  // break-even at 3.1 Gbp: 6 M queries for 16- and 20-mers alike, profiles/r02_sweep_probe.jsonl; round 1's slower
+  // sweep: 12 M).  With a derived deep seed table most of the LF steps the sweep would stream for are gone already and
+  // the tile kernel is the faster of the two.
   if (c->ix.deepSeedK && len >= c->ix.deepSeedK) return false;
-  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : 8));
+  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : 9));
 }
 
 static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {

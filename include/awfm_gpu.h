@@ -128,7 +128,7 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
  * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length batches of either alphabet, counts and ranges):
- * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per 128-B line of the index) queries and no
+ * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per two 128-B lines of the index) queries and no
  * derived deep seed table; n > 0 = batches of at least n queries; -1 = never), "sweep_sort_bits" (top bits of the seed
  * index the radix sort orders, default 32 = all but the low "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 =
  * automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items" /

@@ -633,7 +633,8 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
   // sweep: 12 M).  With a derived deep seed table most of the LF steps the sweep would stream for are gone already and
   // the tile kernel is the faster of the two.
   if (c->ix.deepSeedK && len >= c->ix.deepSeedK) return false;
-  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : 9));
+  // (with range output every query also pays a scattered 16-B store: the break-even stays where round 1 measured it)
+  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : dRanges ? 8 : 9));
 }
 
 static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {

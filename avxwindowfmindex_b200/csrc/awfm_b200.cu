@@ -675,7 +675,7 @@ static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
 
 template <bool AMINO>
 static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
-                           uint32_t *dCounts, uint4 *dRanges, cudaStream_t st) {
+                           uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
   SweepScratch &w = L.sweep;
   const uint32_t k = sweepSeedK(c, len), steps = len - k;
   const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
@@ -811,10 +811,11 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
-                                         steps, localBits, dCounts, dRanges, w.irregularIds, irregularCount);
+                                         steps, localBits, dCounts, dRanges, w.irregularIds, irregularCount, hitsOnly);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
-                                         gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges, w.irregularIds, irregularCount);
+                                         gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges, w.irregularIds, irregularCount,
+                                         hitsOnly);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   };
@@ -838,10 +839,12 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     mark();
   }
   if (format == AWFM_QUERY_ASCII) {
-    sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
+    sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges,
+                                                         hitsOnly);
     CU(cudaGetLastError());
   } else if (rec12) {  // the 2-bit format has no irregular letters, but a seed range may be too wide for 12-byte records
-    sweepIrregularBits<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges);
+    sweepIrregularBits<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges,
+                                                      hitsOnly);
     CU(cudaGetLastError());
   }
   mark();
@@ -855,7 +858,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
 // Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
 // slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
 static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
-                      uint32_t *dCounts, uint4 *dRanges, cudaStream_t st) {
+                      uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
   const bool amino = c->ix.amino != 0;
   const uint64_t maxBatch = amino ? std::min<int64_t>(c->sweepMaxBatch, 1ll << 26) : c->sweepMaxBatch;
   const uint64_t slice = std::min<uint64_t>(n, maxBatch & ~255ull);  // slices start 16-B aligned
@@ -864,8 +867,8 @@ static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_
   for (uint64_t first = 0; first < n; first += slice) {
     const uint64_t m = std::min(slice, n - first);
     uint4 *ranges = dRanges ? dRanges + first : nullptr;
-    const int r = amino ? sweepCountBatch<true>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, st)
-                        : sweepCountBatch<false>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, st);
+    const int r = amino ? sweepCountBatch<true>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, hitsOnly, st)
+                        : sweepCountBatch<false>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, hitsOnly, st);
     if (r) return r;
   }
   return AWFM_GPU_OK;
@@ -889,8 +892,10 @@ int awfm_count_device_impl(awfm_gpu_ctx *c, Lane &L, const PackedBatch &batch, u
   const uint8_t *dLetters = batch.data;
   uint32_t format = batch.format;
   const uint32_t fixedLen = batch.length;
+  // (ranges of hits only cost a store per HIT, not per query: the counts-only break-even applies)
+  const awfm_range *thresholdRanges = batch.rangesOfHitsOnly ? nullptr : dRanges;
   const bool directBits = format == AWFM_QUERY_2BIT && fixedLen <= 32 &&
-                          sweepEligible(c, dLetters, nullptr, fixedLen, n, dRanges);
+                          sweepEligible(c, dLetters, nullptr, fixedLen, n, thresholdRanges);
   const bool unpack = format != AWFM_QUERY_ASCII && !directBits;
   if (unpack) {
     CU(cudaStreamWaitEvent(st, L.unpackDone, 0));
@@ -905,10 +910,10 @@ int awfm_count_device_impl(awfm_gpu_ctx *c, Lane &L, const PackedBatch &batch, u
     dLetters = (const uint8_t *)L.dUnpacked.p;
     format = AWFM_QUERY_ASCII;
   }
-  QueryBatch qb{dLetters, batch.offsets, n, fixedLen};
+  QueryBatch qb{dLetters, batch.offsets, n, fixedLen, batch.rangesOfHitsOnly ? 1u : 0u};
   int r;
-  const bool sweep = directBits || sweepEligible(c, dLetters, batch.offsets, fixedLen, n, dRanges);
-  r = sweep ? sweepCount(c, L, dLetters, format, fixedLen, n, dCounts, (uint4 *)dRanges, st) : AWFM_GPU_OK;
+  const bool sweep = directBits || sweepEligible(c, dLetters, batch.offsets, fixedLen, n, thresholdRanges);
+  r = sweep ? sweepCount(c, L, dLetters, format, fixedLen, n, dCounts, (uint4 *)dRanges, batch.rangesOfHitsOnly, st) : AWFM_GPU_OK;
   if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
     L.sweep.stagesRecorded = 0;
     if (format != AWFM_QUERY_ASCII) return awfm_fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");
@@ -977,8 +982,8 @@ extern "C" int awfm_gpu_count_device_format(awfm_gpu_ctx *c, const void *dQuerie
   return awfm_count_device_impl(c, L, b, dCounts, dRanges, (cudaStream_t)stream);
 }
 
-// hitOffsets[q] = base + sum of the (u32-truncated) range lengths of the queries before q; hitOffsets[n] = base + total
-int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range *dRanges, uint64_t n,
+// hitOffsets[q] = base + sum of the (u32-truncated) hit-list lengths of the queries before q; hitOffsets[n] = base + total
+int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const void *lengthSource, bool fromCounts, uint64_t n,
                    uint64_t *dHitOffsets, uint64_t base, cudaStream_t st) {
   (void)c;
   const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
@@ -992,10 +997,17 @@ int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range
     sc.scanTempBytes = need + need / 4;
   }
   uint64_t *tileSums = (uint64_t *)sc.scanTemp;
-  if (tiles) scanTileSums<<<(unsigned)tiles, 256, 0, st>>>((const uint4 *)dRanges, n, tileSums);
+  if (tiles) {
+    if (fromCounts) scanTileSums<true><<<(unsigned)tiles, 256, 0, st>>>(lengthSource, n, tileSums);
+    else scanTileSums<false><<<(unsigned)tiles, 256, 0, st>>>(lengthSource, n, tileSums);
+  }
   scanTileBases<<<1, 256, 0, st>>>(tileSums, tiles, base);
-  if (tiles) scanTileOffsets<<<(unsigned)tiles, 256, 0, st>>>((const uint4 *)dRanges, n, tileSums, dHitOffsets);
-  else CU(cudaMemcpyAsync(dHitOffsets, tileSums, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  if (tiles) {
+    if (fromCounts) scanTileOffsets<true><<<(unsigned)tiles, 256, 0, st>>>(lengthSource, n, tileSums, dHitOffsets);
+    else scanTileOffsets<false><<<(unsigned)tiles, 256, 0, st>>>(lengthSource, n, tileSums, dHitOffsets);
+  } else {
+    CU(cudaMemcpyAsync(dHitOffsets, tileSums, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  }
   CU(cudaGetLastError());
   L.stats.launches += tiles ? 3 : 1;
   return AWFM_GPU_OK;
@@ -1005,7 +1017,7 @@ extern "C" int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *c, const awfm_range *dR
                                            uint64_t *dHitOffsets, void *stream) {
   if (!c || !dHitOffsets || (n && !dRanges)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
   if (int r = awfm_set_device(c)) return r;
-  return awfm_scan_impl(c, c->lanes[0], c->lanes[0].sc, dRanges, n, dHitOffsets, 0, (cudaStream_t)stream);
+  return awfm_scan_impl(c, c->lanes[0], c->lanes[0].sc, dRanges, false, n, dHitOffsets, 0, (cudaStream_t)stream);
 }
 
 // Backtrace walk of the flat hit indices [hb, he) (in the numbering of dHitOffsets) into dPos[h - hb].
@@ -1317,8 +1329,11 @@ extern "C" int awfm_gpu_locate_host(awfm_gpu_ctx *c, const uint8_t *letters, con
   PackedBatch b;
   b.data = (const uint8_t *)L.dLetters.p, b.offsets = offsets ? (const uint64_t *)L.dOffsets.p : nullptr;
   b.length = fixedLen, b.numQueries = n;
+  b.rangesOfHitsOnly = ranges == nullptr;  // the walk only needs the ranges of queries with hits
   if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)L.dCounts.p, (awfm_range *)L.dRanges.p, st)) return r;
-  if (int r = awfm_scan_impl(c, L, L.sc, (const awfm_range *)L.dRanges.p, n, (uint64_t *)L.dHits.p, 0, st)) return r;
+  if (int r = awfm_scan_impl(c, L, L.sc, b.rangesOfHitsOnly ? L.dCounts.p : L.dRanges.p, b.rangesOfHitsOnly, n,
+                             (uint64_t *)L.dHits.p, 0, st))
+    return r;
   CU(cudaMemcpyAsync(hitOffsets, L.dHits.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (ranges) CU(cudaMemcpyAsync(ranges, L.dRanges.p, n * 16, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1548,6 +1563,7 @@ static int submitCount(awfm_gpu_ctx *c, Lane &L, PipeSlot &s, const Packed &pk, 
   if (!fixed) CU(cudaMemcpyAsync(s.dOffsets, s.hOffsets, (s.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
   PackedBatch b;
   b.data = s.dLetters, b.offsets = fixed ? nullptr : s.dOffsets, b.length = pk.uniformLen, b.numQueries = s.n;
+  b.rangesOfHitsOnly = wantRanges;  // the locate engine scans the counts and reads the ranges of queries with hits only
   if (int r = awfm_count_device_impl(c, L, b, s.dCounts, wantRanges ? (awfm_range *)s.dRanges : nullptr, s.stream))
     return r;
   L.stats.h2dBytes += pk.letterBytes + (fixed ? 0 : (s.n + 1) * 8);

@@ -164,6 +164,8 @@ struct PackedBatch {
   uint32_t format = AWFM_QUERY_ASCII;
   uint32_t length = 0;              // letters per query (fixed-length batches)
   uint64_t numQueries = 0;
+  bool rangesOfHitsOnly = false;    // locate pipelines: dRanges is only written for queries with hits (the hit offsets
+                                    // are then scanned from dCounts, awfm_scan_impl with fromCounts)
 };
 static inline uint32_t awfm_format_bits(uint32_t format) {
   return format == AWFM_QUERY_2BIT ? 2u : format == AWFM_QUERY_5BIT ? 5u : 8u;
@@ -175,7 +177,9 @@ static inline uint64_t awfm_query_bytes(uint32_t format, uint32_t length) {
 // ---- device-side building blocks used by both translation units (all asynchronous on `st`) ----
 int awfm_count_device_impl(awfm_gpu_ctx *c, Lane &L, const PackedBatch &batch, uint32_t *dCounts, awfm_range *dRanges,
                            cudaStream_t st);
-int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range *dRanges, uint64_t n,
+// hit offsets = exclusive scan of the hit-list lengths, taken from the final ranges (lengthSource = awfm_range[n],
+// fromCounts = false) or from the u32 counts of the same search (uint32_t[n], fromCounts = true)
+int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const void *lengthSource, bool fromCounts, uint64_t n,
                    uint64_t *dHitOffsets, uint64_t base, cudaStream_t st);
 int awfm_locate_device_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const awfm_range *dRanges,
                             const uint64_t *dHitOffsets, uint64_t n, uint64_t hb, uint64_t he, uint64_t *dPos,

@@ -9,6 +9,7 @@ struct QueryBatch {
   const uint64_t *offsets;  // numQueries+1 or nullptr (fixed length)
   uint64_t numQueries;
   uint32_t fixedLen;
+  uint32_t rangesOfHitsOnly;  // != 0: `ranges` is only written for queries with a non-empty final range (locate)
 };
 
 __device__ __forceinline__ void queryExtent(const QueryBatch &qb, uint64_t q, uint64_t &off, uint64_t &len) {
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(256)
     }
     if (sub == 0) {
       counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);  // src/AwFmIndexStruct.c:126-130, u32 store :187-190
-      if (ranges) ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
+      if (ranges && (sp <= ep || !qb.rangesOfHitsOnly))
+        ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
     }
   }
 }
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(256)
       }
       if (sub == 0) {
         counts[q0 + t] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
-        if (ranges)
+        if (ranges && (sp <= ep || !qb.rangesOfHitsOnly))
           ranges[q0 + t] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
       }
     }
@@ -263,8 +265,10 @@ static __global__ void __launch_bounds__(256)
     if (q < numQueries) {
       a = __ldg(hitOffsets + q);
       b = __ldg(hitOffsets + q + 1);
-      const uint4 r = __ldg(ranges + q);
-      sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
+      if (b > a) {  // (with ranges of hits only, the entry of a query without hits was never written)
+        const uint4 r = __ldg(ranges + q);
+        sp = (uint64_t)r.x | ((uint64_t)r.y << 32);
+      }
     }
     const bool live = b > a && b > hitBegin && a < hitEnd;
     const uint64_t lo = max(a, hitBegin), hi = min(b, hitEnd);
@@ -617,6 +621,13 @@ __device__ __forceinline__ uint64_t rangeLengthOf(const uint4 r) {
   const uint64_t sp = (uint64_t)r.x | ((uint64_t)r.y << 32), ep = (uint64_t)r.z | ((uint64_t)r.w << 32);
   return (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
 }
+// length of query q's hit list: from its final range, or from the u32 count the search stored (the same number, a
+// quarter of the bytes; what the locate pipelines scan)
+template <bool FROM_COUNTS>
+__device__ __forceinline__ uint64_t hitsOfQuery(const void *__restrict__ src, uint64_t q) {
+  if (FROM_COUNTS) return __ldg(reinterpret_cast<const uint32_t *>(src) + q);
+  return rangeLengthOf(__ldg(reinterpret_cast<const uint4 *>(src) + q));
+}
 __device__ __forceinline__ uint64_t blockSum256(uint64_t v, uint64_t *warpSums /* [8] shared */) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
@@ -628,15 +639,16 @@ __device__ __forceinline__ uint64_t blockSum256(uint64_t v, uint64_t *warpSums /
   __syncthreads();
   return total;
 }
-static __global__ void __launch_bounds__(256)
-    scanTileSums(const uint4 *__restrict__ ranges, uint64_t n, uint64_t *__restrict__ tileSums) {
+template <bool FROM_COUNTS>
+__global__ void __launch_bounds__(256)
+    scanTileSums(const void *__restrict__ ranges, uint64_t n, uint64_t *__restrict__ tileSums) {
   __shared__ uint64_t warpSums[8];
   const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile;
   uint64_t mine = 0;
 #pragma unroll
   for (int it = 0; it < kScanTile / 256; it++) {
     const uint64_t q = q0 + it * 256 + threadIdx.x;
-    if (q < n) mine += rangeLengthOf(__ldg(ranges + q));
+    if (q < n) mine += hitsOfQuery<FROM_COUNTS>(ranges, q);
   }
   const uint64_t total = blockSum256(mine, warpSums);
   if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
@@ -667,8 +679,9 @@ static __global__ void __launch_bounds__(256) scanTileBases(uint64_t *__restrict
   }
   if (threadIdx.x == 0) tileSums[numTiles] = carry;
 }
-static __global__ void __launch_bounds__(256)
-    scanTileOffsets(const uint4 *__restrict__ ranges, uint64_t n, const uint64_t *__restrict__ tileBases,
+template <bool FROM_COUNTS>
+__global__ void __launch_bounds__(256)
+    scanTileOffsets(const void *__restrict__ ranges, uint64_t n, const uint64_t *__restrict__ tileBases,
                     uint64_t *__restrict__ hitOffsets) {
   __shared__ uint64_t warpSums[8];
   const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile;
@@ -678,7 +691,7 @@ static __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int j = 0; j < kScanTile / 256; j++) {
     const uint64_t q = q0 + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
-    len[j] = q < n ? rangeLengthOf(__ldg(ranges + q)) : 0;
+    len[j] = q < n ? hitsOfQuery<FROM_COUNTS>(ranges, q) : 0;
     mine += len[j];
   }
   uint64_t incl = mine;

@@ -47,7 +47,7 @@ struct GroupDevice {
   bool owned = false, ready = false;
   static constexpr int kSlots = 3;
   PackSlot slots[kSlots];
-  GrowBuf dRanges, dHit;  // locate: the shard's ranges and hit offsets stay on the device between the two phases
+  GrowBuf dRanges, dHit, dCounts;  // locate: the shard's ranges, counts and hit offsets stay on the device between the two phases
   uint64_t *hTotal = nullptr;  // page-locked
   cudaEvent_t rebased = nullptr;  // locate phase B: the shard's hit offsets carry their global base
   uint64_t total = 0, base = 0;
@@ -97,6 +97,7 @@ void releaseDevice(GroupDevice &D) {
   }
   D.dRanges.release();
   D.dHit.release();
+  D.dCounts.release();
   if (D.hTotal) cudaFreeHost(D.hTotal);
   D.hTotal = nullptr;
   if (D.rebased) cudaEventDestroy(D.rebased);
@@ -275,6 +276,7 @@ int locateShardRanges(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_
   if (shard == 0) return AWFM_GPU_OK;
   if (int r = D.dRanges.ensure(shard * 16)) return r;
   if (int r = D.dHit.ensure((shard + 1) * 8)) return r;
+  if (int r = D.dCounts.ensure(shard * 4)) return r;
   const std::vector<uint64_t> starts = chunkStarts(qa, qb, (uint64_t)g->chunkQueries);
   uint64_t h2d = 0;
   for (size_t k = 0; k + 1 < starts.size(); k++) {
@@ -283,13 +285,13 @@ int locateShardRanges(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_
     if (k >= GroupDevice::kSlots) CU(cudaStreamSynchronize(s.stream));  // the slot's input buffer is about to be rewritten
     PackedBatch b;
     if (int r = shipChunk(job, s, q0, m, &b, &h2d)) return r;
-    if (int r = s.dCounts.ensure(m * 4)) return r;
-    if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)s.dCounts.p, (awfm_range *)D.dRanges.p + (q0 - qa), s.stream))
+    b.rangesOfHitsOnly = true;  // the hit offsets are scanned from the counts; the walk reads the ranges of hits only
+    if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)D.dCounts.p + (q0 - qa), (awfm_range *)D.dRanges.p + (q0 - qa), s.stream))
       return r;
   }
   for (auto &s : D.slots) CU(cudaStreamSynchronize(s.stream));
   PackSlot &s0 = D.slots[0];
-  if (int r = awfm_scan_impl(c, L, s0.sc, (const awfm_range *)D.dRanges.p, shard, (uint64_t *)D.dHit.p, 0, s0.stream)) return r;
+  if (int r = awfm_scan_impl(c, L, s0.sc, D.dCounts.p, true, shard, (uint64_t *)D.dHit.p, 0, s0.stream)) return r;
   CU(cudaMemcpyAsync(D.hTotal, (uint64_t *)D.dHit.p + shard, 8, cudaMemcpyDeviceToHost, s0.stream));
   CU(cudaStreamSynchronize(s0.stream));
   D.total = *D.hTotal;

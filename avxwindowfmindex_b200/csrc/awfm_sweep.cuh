@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
               uint4 *__restrict__ ranges /* or nullptr: every query's final (sp, ep) as the reference leaves it */,
-              uint32_t *__restrict__ irregularIds, uint32_t *__restrict__ irregularCount) {
+              uint32_t *__restrict__ irregularIds, uint32_t *__restrict__ irregularCount,
+              bool rangesOfHitsOnly /* ranges only of queries whose final range is non-empty (locate) */) {
   static_assert(!(REC12 && AMINO), "12-byte records are a nucleotide format");
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++) {
         if (s64[it] > e64[it]) {  // empty seed range: count stays 0, the stored pair is the query's final range
-          if (ranges && id[it] != kSweepNoId)
+          if (ranges && !rangesOfHitsOnly && id[it] != kSweepNoId)
             ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
           id[it] = kSweepNoId;
         }
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
         rest[it] >>= LB;
         if (valid && nep == nsp - 1u) {  // ep == sp - 1 <=> empty: the search stops here (src/AwFmParallelSearch.c:279-311)
           valid = false;
-          if (ranges) ranges[id[it]] = make_uint4(nsp, 0u, nep, nep == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u);
+          if (ranges && !rangesOfHitsOnly) ranges[id[it]] = make_uint4(nsp, 0u, nep, nep == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u);
         }
       }
       bucket[it] = NB;  // no output
@@ -680,7 +681,7 @@ template <bool AMINO>
 __global__ void __launch_bounds__(256)
     sweepIrregular(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ letters, uint32_t len,
                    const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
-                   uint32_t *__restrict__ counts, uint4 *__restrict__ ranges) {
+                   uint32_t *__restrict__ counts, uint4 *__restrict__ ranges, bool rangesOfHitsOnly) {
   const uint32_t n = *numIds;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t q = ids[i];
@@ -698,7 +699,8 @@ __global__ void __launch_bounds__(256)
       next--;
     }
     counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
-    if (ranges) ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
+    if (ranges && (sp <= ep || !rangesOfHitsOnly))
+      ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
   }
 }
 
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(256)
 static __global__ void __launch_bounds__(256)
     sweepIrregularBits(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ packed, uint32_t len,
                        const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
-                       uint32_t *__restrict__ counts, uint4 *__restrict__ ranges) {
+                       uint32_t *__restrict__ counts, uint4 *__restrict__ ranges, bool rangesOfHitsOnly) {
   const uint32_t n = *numIds, B = (len + 3u) >> 2;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t q = ids[i];
@@ -721,7 +723,8 @@ static __global__ void __launch_bounds__(256)
       next--;
     }
     counts[q] = (uint32_t)(sp <= ep ? ep - sp + 1 : 0);
-    if (ranges) ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
+    if (ranges && (sp <= ep || !rangesOfHitsOnly))
+      ranges[q] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
   }
 }
 

@@ -163,13 +163,19 @@ class GpuIndex:
             offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         hit_offsets = np.zeros(n + 1, dtype=np.uint64)
         ranges = np.zeros((n, 2), dtype=np.uint64) if want_ranges else None
-        capi.check(self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
-                                                 _ptr(hit_offsets), None, 0, _ptr(ranges)))
+        # one call when the hits fit a generous first guess (the C-ABI fills hitOffsets before it checks the capacity),
+        # a second one with the exact size otherwise
+        guess = max(4 * n, 1 << 12)
+        positions = np.zeros(guess, dtype=np.uint64)
+        rc = self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n, _ptr(hit_offsets),
+                                           _ptr(positions), guess, _ptr(ranges))
         total = int(hit_offsets[n]) if n else 0
-        positions = np.zeros(total, dtype=np.uint64)
-        if total:
-            capi.check(self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
-                                                     _ptr(hit_offsets), _ptr(positions), total, _ptr(ranges)))
+        if rc != 0 and total > guess:
+            positions = np.zeros(total, dtype=np.uint64)
+            rc = self.lib.awfm_gpu_locate_host(self._ctx, _ptr(letters), _ptr(offsets), fixed_len, n,
+                                               _ptr(hit_offsets), _ptr(positions), total, _ptr(ranges))
+        capi.check(rc)
+        positions = positions[:total].copy() if total < len(positions) else positions
         return (hit_offsets, positions, ranges) if want_ranges else (hit_offsets, positions)
 
     # ---- packed batch, device buffers (raw device pointers, e.g. torch tensors' data_ptr()) ----

@@ -20,7 +20,7 @@ GPU_SYMBOLS = [
     "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
     "awfm_gpu_ctx_create_from_file", "awfm_gpu_ctx_set_sequences", "awfm_gpu_ctx_extend_seed_table",
     "awfm_gpu_ctx_densify_suffix_array", "awfm_gpu_map_positions_device", "awfm_gpu_map_positions_host",
-    "awfm_gpu_ctx_sweep_stage_ms", "awfm_gpu_ctx_sweep_live", "awfm_gpu_count_device_format",
+    "awfm_gpu_ctx_sweep_stage_ms", "awfm_gpu_ctx_sweep_live", "awfm_gpu_count_device_format", "awfm_gpu_locate_prepare_device",
     "awfm_gpu_group_create", "awfm_gpu_group_create_from_contexts", "awfm_gpu_group_destroy", "awfm_gpu_group_size",
     "awfm_gpu_group_context", "awfm_gpu_group_set_sequences", "awfm_gpu_group_set_tuning", "awfm_gpu_group_get_stats",
     "awfm_gpu_group_count", "awfm_gpu_group_locate", "awfm_gpu_group_search_list_count",
@@ -103,6 +103,7 @@ def load():
     lib.awfm_gpu_map_positions_host.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]
     lib.awfm_gpu_ctx_sweep_live.argtypes = [vp, C.POINTER(u64), C.c_int, C.POINTER(u64)]
     lib.awfm_gpu_count_device_format.argtypes = [vp, vp, u32, vp, u32, u64, vp, vp, vp]
+    lib.awfm_gpu_locate_prepare_device.argtypes = [vp, vp, u32, vp, u32, u64, vp, vp, vp, vp]
     lib.awfm_gpu_group_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(abi.awfm_index_view)]
     lib.awfm_gpu_group_create_from_contexts.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int]
     lib.awfm_gpu_group_destroy.argtypes = [vp]

@@ -1013,6 +1013,23 @@ int awfm_scan_impl(awfm_gpu_ctx *c, Lane &L, LocateScratch &sc, const void *leng
   return AWFM_GPU_OK;
 }
 
+// The front end of a device-resident locate in one call: search, ranges of the queries WITH hits only, hit offsets
+// scanned from the u32 counts (a quarter of the bytes of the ranges, and no scattered 16-B store per empty query).
+extern "C" int awfm_gpu_locate_prepare_device(awfm_gpu_ctx *c, const void *dQueries, uint32_t format,
+                                              const uint64_t *dOffsets, uint32_t fixedLen, uint64_t n, uint32_t *dCounts,
+                                              awfm_range *dRanges, uint64_t *dHitOffsets, void *stream) {
+  if (!c || !dCounts || !dRanges || !dHitOffsets || (n && !dQueries)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
+  if (int r = awfm_set_device(c)) return r;
+  Lane &L = c->lanes[0];
+  c->lastLane.store(0);
+  awfm_begin_call(L);
+  PackedBatch b;
+  b.data = (const uint8_t *)dQueries, b.offsets = dOffsets, b.format = format, b.length = fixedLen, b.numQueries = n;
+  b.rangesOfHitsOnly = true;
+  if (int r = awfm_count_device_impl(c, L, b, dCounts, dRanges, (cudaStream_t)stream)) return r;
+  return awfm_scan_impl(c, L, L.sc, dCounts, true, n, dHitOffsets, 0, (cudaStream_t)stream);
+}
+
 extern "C" int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *c, const awfm_range *dRanges, uint64_t n,
                                            uint64_t *dHitOffsets, void *stream) {
   if (!c || !dHitOffsets || (n && !dRanges)) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");

@@ -183,6 +183,11 @@ class GpuIndex:
         capi.check(self.lib.awfm_gpu_count_device(self._ctx, d_letters, d_offsets or None, fixed_len, n, d_counts,
                                                   d_ranges or None, stream or None))
 
+    def locate_prepare_device(self, d_queries, fmt, fixed_len, n, d_counts, d_ranges, d_hit_offsets, stream=0):
+        """search + hit offsets in one call; d_ranges is only written for queries with hits"""
+        capi.check(self.lib.awfm_gpu_locate_prepare_device(self._ctx, d_queries, fmt, None, fixed_len, n, d_counts,
+                                                           d_ranges, d_hit_offsets, stream or None))
+
     def scan_ranges_device(self, d_ranges, n, d_hit_offsets, stream=0):
         capi.check(self.lib.awfm_gpu_scan_ranges_device(self._ctx, d_ranges, n, d_hit_offsets, stream or None))
 

@@ -556,18 +556,25 @@ def locate_leg(env, gpu, arrays, d_lq, nl, Ll, label, reference_sample=1_000_000
     hits = int(d_lh[-1].item())
     d_lp = torch.zeros(max(hits, 1), dtype=torch.int64, device=env.dev)
 
+    def prepare():  # search + ranges of the queries with hits + hit offsets scanned from the counts
+        gpu.locate_prepare_device(d_lq.data_ptr(), 0, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), d_lh.data_ptr(), stream)
+
     def locate_all():
-        gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream)
-        gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream)
+        prepare()
         gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(), stream)
 
     ms_all = env.event_ms(locate_all)
-    ms_count = env.event_ms(lambda: gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream))
-    ms_scan = env.event_ms(lambda: gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream))
+    ms_prepare = env.event_ms(prepare)
     ms_walk = env.event_ms(lambda: gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(), stream))
+    # the same through the three separate calls with full range output (every query's final range, as the reference
+    # leaves it), for the record
+    ms_count = env.event_ms(lambda: gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream), reps=3)
+    ms_scan = env.event_ms(lambda: gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream), reps=3)
+    prepare()
     loc = {"workload": label, "queries": nl, "hits": hits, "locate_ms": ms_all, "located_hits_per_s": hits / ms_all * 1e3,
            "locate_queries_per_s": nl / ms_all * 1e3,
-           "stages_ms": {"count_with_ranges": ms_count, "scan": ms_scan, "expand+walk": ms_walk},
+           "stages_ms": {"search+ranges_of_hits+scan (awfm_gpu_locate_prepare_device)": ms_prepare, "expand+walk": ms_walk},
+           "separate_calls_ms": {"count_with_all_ranges": ms_count, "scan_of_ranges": ms_scan},
            "walk_ms": ms_walk, "walk_hits_per_s": hits / ms_walk * 1e3}
     o_hit = o_pos = None
     if arrays is not None:

@@ -189,6 +189,13 @@ int awfm_gpu_count_device_format(awfm_gpu_ctx *ctx, const void *dQueries, uint32
 /* dRanges (in) come from awfm_gpu_count_device; dHitOffsets (out, numQueries+1) is their exclusive scan. */
 int awfm_gpu_scan_ranges_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, uint64_t numQueries,
                                 uint64_t *dHitOffsets, void *stream);
+/* The front end of a device-resident locate in ONE call (what the locate pipelines of this library use themselves):
+ * the search, then dHitOffsets (numQueries+1) scanned from the u32 counts.  dRanges[q] is written ONLY for queries with
+ * dCounts[q] > 0 — enough for awfm_gpu_locate_device, and it spares a scattered 16-B store per query without hits and
+ * three quarters of the scan's reads. */
+int awfm_gpu_locate_prepare_device(awfm_gpu_ctx *ctx, const void *dQueries, uint32_t format, const uint64_t *dOffsets,
+                                   uint32_t fixedLen, uint64_t numQueries, uint32_t *dCounts, awfm_range *dRanges,
+                                   uint64_t *dHitOffsets, void *stream);
 /* Backtrace + sampled-SA read for flat hit indices [hitBegin, hitEnd) into dPositions[h - hitBegin]. */
 int awfm_gpu_locate_device(awfm_gpu_ctx *ctx, const awfm_range *dRanges, const uint64_t *dHitOffsets,
                            uint64_t numQueries, uint64_t hitBegin, uint64_t hitEnd, uint64_t *dPositions,

@@ -293,3 +293,37 @@ print("ok")
     env = dict(os.environ, OMP_THREAD_LIMIT="1")
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "amino_r8"])
+def test_locate_prepare_device_then_walk(small_indexes, name):
+    """awfm_gpu_locate_prepare_device: search + ranges of the queries with hits only + hit offsets scanned from the
+    counts, in one call on device buffers; followed by awfm_gpu_locate_device.  Sweep and tile path."""
+    import torch
+    b = small_indexes[name]
+    length = b.arrays.seed_k + 3
+    letters = fixed_queries(b, length, 7000, seed=31)
+    n = len(letters) // length
+    oracle = harness.Oracle(b.arrays)
+    o_counts, _, _ = oracle.count(letters, fixed_len=length)
+    o_hit, o_pos, _ = oracle.locate(letters, fixed_len=length)
+    gpu = GpuIndex(b.arrays)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_q = torch.from_numpy(letters).cuda()
+    for sweep in (-1, 1):
+        gpu.set_tuning(sweep_min_queries=sweep)
+        d_c = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        d_r = torch.full((n, 2), -7, dtype=torch.int64, device="cuda")  # entries of queries without hits stay untouched
+        d_h = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        gpu.locate_prepare_device(d_q.data_ptr(), QUERY_ASCII, length, n, d_c.data_ptr(), d_r.data_ptr(), d_h.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_c.cpu().numpy().astype(np.uint32), o_counts), (name, sweep)
+        assert np.array_equal(d_h.cpu().numpy().astype(np.uint64), o_hit), (name, sweep)
+        untouched = (d_r.cpu().numpy() == -7).all(axis=1)
+        assert np.array_equal(untouched, o_counts == 0), "ranges must be written exactly for the queries with hits"
+        total = int(o_hit[-1])
+        d_p = torch.zeros(max(total, 1), dtype=torch.int64, device="cuda")
+        gpu.locate_device(d_r.data_ptr(), d_h.data_ptr(), n, 0, total, d_p.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_p[:total].cpu().numpy().astype(np.uint64), o_pos), (name, sweep)
+    gpu.close()

@@ -469,6 +469,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
   else if (k == "sweep_record12" && (value == 0 || value == 1)) c->sweepRecord12 = (int)value;
+  else if (k == "sweep_variable" && (value == 0 || value == 1)) c->sweepVariable = (int)value;
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
@@ -618,14 +619,18 @@ static uint32_t sweepKeyBits(const awfm_gpu_ctx *c, uint32_t k) {  // bits of a 
 }
 static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t len,
                           uint64_t n, const awfm_range *dRanges) {
-  if (c->sweepMinQueries < 0 || c->countVariant != 1 || dOffsets) return false;
+  if (c->sweepMinQueries < 0 || c->countVariant != 1) return false;
   if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
   if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0x70000000ull) return false;  // 32-bit positions and record indices
-  const uint32_t k = sweepSeedK(c, len);
-  if (c->ix.amino) {  // 5 bits per remaining letter in a 32-bit payload, 20^k seed entries in a 32-bit key
-    if (k == 0 || k > 7 || len < k || len - k > 6 || len > 64) return false;
-  } else if (k == 0 || k > 16 || len < k || len - k > 16) {
-    return false;
+  if (dOffsets) {  // variable lengths (sweepPackVar): the index's own seed table only; lengths are checked per query
+    if (!c->sweepVariable || c->ix.deepSeedK || c->ix.seedK == 0 || c->ix.seedK > (c->ix.amino ? 7u : 16u)) return false;
+  } else {
+    const uint32_t k = sweepSeedK(c, len);
+    if (c->ix.amino) {  // 5 bits per remaining letter in a 32-bit payload, 20^k seed entries in a 32-bit key
+      if (k == 0 || k > 7 || len < k || len - k > 6 || len > 64) return false;
+    } else if (k == 0 || k > 16 || len < k || len - k > 16) {
+      return false;
+    }
   }
   if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
   // automatic: pays off once the batch puts about one query on every second 128-B line of the index (measured
@@ -673,12 +678,18 @@ static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
   return AWFM_GPU_OK;
 }
 
+// dOffsets != nullptr: a variable-length batch (n+1 letter offsets into dLetters); `len` is then the longest query of
+// the batch if the caller knows it, else 0.
 template <bool AMINO>
-static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
-                           uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
+static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t format,
+                           uint32_t len, uint64_t n, uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
   SweepScratch &w = L.sweep;
-  const uint32_t k = sweepSeedK(c, len), steps = len - k;
-  const bool deep = c->ix.deepSeedK && len >= c->ix.deepSeedK;
+  const bool variable = dOffsets != nullptr;
+  constexpr uint32_t kVarMaxRest = AMINO ? kSweepVarMaxRestAmino : kSweepVarMaxRestNuc;
+  const uint32_t k = variable ? c->ix.seedK : sweepSeedK(c, len);
+  // variable: as many passes as the longest query the records can hold needs (a pass over no records costs a launch)
+  const uint32_t steps = !variable ? len - k : (len > k ? std::min(len - k, kVarMaxRest) : len ? 1u : kVarMaxRest);
+  const bool deep = !variable && c->ix.deepSeedK && len >= c->ix.deepSeedK;
   int stage = 0;
   auto mark = [&]() {
     if (c->sweepProfile && stage < w.numStages) cudaEventRecord(w.stage[stage++], st);
@@ -716,7 +727,9 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
   {
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
-    if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
+    if (variable) {
+      sweepPackVar<AMINO><<<grid, 256, 0, st>>>(dLetters, dOffsets, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA);
+    } else if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
       const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
       sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA);
     } else if (AMINO && len % 4 == 0 && len <= 12) {
@@ -799,12 +812,13 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     return r;
   };
   // 12-byte records (nucleotide, at most 8 letters left of the seed table's k-mer): see sweepStep
-  const bool rec12 = !AMINO && steps <= 8 && c->sweepRecord12;
-  auto launchPass = [&](auto first, auto items, auto small, uint32_t pass) -> int {
+  const bool rec12 = !AMINO && !variable && steps <= 8 && c->sweepRecord12;
+  auto launchPass = [&](auto first, auto items, auto small, auto var, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
-    constexpr bool REC12 = decltype(small)::value && !AMINO;
-    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12>;
+    constexpr bool VARLEN = decltype(var)::value;
+    constexpr bool REC12 = decltype(small)::value && !AMINO && !VARLEN;
+    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12, VARLEN>;
     int grid = 0;
     if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
     const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
@@ -820,9 +834,12 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     return AWFM_GPU_OK;
   };
   auto launchPassRec = [&](auto first, auto items, uint32_t pass) -> int {
-    return rec12 ? launchPass(first, items, std::true_type(), pass) : launchPass(first, items, std::false_type(), pass);
+    return rec12 ? launchPass(first, items, std::true_type(), std::false_type(), pass)
+                 : launchPass(first, items, std::false_type(), std::false_type(), pass);
   };
   auto launchPassItems = [&](auto first, uint32_t pass) -> int {
+    if (variable)  // one instantiation per alphabet and pass kind: 4 records per thread
+      return launchPass(first, std::integral_constant<int, 4>(), std::false_type(), std::true_type(), pass);
     switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
       case 1: return launchPassRec(first, std::integral_constant<int, 1>(), pass);
       case 2: return launchPassRec(first, std::integral_constant<int, 2>(), pass);
@@ -839,8 +856,8 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
     mark();
   }
   if (format == AWFM_QUERY_ASCII) {
-    sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges,
-                                                         hitsOnly);
+    sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, dOffsets, len, w.irregularIds, irregularCount, dCounts,
+                                                         dRanges, hitsOnly);
     CU(cudaGetLastError());
   } else if (rec12) {  // the 2-bit format has no irregular letters, but a seed range may be too wide for 12-byte records
     sweepIrregularBits<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges,
@@ -857,18 +874,19 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, ui
 
 // Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
 // slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
-static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, uint32_t format, uint32_t len, uint64_t n,
-                      uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
+static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t format,
+                      uint32_t len, uint64_t n, uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
   const bool amino = c->ix.amino != 0;
   const uint64_t maxBatch = amino ? std::min<int64_t>(c->sweepMaxBatch, 1ll << 26) : c->sweepMaxBatch;
   const uint64_t slice = std::min<uint64_t>(n, maxBatch & ~255ull);  // slices start 16-B aligned
-  const uint64_t queryBytes = awfm_query_bytes(format, len);
+  const uint64_t queryBytes = dOffsets ? 0 : awfm_query_bytes(format, len);  // offsets are absolute: same letter base
   if (int r = ensureSweep(c, L, slice, amino ? 10 : 2)) return r;
   for (uint64_t first = 0; first < n; first += slice) {
     const uint64_t m = std::min(slice, n - first);
     uint4 *ranges = dRanges ? dRanges + first : nullptr;
-    const int r = amino ? sweepCountBatch<true>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, hitsOnly, st)
-                        : sweepCountBatch<false>(c, L, dLetters + first * queryBytes, format, len, m, dCounts + first, ranges, hitsOnly, st);
+    const uint64_t *offsets = dOffsets ? dOffsets + first : nullptr;
+    const int r = amino ? sweepCountBatch<true>(c, L, dLetters + first * queryBytes, offsets, format, len, m, dCounts + first, ranges, hitsOnly, st)
+                        : sweepCountBatch<false>(c, L, dLetters + first * queryBytes, offsets, format, len, m, dCounts + first, ranges, hitsOnly, st);
     if (r) return r;
   }
   return AWFM_GPU_OK;
@@ -914,7 +932,10 @@ int awfm_count_device_impl(awfm_gpu_ctx *c, Lane &L, const PackedBatch &batch, u
   QueryBatch qb{dLetters, batch.offsets, n, fixedLen, batch.rangesOfHitsOnly ? 1u : 0u};
   int r;
   const bool sweep = directBits || sweepEligible(c, dLetters, batch.offsets, fixedLen, n, thresholdRanges);
-  r = sweep ? sweepCount(c, L, dLetters, format, fixedLen, n, dCounts, (uint4 *)dRanges, batch.rangesOfHitsOnly, st) : AWFM_GPU_OK;
+  // (a variable-length batch hands the sweep its longest query's length if the caller stated one, else 0)
+  r = sweep ? sweepCount(c, L, dLetters, batch.offsets, format, batch.offsets ? batch.maxLength : fixedLen, n, dCounts,
+                         (uint4 *)dRanges, batch.rangesOfHitsOnly, st)
+            : AWFM_GPU_OK;
   if (!sweep || r == AWFM_GPU_ERR_ALLOC) {  // no room for the sweep's scratch: the tile kernel needs none
     L.sweep.stagesRecorded = 0;
     if (format != AWFM_QUERY_ASCII) return awfm_fail(AWFM_GPU_ERR_ALLOC, "sweep scratch does not fit in device memory");

@@ -131,6 +131,7 @@ struct awfm_gpu_ctx {
   int64_t sweepMaxBatch = 1ll << 27;
   int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
   int sweepRecord12 = 0;  // 12-byte live records when the batch allows it (nucleotide, <= 8 letters left of the seed)
+  int sweepVariable = 1;  // variable-length batches may take the sweep (marker-bit payloads, sweepPackVar)
   int sweepOwnSort = 1;  // 1 = the hand-written stable radix passes (awfm_sort.cuh), 0 = CUB (cross-check)
   static constexpr int kLanes = 3;
   Lane lanes[kLanes];
@@ -163,6 +164,7 @@ struct PackedBatch {
   const uint64_t *offsets = nullptr;  // ASCII only: numQueries+1 letter offsets, or nullptr (fixed length)
   uint32_t format = AWFM_QUERY_ASCII;
   uint32_t length = 0;              // letters per query (fixed-length batches)
+  uint32_t maxLength = 0;           // variable-length batches: longest query if the caller knows it, else 0
   uint64_t numQueries = 0;
   bool rangesOfHitsOnly = false;    // locate pipelines: dRanges is only written for queries with hits (the hit offsets
                                     // are then scanned from dCounts, awfm_scan_impl with fromCounts)

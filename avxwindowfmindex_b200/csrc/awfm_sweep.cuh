@@ -291,6 +291,89 @@ static __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// sweepPackVar: VARIABLE-length ASCII batches (letters + numQueries+1 letter offsets, the layout the search-list
+// engine and awfm_gpu_count_device already use).  The payload's 32 bits hold the letters left of the seed k-mer as
+// above PLUS a marker bit right above the last of them: a record has prepended all its letters when its payload has
+// shrunk to 1, so every record carries its own length and the passes need no common one.  Queries shorter than k
+// (the reference opens those from the last letter, src/AwFmParallelSearch.c:241-268), with more than 15 (amino: 6)
+// letters left of the seed, or holding anything but plain letters go to the irregular list.
+// One thread per query reads the aligned 32-bit words covering its letters (a warp's queries are neighbours: the
+// repeats are L1 hits) and realigns them with a funnel shift; `letters` is 4-byte aligned, nothing past
+// offsets[numQueries] is read.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kSweepVarMaxRestNuc = 15, kSweepVarMaxRestAmino = 6;
+__device__ __forceinline__ uint32_t sweepSafeWord(const uint8_t *__restrict__ letters, uint64_t wordIndex, uint64_t totalBytes) {
+  const uint64_t g = wordIndex * 4ull;
+  if (g + 4 <= totalBytes) return __ldg(reinterpret_cast<const uint32_t *>(letters) + wordIndex);
+  uint32_t w = 0;
+  for (uint32_t b = 0; g + b < totalBytes; b++) w |= (uint32_t)__ldg(letters + g + b) << (8u * b);
+  return w;
+}
+template <bool AMINO>
+__global__ void __launch_bounds__(256)
+    sweepPackVar(const uint8_t *__restrict__ letters, const uint64_t *__restrict__ offsets, uint64_t numQueries, uint32_t k,
+                 uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
+                 uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+  constexpr uint32_t kMaxRest = AMINO ? kSweepVarMaxRestAmino : kSweepVarMaxRestNuc;
+  __shared__ uint32_t histShared[kSortBins];
+  PackHistogram hist;
+  hist.begin(histShared, sortCtrl);
+  const uint64_t totalBytes = __ldg(offsets + numQueries);
+  const uint64_t keyMask = (k >= 16) ? 0xFFFFFFFFull : ((1ull << (2 * k)) - 1ull);
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
+       q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o = __ldg(offsets + q), len64 = __ldg(offsets + q + 1) - o;
+    uint32_t key = 0, payload = 1u, bad = (len64 < k || len64 - k > kMaxRest) ? 1u : 0u;
+    if (!bad) {
+      const uint32_t len = (uint32_t)len64, rest = len - k, shift = (uint32_t)(o & 3u) * 8u;
+      const uint64_t w0 = o >> 2, wEnd = (o + len + 3) >> 2;  // words [w0, wEnd) cover the query's letters
+      uint32_t a = sweepSafeWord(letters, w0, totalBytes);
+      uint64_t Q = 0;
+      uint32_t packed = 0;
+      for (uint32_t i = 0; 4u * i < len; i++) {
+        const uint32_t b = (w0 + i + 1 < wEnd) ? sweepSafeWord(letters, w0 + i + 1, totalBytes) : 0u;
+        const uint32_t group = __funnelshift_r(a, b, shift);  // letters 4i .. 4i+3 of the query
+        a = b;
+        const uint32_t t = min(4u, len - 4u * i);
+        if constexpr (AMINO) {
+          for (uint32_t j = 0; j < t; j++) {
+            const uint32_t at = 4u * i + j;
+            const uint32_t l = aminoLetterIndex((group >> (8u * j)) & 0xFFu);
+            bad |= l >= 20u;
+            const uint32_t v = l < 20u ? l : 0u;
+            if (at >= rest) key = key * 20u + v;            // leftmost of the last k letters most significant
+            else packed |= v << (5u * (rest - 1u - at));    // letter prepended at step j+1 is s[rest-1-j]
+          }
+        } else {
+          uint32_t bad4 = 0;
+          uint32_t p = packFourLetters(group, bad4);  // first letter in bits 7..6
+          if (t < 4u) p >>= 2u * (4u - t), bad4 &= (1u << (8u * t)) - 1u;
+          Q = (Q << (2u * t)) | p;
+          bad |= bad4;
+        }
+      }
+      if constexpr (AMINO) {
+        payload = packed | (1u << (5u * rest));
+      } else {
+        key = (uint32_t)(Q & keyMask);
+        payload = (uint32_t)(Q >> (2 * k)) | (1u << (2u * rest));
+      }
+    }
+    uint32_t id = (uint32_t)q;
+    if (bad) {
+      irregularIds[atomicAdd(irregularCount, 1u)] = id;
+      id = kSweepNoId;
+      key = 0;
+      payload = 1u;
+    }
+    keys[q] = key;
+    vals[q] = ((uint64_t)payload << 32) | id;
+    hist.add(sortCtrl, key, shiftA);
+  }
+  hist.flush(sortCtrl);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // sweepStep: one pass.  FIRST: input = sorted (key, payload) pairs, range from the seed table; else input = the
 // previous generation's buckets in letter order.  `steps` = LF steps the queries of this pass still have to do
 // INCLUDING this pass's (0 only for FIRST with len == k).
@@ -383,7 +466,9 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // range is wider than 65534 goes to the irregular list (sweepIrregular answers it with the generic per-query search).
 // (forcing more resident CTAs per SM through __launch_bounds__ was measured: 5, 6 and 8 CTAs spill and run 20-30 %
 // slower than the 64 registers / 4 CTAs the compiler picks on its own, profiles/r02_sweep_probe.jsonl)
-template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false>
+// VARLEN (sweepPackVar's payloads, marker bit above the last remaining letter): a record is finished when its payload
+// has shrunk to 1; `steps` is then the largest number of steps any record of the batch can still have to do.
+template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false>
 __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
@@ -392,6 +477,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
               uint32_t *__restrict__ irregularIds, uint32_t *__restrict__ irregularCount,
               bool rangesOfHitsOnly /* ranges only of queries whose final range is non-empty (locate) */) {
   static_assert(!(REC12 && AMINO), "12-byte records are a nucleotide format");
+  static_assert(!(REC12 && VARLEN), "12-byte records hold 16 bits of letters, no room for the marker bit");
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   constexpr uint32_t kLetterMask = (1u << LB) - 1u;
@@ -572,6 +658,12 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
           irregularIds[atomicAdd(irregularCount, 1u)] = id[it];
           id[it] = kSweepNoId;
         }
+        if (VARLEN && id[it] != kSweepNoId && rest[it] == 1u) {  // len == k: the seed entry is the answer
+          counts[id[it]] = (uint32_t)(e64[it] - s64[it] + 1ull);
+          if (ranges)
+            ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
+          id[it] = kSweepNoId;
+        }
         if (id[it] != kSweepNoId) sp[it] = (uint32_t)s64[it], ep[it] = (uint32_t)e64[it];
       }
     }
@@ -614,8 +706,9 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
       }
       bucket[it] = NB;  // no output
       if (valid) {
-        if (steps <= 1 && ranges) ranges[id[it]] = make_uint4(sp[it], 0u, ep[it], 0u);
-        if (steps <= 1) counts[id[it]] = ep[it] - sp[it] + 1u;
+        const bool last = VARLEN ? (steps <= 1 || rest[it] == 1u) : steps <= 1;
+        if (last && ranges) ranges[id[it]] = make_uint4(sp[it], 0u, ep[it], 0u);
+        if (last) counts[id[it]] = ep[it] - sp[it] + 1u;
         else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
       }
     }
@@ -679,13 +772,16 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
 // business for one query (countKernelV0's body), one thread per listed id.
 template <bool AMINO>
 __global__ void __launch_bounds__(256)
-    sweepIrregular(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ letters, uint32_t len,
+    sweepIrregular(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ letters,
+                   const uint64_t *__restrict__ offsets /* or nullptr: fixed length */, uint32_t fixedLen,
                    const uint32_t *__restrict__ ids, const uint32_t *__restrict__ numIds,
                    uint32_t *__restrict__ counts, uint4 *__restrict__ ranges, bool rangesOfHitsOnly) {
   const uint32_t n = *numIds;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t q = ids[i];
-    const uint8_t *s = letters + (uint64_t)q * len;
+    const uint64_t off = offsets ? __ldg(offsets + q) : (uint64_t)q * fixedLen;
+    const uint64_t len = offsets ? __ldg(offsets + q + 1) - off : (uint64_t)fixedLen;
+    const uint8_t *s = letters + off;
     uint64_t sp, ep;
     uint64_t next = openRange<AMINO>(ix, s, len, sp, ep);
     while (next > 0 && sp <= ep) {

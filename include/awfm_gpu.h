@@ -127,7 +127,7 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * A/B switch for a table already derived with awfm_gpu_ctx_extend_seed_table); of the search-list engine:
  * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
- * Sweep count path (csrc/awfm_sweep.cuh; large fixed-length batches of either alphabet, counts and ranges):
+ * Sweep count path (csrc/awfm_sweep.cuh; large batches of either alphabet, fixed or variable length, counts and ranges):
  * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per two 128-B lines of the index) queries and no
  * derived deep seed table; n > 0 = batches of at least n queries; -1 = never), "sweep_sort_bits" (top bits of the seed
  * index the radix sort orders, default 32 = all but the low "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 =
@@ -140,7 +140,10 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * deeper seed tables), "sweep_record12" (1: live records of nucleotide batches with at most 8 letters left of the seed
  * travel as 12 bytes — 16-bit range width, 16 bits of letters — and queries whose seed range is wider than 65534 take
  * the generic per-query search; 0, the default: 16-byte records — the passes are latency-bound, not byte-bound, and the
- * smaller records measured no faster, profiles/r02_sweep_probe.jsonl). */
+ * smaller records measured no faster, profiles/r02_sweep_probe.jsonl), "sweep_variable" (1, the default: variable-length
+ * ASCII batches — an offsets array — take the sweep too, every record carrying its own length as a marker bit above its
+ * remaining letters; queries shorter than the seed k-mer or with more than 15 (amino: 6) letters left of it are answered
+ * by the generic per-query search inside the same call; 0: such batches always take the tile kernel). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 /* Device time of every stage of the most recent sweep count call made with "sweep_profile" = 1, in launch order:
  * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.

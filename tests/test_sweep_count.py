@@ -111,8 +111,95 @@ def test_sweep_matches_oracle(small_indexes, name):
     gpu.close()
 
 
+def variable_batch(b, num, seed, lo, hi, irregular=True):
+    """Queries of lengths lo..hi (uniform), 60 % substrings of the text, some with irregular letters / lower case."""
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(lo, hi + 1, num)
+    offsets = np.zeros(num + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths)
+    alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY" if b.amino else b"ACGT", dtype=np.uint8)
+    odd = (b"X", b"b", b"$", b"z", b"-", b"j", b"O") if b.amino else (b"N", b"n", b"$", b"x", b"-")
+    text = b.text
+    letters = np.empty(int(offsets[-1]), dtype=np.uint8)
+    for i in range(num):
+        o, n = int(offsets[i]), int(lengths[i])
+        if n == 0:
+            continue
+        if rng.random() < 0.6:
+            s = int(rng.integers(0, len(text) - n))
+            letters[o:o + n] = text[s:s + n]
+        else:
+            letters[o:o + n] = alphabet[rng.integers(0, len(alphabet), n)]
+        if irregular:
+            r = rng.random()
+            if r < 0.05:
+                letters[o + int(rng.integers(0, n))] = odd[i % len(odd)][0]
+            elif r < 0.15:
+                letters[o:o + n] |= 0x20
+            elif r < 0.18 and not b.amino:
+                letters[o:o + n] = ord("U")
+    return letters, offsets
+
+
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r16", "amino_r8", "amino_r1"])
+def test_sweep_variable_lengths(small_indexes, name):
+    """Variable-length batches (letters + offsets): every record carries its own length as a marker bit above its
+    remaining letters.  Lengths from 0 to past what the payload holds — shorter than the seed k-mer, exactly k, up to
+    k + 15 (amino: k + 6) letters, and longer — in one batch; counts and ranges against the oracle, with every ordering
+    configuration, sliced scratch, and the tile kernel as cross-check."""
+    b = small_indexes[name]
+    k = b.arrays.seed_k
+    room = 6 if b.amino else 15
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    for num, lo, hi, seed in ((9000, 0, k + room + 3, 1), (5000, k, k + room, 2), (1, k + 2, k + 2, 3),
+                              (300, 1, max(k - 1, 1), 4), (2500, k + room, k + room, 5), (20000, k, k + 4, 6)):
+        letters, offsets = variable_batch(b, num, seed=seed * 131 + num, lo=lo, hi=hi)
+        o_counts, o_ranges, _ = oracle.count(letters, offsets)
+        for bits, local, own, max_batch in ((32, -1, 1, 1 << 27), (16, 0, 0, 1 << 27), (3, 5, 1, 1024), (32, 8, 1, 4096)):
+            gpu.set_tuning(sweep_min_queries=1, sweep_variable=1, sweep_sort_bits=bits, sweep_local_bits=local,
+                           sweep_own_sort=own, sweep_max_batch=max_batch, sweep_profile=1)
+            counts, ranges = gpu.count(letters, offsets, want_ranges=True)
+            assert len(gpu.sweep_stage_ms()) == 3 + room, "the batch did not take the sweep path"
+            assert np.array_equal(counts, o_counts), (name, num, lo, hi, bits, local, own, max_batch)
+            assert np.array_equal(ranges, o_ranges), (name, num, lo, hi, bits, local, own, max_batch)
+            assert np.array_equal(gpu.count(letters, offsets), o_counts)
+        gpu.set_tuning(sweep_variable=0, sweep_max_batch=1 << 27)
+        counts, ranges = gpu.count(letters, offsets, want_ranges=True)
+        assert not gpu.sweep_stage_ms(), "sweep_variable=0 still took the sweep path"
+        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges)
+    gpu.close()
+
+
+def test_sweep_variable_lengths_on_device_buffers(small_indexes):
+    """awfm_gpu_count_device with an offsets array whose letters end exactly at the end of the allocation's payload
+    (the pack kernel reads aligned words but nothing past offsets[n]) and a letter base that is only 16-B aligned."""
+    import torch
+    b = small_indexes["nuc_r8"]
+    k = b.arrays.seed_k
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    gpu.set_tuning(sweep_min_queries=1, sweep_profile=1)
+    for num, seed in ((4097, 11), (513, 12), (7, 13)):
+        letters, offsets = variable_batch(b, num, seed=seed, lo=k - 2, hi=k + 17)
+        o_counts, o_ranges, _ = oracle.count(letters, offsets)
+        pad = torch.zeros(len(letters) + 48, dtype=torch.uint8, device="cuda")
+        d_letters = pad[16:16 + len(letters)]
+        d_letters.copy_(torch.from_numpy(letters))
+        d_offsets = torch.from_numpy(offsets.view(np.int64)).cuda()
+        d_counts = torch.full((num,), 7, dtype=torch.int32, device="cuda")
+        d_ranges = torch.zeros((num, 2), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        gpu.count_device(d_letters.data_ptr(), d_offsets.data_ptr(), 0, num, d_counts.data_ptr(), d_ranges.data_ptr())
+        torch.cuda.synchronize()
+        assert gpu.sweep_stage_ms(), "the batch did not take the sweep path"
+        assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), o_counts)
+        assert np.array_equal(d_ranges.cpu().numpy().view(np.uint64), o_ranges)
+    gpu.close()
+
+
 def test_sweep_falls_back_outside_its_domain(small_indexes):
-    """Too many letters left of the seed, variable lengths: the tile kernels answer, same results."""
+    """Too many letters left of the seed in a fixed-length batch: the tile kernels answer, same results."""
     b = small_indexes["nuc_r8"]
     k = b.arrays.seed_k
     oracle = harness.Oracle(b.arrays)

@@ -297,9 +297,7 @@ static __global__ void __launch_bounds__(256)
 // shrunk to 1, so every record carries its own length and the passes need no common one.  Queries shorter than k
 // (the reference opens those from the last letter, src/AwFmParallelSearch.c:241-268), with more than 15 (amino: 6)
 // letters left of the seed, or holding anything but plain letters go to the irregular list.
-// One thread per query reads the aligned 32-bit words covering its letters (a warp's queries are neighbours: the
-// repeats are L1 hits) and realigns them with a funnel shift; `letters` is 4-byte aligned, nothing past
-// offsets[numQueries] is read.
+// `letters` is 16-byte aligned, nothing past offsets[numQueries] is read.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kSweepVarMaxRestNuc = 15, kSweepVarMaxRestAmino = 6;
 __device__ __forceinline__ uint32_t sweepSafeWord(const uint8_t *__restrict__ letters, uint64_t wordIndex, uint64_t totalBytes) {
@@ -309,6 +307,51 @@ __device__ __forceinline__ uint32_t sweepSafeWord(const uint8_t *__restrict__ le
   for (uint32_t b = 0; g + b < totalBytes; b++) w |= (uint32_t)__ldg(letters + g + b) << (8u * b);
   return w;
 }
+// one query straight from global memory (amino batches; nucleotide tiles too long for the staging buffer)
+template <bool AMINO>
+__device__ __forceinline__ void sweepPackVarDirect(const uint8_t *__restrict__ letters, uint64_t totalBytes, uint64_t o,
+                                                   uint32_t len, uint32_t k, uint64_t keyMask, uint32_t &key,
+                                                   uint32_t &payload, uint32_t &bad) {
+  const uint32_t rest = len - k, shift = (uint32_t)(o & 3u) * 8u;
+  const uint64_t w0 = o >> 2, wEnd = (o + len + 3) >> 2;  // words [w0, wEnd) cover the query's letters
+  uint32_t a = sweepSafeWord(letters, w0, totalBytes);
+  uint64_t Q = 0;
+  uint32_t packed = 0;
+  for (uint32_t i = 0; 4u * i < len; i++) {
+    const uint32_t b = (w0 + i + 1 < wEnd) ? sweepSafeWord(letters, w0 + i + 1, totalBytes) : 0u;
+    const uint32_t group = __funnelshift_r(a, b, shift);  // letters 4i .. 4i+3 of the query
+    a = b;
+    const uint32_t t = min(4u, len - 4u * i);
+    if constexpr (AMINO) {
+      for (uint32_t j = 0; j < t; j++) {
+        const uint32_t at = 4u * i + j;
+        const uint32_t l = aminoLetterIndex((group >> (8u * j)) & 0xFFu);
+        bad |= l >= 20u;
+        const uint32_t v = l < 20u ? l : 0u;
+        if (at >= rest) key = key * 20u + v;            // leftmost of the last k letters most significant
+        else packed |= v << (5u * (rest - 1u - at));    // letter prepended at step j+1 is s[rest-1-j]
+      }
+    } else {
+      uint32_t bad4 = 0;
+      uint32_t p = packFourLetters(group, bad4);  // first letter in bits 7..6
+      if (t < 4u) p >>= 2u * (4u - t), bad4 &= (1u << (8u * t)) - 1u;
+      Q = (Q << (2u * t)) | p;
+      bad |= bad4;
+    }
+  }
+  if constexpr (AMINO) {
+    payload = packed | (1u << (5u * rest));
+  } else {
+    key = (uint32_t)(Q & keyMask);
+    payload = (uint32_t)(Q >> (2 * k)) | (1u << (2u * rest));
+  }
+}
+// Nucleotide tiles: the 256 queries' letters (at most 31 each if they are to stay in the sweep, so 8 KB hold them) are
+// turned into a 2-bit stream cooperatively — thread i translates bytes [32i, 32i+32) of the tile with eight
+// packFourLetters and notes which of its eight 4-letter groups held anything but A/C/G/T/U — and every query then
+// cuts its own letters out of that stream with two funnel shifts.  A 4-letter group may straddle two queries: an
+// irregular letter then sends its neighbour to the irregular list as well, which only costs that query the slower path.
+constexpr uint32_t kSweepVarStageBytes = 8 * 1024;
 template <bool AMINO>
 __global__ void __launch_bounds__(256)
     sweepPackVar(const uint8_t *__restrict__ letters, const uint64_t *__restrict__ offsets, uint64_t numQueries, uint32_t k,
@@ -316,59 +359,93 @@ __global__ void __launch_bounds__(256)
                  uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
   constexpr uint32_t kMaxRest = AMINO ? kSweepVarMaxRestAmino : kSweepVarMaxRestNuc;
   __shared__ uint32_t histShared[kSortBins];
+  __shared__ uint64_t sOff[257];
+  __shared__ uint32_t sCodes[AMINO ? 1 : kSweepVarStageBytes / 16 + 2];  // word j: letters 16j..16j+15, first in the top bits
+  __shared__ uint8_t sBadGroups[AMINO ? 1 : kSweepVarStageBytes / 32 + 4];  // byte i: groups 8i..8i+7, first in bit 7
   PackHistogram hist;
   hist.begin(histShared, sortCtrl);
   const uint64_t totalBytes = __ldg(offsets + numQueries);
   const uint64_t keyMask = (k >= 16) ? 0xFFFFFFFFull : ((1ull << (2 * k)) - 1ull);
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < numQueries;
-       q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t o = __ldg(offsets + q), len64 = __ldg(offsets + q + 1) - o;
-    uint32_t key = 0, payload = 1u, bad = (len64 < k || len64 - k > kMaxRest) ? 1u : 0u;
-    if (!bad) {
-      const uint32_t len = (uint32_t)len64, rest = len - k, shift = (uint32_t)(o & 3u) * 8u;
-      const uint64_t w0 = o >> 2, wEnd = (o + len + 3) >> 2;  // words [w0, wEnd) cover the query's letters
-      uint32_t a = sweepSafeWord(letters, w0, totalBytes);
-      uint64_t Q = 0;
-      uint32_t packed = 0;
-      for (uint32_t i = 0; 4u * i < len; i++) {
-        const uint32_t b = (w0 + i + 1 < wEnd) ? sweepSafeWord(letters, w0 + i + 1, totalBytes) : 0u;
-        const uint32_t group = __funnelshift_r(a, b, shift);  // letters 4i .. 4i+3 of the query
-        a = b;
-        const uint32_t t = min(4u, len - 4u * i);
-        if constexpr (AMINO) {
-          for (uint32_t j = 0; j < t; j++) {
-            const uint32_t at = 4u * i + j;
-            const uint32_t l = aminoLetterIndex((group >> (8u * j)) & 0xFFu);
-            bad |= l >= 20u;
-            const uint32_t v = l < 20u ? l : 0u;
-            if (at >= rest) key = key * 20u + v;            // leftmost of the last k letters most significant
-            else packed |= v << (5u * (rest - 1u - at));    // letter prepended at step j+1 is s[rest-1-j]
+  const uint64_t numTiles = (numQueries + 255) / 256;
+  // this thread's offset of the tile after the current one (and, thread 0, that tile's closing offset): requested one
+  // tile ahead so that only the letter loads sit between a tile's barriers
+  auto fetchOffsets = [&](uint64_t tile, uint64_t &mine, uint64_t &closing) {
+    if (tile >= numTiles) return;
+    const uint64_t q0 = tile * 256;
+    const uint32_t nq = (uint32_t)min((uint64_t)256, numQueries - q0);
+    if (threadIdx.x <= nq) mine = __ldg(offsets + q0 + threadIdx.x);
+    if (threadIdx.x == 0) closing = __ldg(offsets + q0 + nq);
+  };
+  uint64_t nextMine = 0, nextClosing = 0;
+  fetchOffsets(blockIdx.x, nextMine, nextClosing);
+  for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    const uint64_t q0 = tile * 256;
+    const uint32_t nq = (uint32_t)min((uint64_t)256, numQueries - q0);
+    __syncthreads();  // previous tile consumed
+    if (threadIdx.x <= nq) sOff[threadIdx.x] = nextMine;
+    if (threadIdx.x == 0) sOff[nq] = nextClosing;  // (nq == 256: the 257th offset)
+    __syncthreads();
+    fetchOffsets(tile + gridDim.x, nextMine, nextClosing);
+    const uint64_t aligned0 = sOff[0] & ~15ull, byte1 = sOff[nq];
+    const bool staged = !AMINO && byte1 >= aligned0 && byte1 - aligned0 <= kSweepVarStageBytes;  // uniform per CTA
+    if constexpr (!AMINO) {
+      if (staged) {
+        const uint64_t g = aligned0 + 32ull * threadIdx.x;
+        if (g < byte1) {
+          uint32_t w[8];
+          if (g + 32 <= totalBytes) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(letters + g));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(letters + g) + 1);
+            w[0] = v0.x, w[1] = v0.y, w[2] = v0.z, w[3] = v0.w, w[4] = v1.x, w[5] = v1.y, w[6] = v1.z, w[7] = v1.w;
+          } else {  // never read past the batch's final letter
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = sweepSafeWord(letters, (g >> 2) + j, totalBytes);
           }
+          uint32_t codes[2] = {0, 0}, badGroups = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            uint32_t bad4 = 0;
+            codes[j >> 2] = (codes[j >> 2] << 8) | packFourLetters(w[j], bad4);
+            badGroups = (badGroups << 1) | (bad4 ? 1u : 0u);
+          }
+          sCodes[2 * threadIdx.x] = codes[0];
+          sCodes[2 * threadIdx.x + 1] = codes[1];
+          sBadGroups[threadIdx.x] = (uint8_t)badGroups;
+        }
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x < nq) {
+      const uint64_t q = q0 + threadIdx.x;
+      const uint64_t o = sOff[threadIdx.x], len64 = sOff[threadIdx.x + 1] - o;
+      uint32_t key = 0, payload = 1u, bad = (len64 < k || len64 - k > kMaxRest) ? 1u : 0u;
+      if (!bad) {
+        const uint32_t len = (uint32_t)len64;
+        if (staged) {
+          const uint32_t a = (uint32_t)(o - aligned0), word = a >> 4, sh = 2u * (a & 15u);
+          const uint32_t c0 = sCodes[word], c1 = sCodes[word + 1], c2 = sCodes[word + 2];
+          const uint64_t window = ((uint64_t)__funnelshift_l(c1, c0, sh) << 32) | __funnelshift_l(c2, c1, sh);  // letters a .. a+31
+          const uint64_t Q = window >> (64u - 2u * len);  // 1 <= len <= 31: first letter most significant
+          key = (uint32_t)(Q & keyMask);
+          payload = (uint32_t)(Q >> (2 * k)) | (1u << (2u * (len - k)));
+          const uint32_t g0 = a >> 2, groups = ((a + len - 1u) >> 2) - g0 + 1u;  // <= 9 groups, within 16 bits from g0's byte
+          const uint32_t two = ((uint32_t)sBadGroups[g0 >> 3] << 8) | sBadGroups[(g0 >> 3) + 1];
+          bad = (two >> (16u - (g0 & 7u) - groups)) & ((1u << groups) - 1u);
         } else {
-          uint32_t bad4 = 0;
-          uint32_t p = packFourLetters(group, bad4);  // first letter in bits 7..6
-          if (t < 4u) p >>= 2u * (4u - t), bad4 &= (1u << (8u * t)) - 1u;
-          Q = (Q << (2u * t)) | p;
-          bad |= bad4;
+          sweepPackVarDirect<AMINO>(letters, totalBytes, o, len, k, keyMask, key, payload, bad);
         }
       }
-      if constexpr (AMINO) {
-        payload = packed | (1u << (5u * rest));
-      } else {
-        key = (uint32_t)(Q & keyMask);
-        payload = (uint32_t)(Q >> (2 * k)) | (1u << (2u * rest));
+      uint32_t id = (uint32_t)q;
+      if (bad) {
+        irregularIds[atomicAdd(irregularCount, 1u)] = id;
+        id = kSweepNoId;
+        key = 0;
+        payload = 1u;
       }
+      keys[q] = key;
+      vals[q] = ((uint64_t)payload << 32) | id;
+      hist.add(sortCtrl, key, shiftA);
     }
-    uint32_t id = (uint32_t)q;
-    if (bad) {
-      irregularIds[atomicAdd(irregularCount, 1u)] = id;
-      id = kSweepNoId;
-      key = 0;
-      payload = 1u;
-    }
-    keys[q] = key;
-    vals[q] = ((uint64_t)payload << 32) | id;
-    hist.add(sortCtrl, key, shiftA);
   }
   hist.flush(sortCtrl);
 }

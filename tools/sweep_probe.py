@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--no-tile", action="store_true")
     ap.add_argument("--amino", action="store_true", help="cfg 4 shape: pass --bp 1000000000 --queries 50000000 --kmer 8 --seed-k 5")
     ap.add_argument("--own-sort", type=str, default="1,0", help="ordering step: 1 = csrc/awfm_sort.cuh, 0 = CUB")
+    ap.add_argument("--variable", type=str, default="", help="lo,hi: also time a variable-length batch of --queries queries with lengths uniform in lo..hi (tile kernel vs sweep)")
     ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
     lib = capi.load()
@@ -99,6 +100,37 @@ def main():
         emit({"variant": "size", "queries": nq, "tile_ms": t_tile, "sweep_ms": t_sweep,
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": bool(torch.equal(d_counts[:nq], d_ref[:nq]))})
+    if args.variable:
+        lo, hi = (int(x) for x in args.variable.split(","))
+        g = torch.Generator(device="cuda").manual_seed(7)
+        lengths = torch.randint(lo, hi + 1, (n,), device="cuda", generator=g, dtype=torch.int64)
+        d_offsets = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        torch.cumsum(lengths, 0, out=d_offsets[1:])
+        total = int(d_offsets[-1])
+        del lengths
+        d_var = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        capi.check(lib.awfm_gpu_synth_letters(0, d_var.data_ptr(), total, synth.QUERY_SEED + 5, 0, int(args.amino)))
+
+        def timed_var(dst, reps=3):
+            best = 1e30
+            for _ in range(reps + 1):
+                a.record(stream)
+                gpu.count_device(d_var.data_ptr(), d_offsets.data_ptr(), 0, n, dst.data_ptr(), None, stream.cuda_stream)
+                b.record(stream)
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return best
+
+        gpu.set_tuning(sweep_min_queries=-1)
+        t_tile = timed_var(d_ref)
+        gpu.set_tuning(sweep_min_queries=1, sweep_profile=1, sweep_items=4, sweep_local_bits=-1)
+        d_counts.fill_(-1)
+        t_sweep = timed_var(d_counts)
+        emit({"variant": "variable", "lengths": [lo, hi], "queries": n, "letters": total, "tile_ms": t_tile, "sweep_ms": t_sweep,
+              "tile_Gq_per_s": n / t_tile / 1e6, "sweep_Gq_per_s": n / t_sweep / 1e6,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()], "equal_to_tile": bool(torch.equal(d_counts, d_ref)),
+              "hits": int(d_ref.sum(dtype=torch.int64))})
+        del d_var, d_offsets
     if args.deep:
         gpu.extend_seed_table(args.deep)
         gpu.set_tuning(sweep_min_queries=-1)

@@ -121,3 +121,87 @@ def test_suffix_array_fields_wider_than_32_bits(small_indexes, width):
         hit, pos = gpu.locate(letters, fixed_len=9)
         assert np.array_equal(hit, o_hit) and np.array_equal(pos, o_pos), (width, variant)
     gpu.close()
+
+
+def big_garbage_index(num_blocks, pattern_blocks, seed_k, rng):
+    """A nucleotide 'index' of num_blocks * 256 positions (more than 2^32) without 13 GB of random bits: a random
+    pattern of pattern_blocks blocks repeated, base occurrences consistent with it, REALISTIC prefix sums (C[c] =
+    matches of the letters before c) so that LF steps with G/T land above 2^32 again, and a seed table whose ranges
+    lie anywhere in the BWT — below, above and across position 2^32."""
+    bbytes = abi.NUC_BLOCK_BYTES
+    n = num_blocks * 256
+    pattern = rng.integers(0, 256, (pattern_blocks, 96), dtype=np.uint8)
+    words = pattern.view("<u8").reshape(pattern_blocks, 3, 4)
+    per_block = []
+    for code, care in NUC_CODE_CARE:
+        match = np.full((pattern_blocks, 4), np.uint64(0xFFFFFFFFFFFFFFFF))
+        for v in range(3):
+            if (care >> v) & 1:
+                match &= words[:, v, :] if (code >> v) & 1 else ~words[:, v, :]
+        per_block.append(np.bitwise_count(match).sum(axis=1).astype(np.uint64))
+    blocks = aligned_empty(num_blocks * bbytes)
+    view = blocks.reshape(num_blocks, bbytes)
+    for lo in range(0, num_blocks, pattern_blocks):
+        hi = min(num_blocks, lo + pattern_blocks)
+        view[lo:hi, :96] = pattern[: hi - lo]
+    base = view[:, 96:].view("<u8")
+    base[:] = 0
+    index = np.arange(num_blocks, dtype=np.uint64)
+    within, repeat = (index % np.uint64(pattern_blocks)).astype(np.int64), index // np.uint64(pattern_blocks)
+    totals = []
+    for letter, counts in enumerate(per_block):
+        before = np.concatenate([[np.uint64(0)], np.cumsum(counts, dtype=np.uint64)[:-1]])
+        base[:, letter] = before[within] + repeat * np.uint64(counts.sum())
+        full, rest = divmod(num_blocks, pattern_blocks)
+        totals.append(int(counts.sum()) * full + int(counts[:rest].sum()))
+    prefix = np.zeros(6, np.uint64)
+    for c in range(1, 5):
+        prefix[c] = prefix[c - 1] + np.uint64(totals[c - 1])
+    prefix[5] = n
+    assert int(prefix[4]) < n
+    num_seeds = 4 ** seed_k
+    sp = rng.integers(1, n - 4000, num_seeds).astype(np.uint64)
+    sp[::4] = np.uint64(1 << 32) - rng.integers(0, 1500, len(sp[::4])).astype(np.uint64)   # ranges across 2^32
+    sp[1::4] = np.uint64(1 << 32) + rng.integers(0, n - (1 << 32) - 4000, len(sp[1::4])).astype(np.uint64)  # above it
+    ep = sp + rng.integers(0, 3000, num_seeds).astype(np.uint64)
+    seeds = np.stack([sp, ep], axis=1)
+    seeds[::17] = seeds[::17][:, ::-1] + np.array([1, 0], np.uint64)  # some stored invalid pairs (sp > ep)
+    return IndexArrays(abi.AwFmAlphabetDna, seed_k, 8, n, blocks, prefix, seeds, None)
+
+
+def test_positions_beyond_two_to_the_32():
+    """bwtLength = 1.25 * 2^32 (a two-strand human genome is 6.2 G positions): every 64-bit path of the upload-time
+    re-layout (sector counts relative to 2^16-position superblocks, 64-bit superblock rows) and of the tile kernels,
+    on ranges below, above and across position 2^32, bit-exact against the oracle.  The sweep (32-bit positions) must
+    decline such an index."""
+    rng = np.random.default_rng(2032)
+    k = 5
+    num_blocks = (5 << 30) // 256 + 777
+    arrays = big_garbage_index(num_blocks, 1 << 15, k, rng)
+    alphabet = np.frombuffer(b"ACGT", np.uint8)
+    num_seeds = 4 ** k
+    idx = np.arange(num_seeds)
+    tails = np.stack([alphabet[(idx // 4 ** (k - 1 - j)) % 4] for j in range(k)], axis=1)
+    batches = []
+    rows = [np.concatenate([np.full((num_seeds, 1), ch, np.uint8), tails], axis=1) for ch in b"ACGTN"]
+    batches.append((np.ascontiguousarray(np.concatenate(rows).reshape(-1)), k + 1))      # every seed under every letter
+    for length, weights in ((k + 3, (1, 1, 1, 1)), (k + 7, (1, 1, 3, 6)), (k + 12, (0, 1, 4, 12))):  # G/T-heavy: stays high
+        p = np.array(weights, float) / sum(weights)
+        batches.append((np.ascontiguousarray(alphabet[rng.choice(4, (20000, length), p=p)].reshape(-1)), length))
+    oracle = harness.Oracle(arrays)
+    gpu = GpuIndex(arrays)
+    seen_high = 0
+    for letters, length in batches:
+        o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
+        seen_high += int((o_ranges[:, 0] >= np.uint64(1 << 32)).sum())
+        for variant, lpq in ((1, 2), (1, 1), (0, 2)):
+            gpu.set_tuning(sweep_min_queries=-1, count_variant=variant, count_lpq=lpq)
+            counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+            assert np.array_equal(ranges, o_ranges), (length, variant, lpq)
+            assert np.array_equal(counts, o_counts), (length, variant, lpq)
+        gpu.set_tuning(sweep_min_queries=1, sweep_profile=1, count_variant=1)
+        counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+        assert not gpu.sweep_stage_ms(), "the 32-bit sweep took an index with more than 2^32 positions"
+        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges)
+    assert seen_high > 1000, "the batches never reached positions above 2^32"
+    gpu.close()

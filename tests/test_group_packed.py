@@ -83,12 +83,13 @@ def test_group_count_variable_length_and_irregular(small_indexes, reference):
         r_counts = reference.count(b.ptr, letters, offsets, threads=2)
         indexes = two_contexts(b.arrays)
         group = GpuGroup(indexes=indexes)
-        group.set_tuning(packed_chunk_queries=256, packed_min_shard=700)
-        counts = group.count(letters, QUERY_ASCII, offsets=offsets)
-        assert np.array_equal(counts, r_counts), name
-        hit, pos = group.locate(letters, QUERY_ASCII, offsets=offsets)
         o_hit, o_pos, _ = harness.Oracle(b.arrays).locate(letters, offsets)
-        assert np.array_equal(hit, o_hit) and np.array_equal(pos, o_pos), name
+        for sweep in (-1, 1):  # tile kernel | sweep with marker-bit payloads (chunks start at unaligned letter offsets)
+            group.set_tuning(packed_chunk_queries=256, packed_min_shard=700, sweep_min_queries=sweep)
+            counts = group.count(letters, QUERY_ASCII, offsets=offsets)
+            assert np.array_equal(counts, r_counts), (name, sweep)
+            hit, pos = group.locate(letters, QUERY_ASCII, offsets=offsets)
+            assert np.array_equal(hit, o_hit) and np.array_equal(pos, o_pos), (name, sweep)
         group.close()
         for ix in indexes:
             ix.close()

@@ -470,6 +470,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
   else if (k == "sweep_record12" && (value == 0 || value == 1)) c->sweepRecord12 = (int)value;
   else if (k == "sweep_variable" && (value == 0 || value == 1)) c->sweepVariable = (int)value;
+  else if (k == "sweep_wide" && (value == 0 || value == 1)) c->sweepWide = (int)value;
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
@@ -621,7 +622,9 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
                           uint64_t n, const awfm_range *dRanges) {
   if (c->sweepMinQueries < 0 || c->countVariant != 1) return false;
   if ((reinterpret_cast<uintptr_t>(dLetters) & 15u) != 0) return false;
-  if (c->ix.bwtLength >= 0xFFFFFFF0ull || n >= 0x70000000ull) return false;  // 32-bit positions and record indices
+  if (n >= 0x70000000ull) return false;  // 32-bit record indices
+  // 32-bit positions; nucleotide indexes beyond that take the passes with 64-bit positions (40 bits in a record)
+  if (c->ix.bwtLength >= 0xFFFFFFF0ull && (c->ix.amino || c->ix.bwtLength >= (1ull << 40))) return false;
   if (dOffsets) {  // variable lengths (sweepPackVar): the index's own seed table only; lengths are checked per query
     if (!c->sweepVariable || c->ix.deepSeedK || c->ix.seedK == 0 || c->ix.seedK > (c->ix.amino ? 7u : 16u)) return false;
   } else {
@@ -812,13 +815,15 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     return r;
   };
   // 12-byte records (nucleotide, at most 8 letters left of the seed table's k-mer): see sweepStep
-  const bool rec12 = !AMINO && !variable && steps <= 8 && c->sweepRecord12;
-  auto launchPass = [&](auto first, auto items, auto small, auto var, uint32_t pass) -> int {
+  const bool wide = !AMINO && (c->ix.bwtLength >= 0xFFFFFFF0ull || c->sweepWide);
+  const bool rec12 = !AMINO && !variable && !wide && steps <= 8 && c->sweepRecord12;
+  auto launchPass = [&](auto first, auto items, auto small, auto var, auto big, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
     constexpr bool VARLEN = decltype(var)::value;
-    constexpr bool REC12 = decltype(small)::value && !AMINO && !VARLEN;
-    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12, VARLEN>;
+    constexpr bool WIDE = decltype(big)::value && !AMINO;
+    constexpr bool REC12 = decltype(small)::value && !AMINO && !VARLEN && !WIDE;
+    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12, VARLEN, WIDE>;
     int grid = 0;
     if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
     const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
@@ -834,12 +839,16 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     return AWFM_GPU_OK;
   };
   auto launchPassRec = [&](auto first, auto items, uint32_t pass) -> int {
-    return rec12 ? launchPass(first, items, std::true_type(), std::false_type(), pass)
-                 : launchPass(first, items, std::false_type(), std::false_type(), pass);
+    return rec12 ? launchPass(first, items, std::true_type(), std::false_type(), std::false_type(), pass)
+                 : launchPass(first, items, std::false_type(), std::false_type(), std::false_type(), pass);
   };
   auto launchPassItems = [&](auto first, uint32_t pass) -> int {
-    if (variable)  // one instantiation per alphabet and pass kind: 4 records per thread
-      return launchPass(first, std::integral_constant<int, 4>(), std::false_type(), std::true_type(), pass);
+    // variable lengths / 64-bit positions: one instantiation per pass kind, 4 records per thread
+    constexpr auto four = std::integral_constant<int, 4>();
+    if (wide)
+      return variable ? launchPass(first, four, std::false_type(), std::true_type(), std::true_type(), pass)
+                      : launchPass(first, four, std::false_type(), std::false_type(), std::true_type(), pass);
+    if (variable) return launchPass(first, four, std::false_type(), std::true_type(), std::false_type(), pass);
     switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
       case 1: return launchPassRec(first, std::integral_constant<int, 1>(), pass);
       case 2: return launchPassRec(first, std::integral_constant<int, 2>(), pass);
@@ -859,7 +868,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     sweepIrregular<AMINO><<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, dOffsets, len, w.irregularIds, irregularCount, dCounts,
                                                          dRanges, hitsOnly);
     CU(cudaGetLastError());
-  } else if (rec12) {  // the 2-bit format has no irregular letters, but a seed range may be too wide for 12-byte records
+  } else if (rec12 || wide) {  // the 2-bit format has no irregular letters, but a seed range may be too wide for the record
     sweepIrregularBits<<<c->numSMs * 2, 256, 0, st>>>(c->ix, dLetters, len, w.irregularIds, irregularCount, dCounts, dRanges,
                                                       hitsOnly);
     CU(cudaGetLastError());
@@ -868,7 +877,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
   w.lastSteps = steps, w.lastBuckets = AMINO ? 20 : 4, w.lastQueries = n;
-  L.stats.launches += 2 + ((format == AWFM_QUERY_ASCII || rec12) ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
+  L.stats.launches += 2 + ((format == AWFM_QUERY_ASCII || rec12 || wide) ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
   return AWFM_GPU_OK;
 }
 

@@ -39,6 +39,8 @@
 #include "awfm_kernels.cuh"
 #include "awfm_sort.cuh"
 
+#include <type_traits>
+
 namespace awfm {
 
 #ifndef AWFM_SWEEP_THREADS
@@ -471,8 +473,10 @@ __device__ __forceinline__ SweepSelector sweepSelector(uint32_t letter) {
   s.any2 = letter == 2u ? 0xFFFFFFFFu : 0u;
   return s;
 }
-// C[letter] + Occ(letter, p) for letter 0..3, p < 2^32: sector read by this thread, superblock row from L1/L2
-__device__ __forceinline__ uint32_t sweepRank(const DevIndex &ix, uint32_t p, uint32_t letter, const SweepSelector &s) {
+// C[letter] + Occ(letter, p) for letter 0..3: sector read by this thread, superblock row from L1/L2.
+// Pos = uint32_t (bwtLength < 2^32) or uint64_t (WIDE passes).
+template <typename Pos>
+__device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t letter, const SweepSelector &s) {
   const uint4 *sec = ix.lines + (uint64_t)(p >> 6) * kSectorU4;
   uint4 v0, v1;
 #ifdef AWFM_NO_LDG256
@@ -485,9 +489,11 @@ __device__ __forceinline__ uint32_t sweepRank(const DevIndex &ix, uint32_t p, ui
     v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
   }
 #endif
-  const uint32_t super = __ldg(reinterpret_cast<const uint32_t *>(ix.superC) +
-                               ((uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter) * 2u);
-  const int local = (int)(p & 63u) + 1;                       // positions 0..local-1 of the sector count
+  Pos super;
+  if constexpr (sizeof(Pos) == 8) super = __ldg(ix.superC + (uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter);
+  else super = __ldg(reinterpret_cast<const uint32_t *>(ix.superC) +
+                     ((uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter) * 2u);
+  const int local = (int)((uint32_t)p & 63u) + 1;             // positions 0..local-1 of the sector count
   const uint32_t maskLo = lowBits(local), maskHi = lowBits(local - 32);
   const uint32_t lo = ((v0.z ^ s.flipHi) | s.any1) & ((v1.x ^ s.flipHi) | s.any2) & (v0.x | s.any0) & maskLo;
   const uint32_t hi = ((v0.w ^ s.flipHi) | s.any1) & ((v1.y ^ s.flipHi) | s.any2) & (v0.y | s.any0) & maskHi;
@@ -545,8 +551,11 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // slower than the 64 registers / 4 CTAs the compiler picks on its own, profiles/r02_sweep_probe.jsonl)
 // VARLEN (sweepPackVar's payloads, marker bit above the last remaining letter): a record is finished when its payload
 // has shrunk to 1; `steps` is then the largest number of steps any record of the batch can still have to do.
-template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false>
-__global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
+// WIDE (nucleotide indexes of 2^32 .. 2^40 positions): 64-bit positions in registers; a record is still 16 bytes —
+// {sp bits 0-31, sp bits 32-39 | range width << 8, id, letters} — because a range only narrows from step to step: a
+// query whose SEED range is wider than 2^24 - 2 leaves for the irregular list once, in the first pass.
+template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false, bool WIDE = false>
+__global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
@@ -555,6 +564,8 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
               bool rangesOfHitsOnly /* ranges only of queries whose final range is non-empty (locate) */) {
   static_assert(!(REC12 && AMINO), "12-byte records are a nucleotide format");
   static_assert(!(REC12 && VARLEN), "12-byte records hold 16 bits of letters, no room for the marker bit");
+  static_assert(!(WIDE && (AMINO || REC12)), "64-bit positions: nucleotide, 16-byte records");
+  using Pos = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   constexpr uint32_t kLetterMask = (1u << LB) - 1u;
@@ -611,7 +622,8 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
     if ((uint64_t)tile * kSweepTile >= total) break;
     if (threadIdx.x == 0) nextTile = atomicAdd(out.count + 31, 1u);
     const uint32_t base = tile * kSweepTile;
-    uint32_t sp[kSweepItems], ep[kSweepItems], id[kSweepItems], rest[kSweepItems], bucket[kSweepItems];
+    Pos sp[kSweepItems], ep[kSweepItems];
+    uint32_t id[kSweepItems], rest[kSweepItems], bucket[kSweepItems];
     // Every load of a stage is issued for all items before anything waits on it (no branches around the loads:
     // out-of-range items read a clamped, valid address and are disabled afterwards).
     // ---- stage A: this tile's records / (key, payload) pairs ----
@@ -655,8 +667,13 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
           rest[it] = w >> 16;
         } else {
           const uint4 rec = __ldg((ge2 ? in1 : in0) + slot);
-          sp[it] = rec.x;
-          ep[it] = rec.x + rec.y;
+          if constexpr (WIDE) {
+            sp[it] = (uint64_t)rec.x | ((uint64_t)(rec.y & 0xFFu) << 32);
+            ep[it] = sp[it] + (rec.y >> 8);
+          } else {
+            sp[it] = rec.x;
+            ep[it] = rec.x + rec.y;
+          }
           id[it] = rec.z;
           rest[it] = rec.w;
         }
@@ -731,7 +748,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
             ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
           id[it] = kSweepNoId;
         }
-        if (REC12 && id[it] != kSweepNoId && e64[it] - s64[it] >= 0xFFFFull) {  // width does not fit the 16-bit field
+        if ((REC12 || WIDE) && id[it] != kSweepNoId && e64[it] - s64[it] >= (WIDE ? 0xFFFFFFull : 0xFFFFull)) {  // width does not fit its field
           irregularIds[atomicAdd(irregularCount, 1u)] = id[it];
           id[it] = kSweepNoId;
         }
@@ -741,7 +758,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
             ranges[id[it]] = make_uint4((uint32_t)s64[it], (uint32_t)(s64[it] >> 32), (uint32_t)e64[it], (uint32_t)(e64[it] >> 32));
           id[it] = kSweepNoId;
         }
-        if (id[it] != kSweepNoId) sp[it] = (uint32_t)s64[it], ep[it] = (uint32_t)e64[it];
+        if (id[it] != kSweepNoId) sp[it] = (Pos)s64[it], ep[it] = (Pos)e64[it];
       }
     }
 #pragma unroll
@@ -755,7 +772,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
     if (steps > 0) {
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kLineU4));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.lines + (uint64_t)((sp[it] - 1u) >> 6) * kLineU4));  // (Pos arithmetic)
     }
     // ---- stage C: the LF steps (src/AwFmSearch.c:42-103) ----
 #pragma unroll
@@ -763,29 +780,33 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
       const uint32_t letter = AMINO ? min(rest[it] & kLetterMask, NB - 1u) : (rest[it] & kLetterMask);
       bool valid = id[it] != kSweepNoId;
       if (steps > 0) {
-        uint32_t nsp, nep;
+        Pos nsp, nep;
         if constexpr (AMINO) {
           const AminoSweepSelector sel = aminoSweepSelector(codeCareSh[letter]);
           nsp = aminoSweepRank(ix, sp[it] - 1u, letter, sel);
           nep = aminoSweepRank(ix, ep[it], letter, sel) - 1u;
         } else {
           const SweepSelector sel = sweepSelector(letter);
-          nsp = sweepRank(ix, sp[it] - 1u, letter, sel);
-          nep = sweepRank(ix, ep[it], letter, sel) - 1u;
+          nsp = sweepRank<Pos>(ix, sp[it] - 1u, letter, sel);
+          nep = sweepRank<Pos>(ix, ep[it], letter, sel) - 1u;
         }
         sp[it] = nsp;
         ep[it] = nep;
         rest[it] >>= LB;
         if (valid && nep == nsp - 1u) {  // ep == sp - 1 <=> empty: the search stops here (src/AwFmParallelSearch.c:279-311)
           valid = false;
-          if (ranges && !rangesOfHitsOnly) ranges[id[it]] = make_uint4(nsp, 0u, nep, nep == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u);
+          if (ranges && !rangesOfHitsOnly) {
+            if constexpr (WIDE) ranges[id[it]] = make_uint4((uint32_t)nsp, (uint32_t)(nsp >> 32), (uint32_t)nep, (uint32_t)(nep >> 32));
+            else ranges[id[it]] = make_uint4(nsp, 0u, nep, nep == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u);
+          }
         }
       }
       bucket[it] = NB;  // no output
       if (valid) {
         const bool last = VARLEN ? (steps <= 1 || rest[it] == 1u) : steps <= 1;
-        if (last && ranges) ranges[id[it]] = make_uint4(sp[it], 0u, ep[it], 0u);
-        if (last) counts[id[it]] = ep[it] - sp[it] + 1u;
+        if (last && ranges) ranges[id[it]] = make_uint4((uint32_t)sp[it], (uint32_t)((uint64_t)sp[it] >> 32), (uint32_t)ep[it],
+                                                        (uint32_t)((uint64_t)ep[it] >> 32));
+        if (last) counts[id[it]] = (uint32_t)(ep[it] - sp[it] + 1u);
         else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
       }
     }
@@ -835,8 +856,10 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && kSweepThreads == 256
         uint4 *dst = AMINO ? out.arr[b >> 1] : ((b & 2u) ? out1 : out0);
         const uint32_t slot = (b & 1u) ? outLast - r : r;
         if constexpr (REC12) {
-          reinterpret_cast<uint2 *>(dst)[slot] = make_uint2(sp[it], id[it]);
-          reinterpret_cast<uint32_t *>(reinterpret_cast<uint2 *>(dst) + out.cap)[slot] = (ep[it] - sp[it]) | (rest[it] << 16);
+          reinterpret_cast<uint2 *>(dst)[slot] = make_uint2((uint32_t)sp[it], id[it]);
+          reinterpret_cast<uint32_t *>(reinterpret_cast<uint2 *>(dst) + out.cap)[slot] = (uint32_t)(ep[it] - sp[it]) | (rest[it] << 16);
+        } else if constexpr (WIDE) {
+          dst[slot] = make_uint4((uint32_t)sp[it], (uint32_t)(sp[it] >> 32) | ((uint32_t)(ep[it] - sp[it]) << 8), id[it], rest[it]);
         } else {
           dst[slot] = make_uint4(sp[it], ep[it] - sp[it], id[it], rest[it]);
         }

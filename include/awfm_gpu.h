@@ -143,7 +143,10 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * smaller records measured no faster, profiles/r02_sweep_probe.jsonl), "sweep_variable" (1, the default: variable-length
  * ASCII batches — an offsets array — take the sweep too, every record carrying its own length as a marker bit above its
  * remaining letters; queries shorter than the seed k-mer or with more than 15 (amino: 6) letters left of it are answered
- * by the generic per-query search inside the same call; 0: such batches always take the tile kernel). */
+ * by the generic per-query search inside the same call; 0: such batches always take the tile kernel), "sweep_wide" (0, the
+ * default: 64-bit positions only for nucleotide indexes of 2^32 .. 2^40 positions, where they are needed; 1: always —
+ * cross-check on small indexes.  Records stay 16 bytes: 40 bits of position, 24 bits of range width; a query whose seed
+ * range is wider than 2^24 - 2 is answered by the generic per-query search). */
 int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *ctx, const char *key, int64_t value);
 /* Device time of every stage of the most recent sweep count call made with "sweep_profile" = 1, in launch order:
  * clear + pack, radix sort, first pass (seed entry + LF step 1), one entry per further pass, irregular queries.

@@ -9,7 +9,8 @@ Run with -m gpu on a B200."""
 import numpy as np
 import pytest
 
-from avxwindowfmindex_b200 import GpuIndex, IndexArrays, abi
+from avxwindowfmindex_b200 import GpuGroup, GpuIndex, IndexArrays, abi, pack_queries_bits
+from avxwindowfmindex_b200.search import QUERY_2BIT
 from avxwindowfmindex_b200.index import aligned_empty, sa_num_samples
 from oracle import harness
 
@@ -155,6 +156,7 @@ def big_garbage_index(num_blocks, pattern_blocks, seed_k, rng):
         full, rest = divmod(num_blocks, pattern_blocks)
         totals.append(int(counts.sum()) * full + int(counts[:rest].sum()))
     prefix = np.zeros(6, np.uint64)
+    prefix[0] = 1  # the sentinel sorts first: no range of a real index starts at position 0 (sp - 1 is ranked)
     for c in range(1, 5):
         prefix[c] = prefix[c - 1] + np.uint64(totals[c - 1])
     prefix[5] = n
@@ -164,6 +166,9 @@ def big_garbage_index(num_blocks, pattern_blocks, seed_k, rng):
     sp[::4] = np.uint64(1 << 32) - rng.integers(0, 1500, len(sp[::4])).astype(np.uint64)   # ranges across 2^32
     sp[1::4] = np.uint64(1 << 32) + rng.integers(0, n - (1 << 32) - 4000, len(sp[1::4])).astype(np.uint64)  # above it
     ep = sp + rng.integers(0, 3000, num_seeds).astype(np.uint64)
+    ep[5::64] = np.minimum(sp[5::64] + np.uint64(20_000_000), np.uint64(n - 1))  # wider than a wide record's 24-bit field
+    sp[6::64] = np.minimum(sp[6::64], np.uint64(n - (1 << 25)))
+    ep[6::64] = sp[6::64] + np.uint64((1 << 24) - 2)                              # the widest range that still fits
     seeds = np.stack([sp, ep], axis=1)
     seeds[::17] = seeds[::17][:, ::-1] + np.array([1, 0], np.uint64)  # some stored invalid pairs (sp > ep)
     return IndexArrays(abi.AwFmAlphabetDna, seed_k, 8, n, blocks, prefix, seeds, None)
@@ -171,9 +176,10 @@ def big_garbage_index(num_blocks, pattern_blocks, seed_k, rng):
 
 def test_positions_beyond_two_to_the_32():
     """bwtLength = 1.25 * 2^32 (a two-strand human genome is 6.2 G positions): every 64-bit path of the upload-time
-    re-layout (sector counts relative to 2^16-position superblocks, 64-bit superblock rows) and of the tile kernels,
-    on ranges below, above and across position 2^32, bit-exact against the oracle.  The sweep (32-bit positions) must
-    decline such an index."""
+    re-layout (sector counts relative to 2^16-position superblocks, 64-bit superblock rows), of the tile kernels and of
+    the sweep's wide passes (40-bit positions + 24-bit widths in 16-byte records, seed ranges too wide for that taking the
+    per-query search), on ranges below, above and across position 2^32, bit-exact against the oracle; fixed-length ASCII,
+    2-bit packed and variable-length batches."""
     rng = np.random.default_rng(2032)
     k = 5
     num_blocks = (5 << 30) // 256 + 777
@@ -190,6 +196,7 @@ def test_positions_beyond_two_to_the_32():
         batches.append((np.ascontiguousarray(alphabet[rng.choice(4, (20000, length), p=p)].reshape(-1)), length))
     oracle = harness.Oracle(arrays)
     gpu = GpuIndex(arrays)
+    group = GpuGroup(indexes=[gpu])
     seen_high = 0
     for letters, length in batches:
         o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
@@ -201,7 +208,24 @@ def test_positions_beyond_two_to_the_32():
             assert np.array_equal(counts, o_counts), (length, variant, lpq)
         gpu.set_tuning(sweep_min_queries=1, sweep_profile=1, count_variant=1)
         counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
-        assert not gpu.sweep_stage_ms(), "the 32-bit sweep took an index with more than 2^32 positions"
-        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges)
+        assert gpu.sweep_stage_ms(), "the batch did not take the sweep path"
+        assert np.array_equal(ranges, o_ranges), (length, "sweep")
+        assert np.array_equal(counts, o_counts), (length, "sweep")
+        if b"N" not in letters.tobytes():
+            packed = pack_queries_bits(letters, length)
+            assert np.array_equal(group.count(packed, QUERY_2BIT, fixed_len=length), o_counts), (length, "2bit")
+            assert gpu.sweep_stage_ms()
     assert seen_high > 1000, "the batches never reached positions above 2^32"
+    # variable lengths through the wide passes: the three random batches cut to lengths k-1 .. their own
+    for letters, length in batches[1:]:
+        rows = letters.reshape(-1, length)
+        lengths = rng.integers(k - 1, length + 1, len(rows))
+        offsets = np.zeros(len(rows) + 1, np.uint64)
+        offsets[1:] = np.cumsum(lengths)
+        var = np.concatenate([rows[i, length - lengths[i]:] for i in range(len(rows))])
+        o_counts, o_ranges, _ = oracle.count(var, offsets)
+        counts, ranges = gpu.count(var, offsets, want_ranges=True)
+        assert gpu.sweep_stage_ms(), "the variable-length batch did not take the sweep path"
+        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (length, "variable")
+    group.close()
     gpu.close()

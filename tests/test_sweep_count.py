@@ -101,11 +101,13 @@ def test_sweep_matches_oracle(small_indexes, name):
             counts = gpu.count(letters, fixed_len=length)
             assert np.array_equal(counts, o_counts), (name, length, num, bits, local, items)
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
-        # range output: every query's final (sp, ep) as the reference leaves it, incl. the pair a dying search stops at
-        gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=4, sweep_profile=1)
-        counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
-        assert gpu.sweep_stage_ms(), "range output did not take the sweep path"
-        assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num)
+        # range output: every query's final (sp, ep) as the reference leaves it, incl. the pair a dying search stops at;
+        # with 32-bit positions and with the 64-bit-position passes an index beyond 2^32 positions takes
+        for wide in (0, 1):
+            gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=4, sweep_profile=1, sweep_wide=wide)
+            counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+            assert gpu.sweep_stage_ms(), "range output did not take the sweep path"
+            assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num, wide)
         gpu.set_tuning(sweep_min_queries=-1)
         assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
     gpu.close()
@@ -156,15 +158,16 @@ def test_sweep_variable_lengths(small_indexes, name):
                               (300, 1, max(k - 1, 1), 4), (2500, k + room, k + room, 5), (20000, k, k + 4, 6)):
         letters, offsets = variable_batch(b, num, seed=seed * 131 + num, lo=lo, hi=hi)
         o_counts, o_ranges, _ = oracle.count(letters, offsets)
-        for bits, local, own, max_batch in ((32, -1, 1, 1 << 27), (16, 0, 0, 1 << 27), (3, 5, 1, 1024), (32, 8, 1, 4096)):
+        for bits, local, own, max_batch, wide in ((32, -1, 1, 1 << 27, 0), (16, 0, 0, 1 << 27, 0), (3, 5, 1, 1024, 0),
+                                                  (32, 8, 1, 4096, 0), (32, -1, 1, 1 << 27, 1)):
             gpu.set_tuning(sweep_min_queries=1, sweep_variable=1, sweep_sort_bits=bits, sweep_local_bits=local,
-                           sweep_own_sort=own, sweep_max_batch=max_batch, sweep_profile=1)
+                           sweep_own_sort=own, sweep_max_batch=max_batch, sweep_profile=1, sweep_wide=wide)
             counts, ranges = gpu.count(letters, offsets, want_ranges=True)
             assert len(gpu.sweep_stage_ms()) == 3 + room, "the batch did not take the sweep path"
             assert np.array_equal(counts, o_counts), (name, num, lo, hi, bits, local, own, max_batch)
             assert np.array_equal(ranges, o_ranges), (name, num, lo, hi, bits, local, own, max_batch)
             assert np.array_equal(gpu.count(letters, offsets), o_counts)
-        gpu.set_tuning(sweep_variable=0, sweep_max_batch=1 << 27)
+        gpu.set_tuning(sweep_variable=0, sweep_max_batch=1 << 27, sweep_wide=0)
         counts, ranges = gpu.count(letters, offsets, want_ranges=True)
         assert not gpu.sweep_stage_ms(), "sweep_variable=0 still took the sweep path"
         assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges)

@@ -476,7 +476,12 @@ __device__ __forceinline__ SweepSelector sweepSelector(uint32_t letter) {
 // C[letter] + Occ(letter, p) for letter 0..3: sector read by this thread, superblock row from L1/L2.
 // Pos = uint32_t (bwtLength < 2^32) or uint64_t (WIDE passes).
 template <typename Pos>
-__device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t letter, const SweepSelector &s) {
+__device__ __forceinline__ Pos sweepSuper(const DevIndex &ix, uint64_t row, uint32_t letter) {
+  if constexpr (sizeof(Pos) == 8) return __ldg(ix.superC + row * kSectorSuperStride + letter);
+  else return __ldg(reinterpret_cast<const uint32_t *>(ix.superC) + (row * kSectorSuperStride + letter) * 2u);
+}
+template <typename Pos>  // `super` = sweepSuper(row of p)
+__device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t letter, const SweepSelector &s, Pos super) {
   const uint4 *sec = ix.lines + (uint64_t)(p >> 6) * kSectorU4;
   uint4 v0, v1;
 #ifdef AWFM_NO_LDG256
@@ -489,10 +494,6 @@ __device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t let
     v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
   }
 #endif
-  Pos super;
-  if constexpr (sizeof(Pos) == 8) super = __ldg(ix.superC + (uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter);
-  else super = __ldg(reinterpret_cast<const uint32_t *>(ix.superC) +
-                     ((uint64_t)(p >> kSectorSuperShift) * kSectorSuperStride + letter) * 2u);
   const int local = (int)((uint32_t)p & 63u) + 1;             // positions 0..local-1 of the sector count
   const uint32_t maskLo = lowBits(local), maskHi = lowBits(local - 32);
   const uint32_t lo = ((v0.z ^ s.flipHi) | s.any1) & ((v1.x ^ s.flipHi) | s.any2) & (v0.x | s.any0) & maskLo;
@@ -787,8 +788,17 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
           nep = aminoSweepRank(ix, ep[it], letter, sel) - 1u;
         } else {
           const SweepSelector sel = sweepSelector(letter);
-          nsp = sweepRank<Pos>(ix, sp[it] - 1u, letter, sel);
-          nep = sweepRank<Pos>(ix, ep[it], letter, sel) - 1u;
+          // sp-1 and ep nearly always lie in the same 2^16-position superblock: its row is read once
+          const Pos pa = sp[it] - 1u, pb = ep[it];
+          const uint64_t rowA = (uint64_t)(pa >> kSectorSuperShift), rowB = (uint64_t)(pb >> kSectorSuperShift);
+          const Pos superA = sweepSuper<Pos>(ix, rowA, letter);
+#ifdef AWFM_SWEEP_TWO_SUPER
+          const Pos superB = sweepSuper<Pos>(ix, rowB, letter);
+#else
+          const Pos superB = rowB == rowA ? superA : sweepSuper<Pos>(ix, rowB, letter);
+#endif
+          nsp = sweepRank<Pos>(ix, pa, letter, sel, superA);
+          nep = sweepRank<Pos>(ix, pb, letter, sel, superB) - 1u;
         }
         sp[it] = nsp;
         ep[it] = nep;

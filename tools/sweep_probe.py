@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--amino", action="store_true", help="cfg 4 shape: pass --bp 1000000000 --queries 50000000 --kmer 8 --seed-k 5")
     ap.add_argument("--own-sort", type=str, default="1,0", help="ordering step: 1 = csrc/awfm_sort.cuh, 0 = CUB")
     ap.add_argument("--variable", type=str, default="", help="lo,hi: also time a variable-length batch of --queries queries with lengths uniform in lo..hi (tile kernel vs sweep)")
+    ap.add_argument("--wide", action="store_true", help="also time the 64-bit-position passes (sweep_wide=1) on the same batch")
     ap.add_argument("--nvtx", action="store_true", help="wrap one extra sweep call in the NVTX range 'sweepcall' (for ncu --nvtx)")
     args = ap.parse_args()
     lib = capi.load()
@@ -83,6 +84,14 @@ def main():
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
               "device_bytes": gpu.device_bytes()})
+    if args.wide:
+        gpu.set_tuning(sweep_sort_bits=32, sweep_items=4, sweep_local_bits=-1, sweep_own_sort=1, sweep_wide=1)
+        d_counts.fill_(-1)
+        ms = timed(n, d_counts)
+        emit({"variant": "sweep_wide", "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
+              "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref))})
+        gpu.set_tuning(sweep_wide=0)
     if args.nvtx:
         gpu.set_tuning(sweep_sort_bits=32, sweep_items=4, sweep_profile=0)
         torch.cuda.synchronize()

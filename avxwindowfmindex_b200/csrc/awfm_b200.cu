@@ -638,11 +638,11 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
   if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
   // automatic: pays off once the batch puts about one query on every second 128-B line of the index (measured
   // break-even at 3.1 Gbp: 6 M queries for 16- and 20-mers alike, profiles/r02_sweep_probe.jsonl; round 1's slower
-  // sweep: 12 M).  With a derived deep seed table most of the LF steps the sweep would stream for are gone already and
-  // the tile kernel is the faster of the two.
-  if (c->ix.deepSeedK && len >= c->ix.deepSeedK) return false;
-  // (with range output every query also pays a scattered 16-B store: the break-even stays where round 1 measured it)
-  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : dRanges ? 8 : 9));
+  // sweep: 12 M).
+  // (with range output every query also pays a scattered 16-B store: the break-even stays where round 1 measured it;
+  // with a derived deep seed table the tile kernel has fewer steps left to pay for: twice the batch)
+  const bool deepActive = !dOffsets && c->ix.deepSeedK && len >= c->ix.deepSeedK;
+  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : dRanges ? 8 : 9)) << (deepActive ? 1 : 0);
 }
 
 static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
@@ -715,8 +715,18 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     const int radixPasses = (endBit - wantLocal + 7) / 8;
     wantLocal = std::max(0, endBit - 8 * radixPasses);
   }
-  const uint32_t localBits = (uint32_t)std::min({wantLocal, endBit, 8});
-  const int beginBit = std::max(0, endBit - std::min(c->sweepSortBits, endBit - (int)localBits));
+  uint32_t localBits = (uint32_t)std::min({wantLocal, endBit, 8});
+  int beginBit = std::max(0, endBit - std::min(c->sweepSortBits, endBit - (int)localBits));
+  // Seed tables deeper than 2^24 entries (k = 13..16, the index's own or a derived one): the two bucket passes order
+  // the top 16 key bits, the tiles of the first pass the 8 below them, and the lowest endBit - 24 bits stay unordered —
+  // neighbouring seed entries are neighbouring ranges of the BWT, so that costs no locality worth a third pass (or
+  // CUB's four: 2.5 ms instead of 1.3 per 100 M pairs).
+  uint32_t localShift = 0;
+  if (c->sweepLocalBits < 0 && c->sweepSortBits >= 32 && c->sweepOwnSort && endBit > 3 * kSortMaxDigitBits) {
+    localBits = kSortMaxDigitBits;
+    localShift = (uint32_t)endBit - 3 * kSortMaxDigitBits;
+    beginBit = endBit - 2 * kSortMaxDigitBits;
+  }
   const int sortedBits = endBit - beginBit;
   // our own two bucket passes (awfm_sort.cuh) order up to 16 bits; deeper seed tables go through CUB
   const bool ownSort = c->sweepOwnSort && sortedBits >= 1 && sortedBits <= 2 * kSortMaxDigitBits;
@@ -830,7 +840,8 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tile - 1) / tile);
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
-                                         steps, localBits, dCounts, dRanges, w.irregularIds, irregularCount, hitsOnly);
+                                         steps, localBits | (localShift << 8), dCounts, dRanges, w.irregularIds, irregularCount,
+                                         hitsOnly);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
                                          gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges, w.irregularIds, irregularCount,

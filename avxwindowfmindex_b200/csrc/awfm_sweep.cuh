@@ -687,16 +687,17 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
     //      warp's 32 consecutive pairs touch a handful of neighbouring lines instead of 32 scattered ones.  Order is
     //      a locality matter only — the result of a query does not depend on it. ----
     if constexpr (FIRST) {
-      if (localBits) {  // uniform
+      // (`localBits` carries two fields: bits 0-7 = how many key bits the tile orders, bits 8-15 = the lowest of them)
+      if (const uint32_t lb = localBits & 0xFFu, ls = localBits >> 8; lb) {  // uniform
         uint32_t val32[kSweepItems][2], lk[kSweepItems], pos[kSweepItems];
-        const uint32_t firstUpper = __ldg(keys + base) >> localBits;
+        const uint32_t firstUpper = __ldg(keys + base) >> (ls + lb);
         for (uint32_t b = threadIdx.x; b < 1024; b += kSweepThreads) localBins[b] = 0;
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < kSweepItems; it++) {
-          const uint32_t delta = min((key[it] >> localBits) - firstUpper, 3u);
+          const uint32_t delta = min((key[it] >> (ls + lb)) - firstUpper, 3u);
           lk[it] = base + it * kSweepThreads + threadIdx.x >= total  // padding of the last tile goes to the end
-                       ? 1023u : ((delta << localBits) | (key[it] & ((1u << localBits) - 1u)));
+                       ? 1023u : ((delta << lb) | ((key[it] >> ls) & ((1u << lb) - 1u)));
           pos[it] = atomicAdd(&localBins[lk[it]], 1u);
           val32[it][0] = id[it];
           val32[it][1] = rest[it];

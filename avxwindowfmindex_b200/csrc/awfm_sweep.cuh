@@ -1,5 +1,7 @@
-// awfm_sweep.cuh — the "sweep" count path for LARGE batches of fixed-length queries (sm_100a).  Described for the
-// nucleotide alphabet; amino indexes take the same path with 20 buckets and 5-bit letters (SweepAlphabet<true>).
+// awfm_sweep.cuh — the "sweep" count path for LARGE batches of queries (sm_100a).  Described for fixed-length
+// batches of the nucleotide alphabet; amino indexes take the same path with 20 buckets and 5-bit letters
+// (SweepAlphabet<true>), variable-length batches with a marker bit in every record (sweepPackVar, VARLEN), nucleotide
+// indexes of 2^32 .. 2^40 positions with 64-bit positions in registers and 40 + 24 bits in the record (WIDE).
 //
 // The tile kernels of awfm_kernels.cuh pay one random DRAM line per rank: 1 + 5.64 lines per 20-mer at 3.1 Gbp, and
 // the memory system delivers ~42 G random lines/s whatever their size (profiles/r01_granularity_probe.jsonl), so they
@@ -12,9 +14,10 @@
 //   sweepPack*   thread per query: seed-table index of the last k letters (src/AwFmKmerTable.c:21-51) as the sort key,
 //                the remaining len-k letters packed 2 bits each (next letter to prepend in the low bits) + query id as
 //                the payload.  Queries holding anything but A/C/G/T(/U) go to a side list (sweepIrregular).
-//   radix sort   CUB (stable), on all key bits but the lowest few: the order has to be exact at warp granularity —
-//                32 consecutive queries should rank within a handful of neighbouring lines — or the L1 data pipe pays
-//                one wavefront per lane (measured: DESIGN.md section 3, dropped variants).
+//   ordering     two most-significant-digit-first bucket passes (awfm_sort.cuh; CUB's radix sort as cross-check) on
+//                the top 16 key bits, the first pass's tiles order the 8 bits below them: the order has to be exact at
+//                warp granularity — 32 consecutive queries should rank within a handful of neighbouring lines — or
+//                the L1 data pipe pays one wavefront per lane (measured: DESIGN.md section 3, dropped variants).
 //   sweepStep<FIRST>   finishes the order on those low bits inside each tile (shared-memory counting sort), reads the
 //                seed entry (src/AwFmParallelSearch.c:222-271), does the first LF step (src/AwFmSearch.c:42-103) and
 //                appends the still-valid query as a 16-B record {sp, ep-sp, id, letters} to the bucket of the letter
@@ -33,8 +36,10 @@
 // being gathered line by line, and all other traffic (keys, records) is sequential.  No spin-waits anywhere.
 //
 // Exactness: same seed entries, same ranks (sectorRank), same stop rule; only the processing order differs, and the
-// result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels):
-// variable-length batches, bwtLength > 2^32, len - k > 16 (amino: 6), k > 16 (amino: 7).
+// result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels): fixed-length
+// batches with len - k > 16 (amino: 6), k > 16 (amino: 7), amino indexes beyond 2^32 positions, nucleotide ones beyond
+// 2^40; inside a variable-length batch, queries shorter than k or with more than 15 (amino: 6) letters left of the seed
+// are answered by sweepIrregular within the same call.
 #pragma once
 #include "awfm_kernels.cuh"
 #include "awfm_sort.cuh"

@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--amino-queries", type=int, default=50_000_000)
     ap.add_argument("--cfg5-records", type=int, default=10_000)
     ap.add_argument("--cfg5-queries", type=int, default=10_000_000, help="cfg 5: sampled 32-mers per GPU")
-    ap.add_argument("--skip", default="", help="comma list of legs to skip: cfg1,cfg3,cfg4,cfg5,fanout,derived,dropin,packed,cpu")
+    ap.add_argument("--skip", default="", help="comma list of legs to skip: cfg1,cfg3,cfg4,cfg5,fanout,derived,variable,dropin,packed,cpu")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -1137,11 +1137,24 @@ def run_ours(args):
                 walk = lambda: gpu.locate_device(d_lr.data_ptr(), d_lh.data_ptr(), nl, 0, hits, d_lp.data_ptr(), stream.cuda_stream)  # noqa: E731
                 walk()
                 plain = d_lp.clone()
+                if args.derived_seed_depth > args.seed_k + 2:  # a modest table first: 4^(k+2) x 8 B (2.1 GB at k = 12)
+                    build14_ms = gpu.extend_seed_table(args.seed_k + 2)
+                    bytes14 = gpu.device_bytes()
+                    dms14 = env.event_ms(call, reps=3)
+                    counts14 = d_counts[:1_000_000].cpu().numpy().astype(np.uint32)
                 build_seed_ms = gpu.extend_seed_table(args.derived_seed_depth)
                 dms = env.event_ms(call, reps=3)
                 derived_counts = d_counts[:1_000_000].cpu().numpy().astype(np.uint32)
+                gpu.set_tuning(sweep_min_queries=-1)
+                dms_tile = env.event_ms(call, reps=3)
+                gpu.set_tuning(sweep_min_queries=0 if args.count_path == "auto" else (1 if args.count_path == "sweep" else -1))
                 derived["seed_table"] = {"depth": args.derived_seed_depth, "build_ms": build_seed_ms, "count_ms": dms,
-                                         "count_queries_per_s": n / dms * 1e3}
+                                         "count_queries_per_s": n / dms * 1e3, "tile_kernel_ms": dms_tile,
+                                         "tile_kernel_queries_per_s": n / dms_tile * 1e3}
+                if args.derived_seed_depth > args.seed_k + 2:
+                    derived["seed_table_modest"] = {"depth": args.seed_k + 2, "build_ms": build14_ms, "count_ms": dms14,
+                                                    "count_queries_per_s": n / dms14 * 1e3, "device_bytes_with_it": bytes14,
+                                                    "_counts": counts14}
                 build_sa_ms = gpu.densify_suffix_array(1)
                 wms = env.event_ms(walk)
                 derived["suffix_array"] = {"sa_ratio": 1, "build_ms": build_sa_ms, "walk_ms": wms,
@@ -1152,15 +1165,64 @@ def run_ours(args):
                 gpu.densify_suffix_array(0)
                 call()  # d_counts again from the plain path (what the parity sample below checks)
                 torch.cuda.synchronize()
-                derived["seed_table"]["bit_exact_vs_plain_path"] = bool(
-                    np.array_equal(derived_counts, d_counts[:1_000_000].cpu().numpy().astype(np.uint32)))
+                plain_counts = d_counts[:1_000_000].cpu().numpy().astype(np.uint32)
+                derived["seed_table"]["bit_exact_vs_plain_path"] = bool(np.array_equal(derived_counts, plain_counts))
+                modest_ok = True
+                if "seed_table_modest" in derived:
+                    modest_ok = bool(np.array_equal(derived["seed_table_modest"].pop("_counts"), plain_counts))
+                    derived["seed_table_modest"]["bit_exact_vs_plain_path"] = modest_ok
                 result["derived_structures"] = derived
-                if not (derived["seed_table"]["bit_exact_vs_plain_path"] and derived["suffix_array"]["bit_exact_vs_plain_walk"]):
+                if not (derived["seed_table"]["bit_exact_vs_plain_path"] and modest_ok and
+                        derived["suffix_array"]["bit_exact_vs_plain_walk"]):
                     raise SystemExit("PARITY FAILURE: derived structures change results")
                 del d_lc, d_lr, d_lh, d_lp, plain
             except capi.AwfmGpuError as e:  # e.g. not enough free HBM for the depth asked for
                 result["derived_structures"] = {"error": str(e)}
         del d_lq
+        torch.cuda.empty_cache()
+
+    # ---- variable-length batch (letters + offsets, lengths uniform in kmer-4 .. kmer+7): sweep with marker-bit payloads
+    #      vs the tile kernel, sample checked against the oracle ----
+    if world == 1 and "variable" not in args.skip:
+        nv = min(n, 50_000_000)
+        lo_len, hi_len = max(args.seed_k, L - 4), L + 7
+        g = torch.Generator(device=dev).manual_seed(7)
+        lengths = torch.randint(lo_len, hi_len + 1, (nv,), device=dev, generator=g, dtype=torch.int64)
+        d_voff = torch.zeros(nv + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lengths, 0, out=d_voff[1:])
+        del lengths
+        total_letters = int(d_voff[-1].item())
+        d_var = synth_device(env, total_letters, synth.QUERY_SEED + 5)
+        d_vc = torch.zeros(nv, dtype=torch.int32, device=dev)
+        vcall = lambda: gpu.count_device(d_var.data_ptr(), d_voff.data_ptr(), 0, nv, d_vc.data_ptr(), None, stream.cuda_stream)  # noqa: E731
+        v_ms = env.event_ms(vcall, reps=3)
+        gpu.set_tuning(sweep_profile=1)
+        vcall()
+        torch.cuda.synchronize()
+        v_stages = gpu.sweep_stage_ms()
+        gpu.set_tuning(sweep_profile=0)
+        sweep_counts = d_vc.clone()
+        gpu.set_tuning(sweep_min_queries=-1)
+        v_tile_ms = env.event_ms(vcall, reps=3)
+        gpu.set_tuning(sweep_min_queries=0 if args.count_path == "auto" else (1 if args.count_path == "sweep" else -1))
+        var = {"workload": f"{nv} queries of {lo_len}..{hi_len} letters (uniform), {total_letters} letters + {nv + 1} offsets, device-resident",
+               "ms": v_ms, "queries_per_s": nv / v_ms * 1e3, "path": "sweep (marker-bit payloads)" if v_stages else "tile kernel",
+               "stages_ms": [round(x, 3) for x in v_stages], "tile_kernel_ms": v_tile_ms,
+               "tile_kernel_queries_per_s": nv / v_tile_ms * 1e3,
+               "sweep_equal_to_tile_kernel_all_queries": bool(torch.equal(sweep_counts, d_vc))}
+        if arrays is not None:
+            vs = min(nv, 500_000)
+            h_off = d_voff[: vs + 1].cpu().numpy().astype(np.uint64)
+            h_let = d_var[: int(h_off[-1])].cpu().numpy()
+            o_counts, _, _ = harness.Oracle(arrays).count(h_let, h_off, threads=env.cores)
+            var["parity_sample"] = {"queries": vs, "bit_exact_vs_oracle":
+                                    bool(np.array_equal(o_counts, sweep_counts[:vs].cpu().numpy().astype(np.uint32)))}
+            if not var["parity_sample"]["bit_exact_vs_oracle"]:
+                raise SystemExit("PARITY FAILURE: variable-length counts differ from the oracle")
+        if not var["sweep_equal_to_tile_kernel_all_queries"]:
+            raise SystemExit("PARITY FAILURE: variable-length sweep and tile kernel disagree")
+        result["variable_length"] = var
+        del d_var, d_voff, d_vc, sweep_counts
         torch.cuda.empty_cache()
 
     # ---- parity on a sample + exact algorithmic bytes from the oracle (checker, not the product) ----

@@ -22,6 +22,7 @@ class DeviceBuiltIndex:
         ties, ms = C.c_uint64(), C.c_double()
         capi.check(self.lib.awfm_gpu_built_view(handle, C.byref(self._view), C.byref(ties), C.byref(ms)))
         self.tie_suffixes = int(ties.value)
+        self.tie_rounds = int(self.lib.awfm_gpu_built_tie_rounds(handle))
         self.build_ms = float(ms.value)
 
     @classmethod

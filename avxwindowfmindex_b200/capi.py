@@ -17,7 +17,7 @@ GPU_SYMBOLS = [
     "awfm_gpu_count_host", "awfm_gpu_locate_host", "awfm_gpu_count_device", "awfm_gpu_scan_ranges_device",
     "awfm_gpu_locate_device", "awfm_gpu_search_list_count", "awfm_gpu_search_list_locate",
     "awfm_gpu_gather_bandwidth", "awfm_gpu_build_index", "awfm_gpu_build_index_host", "awfm_gpu_built_view",
-    "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
+    "awfm_gpu_built_download", "awfm_gpu_built_destroy", "awfm_gpu_built_tie_rounds", "awfm_gpu_synth_letters", "awfm_gpu_set_l2_fetch_granularity",
     "awfm_gpu_ctx_create_from_file", "awfm_gpu_ctx_set_sequences", "awfm_gpu_ctx_extend_seed_table",
     "awfm_gpu_ctx_densify_suffix_array", "awfm_gpu_map_positions_device", "awfm_gpu_map_positions_host",
     "awfm_gpu_ctx_sweep_stage_ms", "awfm_gpu_ctx_sweep_live", "awfm_gpu_count_device_format", "awfm_gpu_locate_prepare_device",
@@ -93,6 +93,8 @@ def load():
     lib.awfm_gpu_built_download.argtypes = [vp, vp, vp, vp, vp]
     lib.awfm_gpu_built_destroy.argtypes = [vp]
     lib.awfm_gpu_built_destroy.restype = None
+    lib.awfm_gpu_built_tie_rounds.argtypes = [vp]
+    lib.awfm_gpu_built_tie_rounds.restype = C.c_uint32
     lib.awfm_gpu_synth_letters.argtypes = [C.c_int, vp, u64, u64, u64, C.c_int]
     lib.awfm_gpu_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.awfm_gpu_ctx_create_from_file.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p, C.c_int, C.POINTER(abi.awfm_file_info)]

@@ -3,17 +3,21 @@
 // k-mer seed table and the bit-packed sampled suffix array, all in the reference's own formats
 // (src/AwFmCreate.c:31-450, src/AwFmSuffixArray.c:58-112) so the result can be written as an unchanged `.awfmi`.
 //
-// Scope of this first version: texts with bwtLength < 2^32; suffixes are ordered by one radix sort of their first
-// 22 (nucleotide) / 13 (amino) symbols per leading-symbol bucket, and the (rare, on non-repetitive text) groups
-// that still tie are finished on the host by direct suffix comparison.  Correct for any text, fast for texts
-// without long repeats (all synthetic BASELINE configs).  Amino texts must be single-case over the 20 letters plus
-// ambiguity codes, as the reference's own sanitizer assumes (src/AwFmLetter.c:69-79).
+// Scope: texts with bwtLength < 2^32.  Suffixes are first ordered by one radix sort of their first 22 (nucleotide) /
+// 13 (amino) symbols per leading-symbol bucket; the groups that still tie are finished ON THE DEVICE by prefix
+// doubling (Manber-Myers / Larsson-Sadakane): with rank_h = the position of a suffix's group in the h-order, the tied
+// suffixes are sorted by (rank_h[i], rank_h[i + h]) — one radix sort of the tied elements only — which gives the
+// 2h-order, so a repeat of length L costs log2(L / 22) rounds instead of a comparison of L symbols per pair (tandem
+// arrays, satellite DNA, duplicated segments; the reference's libdivsufsort is O(n log n) as well).  Amino texts must
+// be single-case over the 20 letters plus ambiguity codes, as the reference's own sanitizer assumes
+// (src/AwFmLetter.c:69-79).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
 
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -109,23 +113,57 @@ __global__ void packKeys(const uint8_t *sym, const uint32_t *pos, uint64_t count
   keys[j] = k;
 }
 
-__global__ void tieFlags(const uint64_t *keys, uint64_t count, uint8_t *flags) {
+// per SA position of a bucket: bit 0 = first of its group of equal keys, bit 1 = the group has more than one member
+__global__ void groupFlags(const uint64_t *keys, uint64_t count, uint8_t *flags) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   const uint64_t k = keys[j];
-  flags[j] = (j > 0 && keys[j - 1] == k) || (j + 1 < count && keys[j + 1] == k);
+  const bool head = j == 0 || keys[j - 1] != k;
+  const bool tied = !head || (j + 1 < count && keys[j + 1] == k);
+  flags[j] = (head ? 1u : 0u) | (tied ? 2u : 0u);
 }
-
-__global__ void gatherTies(const uint32_t *tieIdx, uint64_t m, const uint64_t *keys, const uint32_t *pos, uint64_t *tKeys,
-                           uint32_t *tPos) {
+struct IsTied {
+  __host__ __device__ unsigned long long operator()(uint8_t f) const { return (f >> 1) & 1u; }
+};
+struct IsTiedFlag {
+  __host__ __device__ bool operator()(uint8_t f) const { return (f & 2u) != 0; }
+};
+struct HeadPosition {  // SA position j if j starts a group, else 0: the running maximum is the rank of j's group
+  const uint8_t *flags;
+  __host__ __device__ uint32_t operator()(uint32_t j) const { return (flags[j] & 1u) ? j : 0u; }
+};
+struct MaxU32 {
+  __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+__global__ void scatterRanks(const uint32_t *sa, const uint32_t *rank, uint64_t count, uint32_t *isa) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  tKeys[j] = keys[tieIdx[j]];
-  tPos[j] = pos[tieIdx[j]];
+  if (j < count) isa[sa[j]] = rank[j];
 }
-__global__ void scatterTies(const uint32_t *tieIdx, uint64_t m, const uint32_t *tPos, uint32_t *pos) {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < m) pos[tieIdx[j]] = tPos[j];
+// one doubling round over the tied elements (t = index into the list of tied SA positions, ascending)
+__global__ void doublingKeys(const uint32_t *tieIdx, uint64_t m, const uint32_t *sa, const uint32_t *isa, uint64_t h,
+                             uint64_t *keys, uint32_t *pos) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const uint32_t p = sa[tieIdx[t]];
+  pos[t] = p;
+  // tied at depth h => the first h symbols hold no sentinel => p + h <= n: a valid suffix
+  keys[t] = ((uint64_t)isa[p] << 32) | isa[(uint64_t)p + h];
+}
+struct DoublingHead {  // SA position of element t if it starts a group of equal (rank_h, rank_h at +h) pairs, else 0
+  const uint64_t *keys;
+  const uint32_t *tieIdx;
+  __host__ __device__ uint32_t operator()(uint32_t t) const {
+    return (t == 0 || keys[t] != keys[t - 1]) ? tieIdx[t] : 0u;
+  }
+};
+__global__ void doublingScatter(const uint32_t *tieIdx, uint64_t m, const uint64_t *keys, const uint32_t *pos,
+                                const uint32_t *rank, uint32_t *sa, uint32_t *isa, uint8_t *still) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  sa[tieIdx[t]] = pos[t];
+  isa[pos[t]] = rank[t];
+  const bool head = t == 0 || keys[t] != keys[t - 1];
+  still[t] = !head || (t + 1 < m && keys[t + 1] == keys[t]);
 }
 
 // One CTA (256 threads) per BWT block: letter bit-vectors in the reference layout + per-block letter counts.
@@ -247,7 +285,8 @@ struct awfm_built_index {
   uint64_t n = 0, bwtLength = 0, numBlocks = 0, numSeeds = 0, saBytes = 0;
   uint64_t prefixSums[24] = {0};
   Buf blocks, seedTable, sa, prefix;
-  uint64_t tieSuffixes = 0;
+  uint64_t tieSuffixes = 0;  // suffixes in groups that tied after the first radix sort
+  uint32_t tieRounds = 0;    // prefix-doubling rounds that finished them
   double buildMs = 0;
 };
 
@@ -295,28 +334,32 @@ static int buildImpl(awfm_built_index *B, const uint8_t *dText) {
   }
   uint64_t maxBucket = 0;
   for (int s = 1; s < NSYM; s++) maxBucket = std::max<uint64_t>(maxBucket, hist[s]);
-  Buf posA, posB, keyA, keyB, flags, tieIdx, numSel, temp;
+  Buf posA, posB, keyA, keyB, flags, numSel, temp;
   CUB_TRY(posA.alloc(maxBucket * 4));
   CUB_TRY(posB.alloc(maxBucket * 4));
   CUB_TRY(keyA.alloc(maxBucket * 8));
   CUB_TRY(keyB.alloc(maxBucket * 8));
-  CUB_TRY(flags.alloc(maxBucket));
-  CUB_TRY(tieIdx.alloc(maxBucket * 4));
+  CUB_TRY(flags.alloc(N));  // per SA position: bit 0 = head of its group in the (DEPTH+1)-order, bit 1 = group size > 1
   CUB_TRY(numSel.alloc(8));
   size_t tempBytes = 0;
+  auto ensureTemp = [&](size_t bytes) -> cudaError_t {
+    if (bytes <= tempBytes) return cudaSuccess;
+    tempBytes = bytes;
+    return temp.alloc(bytes);
+  };
   {
-    size_t a = 0, b = 0, c = 0;
+    size_t a = 0, b = 0;
     cub::CountingInputIterator<uint32_t> counting(0);
     CUB_TRY(cub::DeviceSelect::If(nullptr, a, counting, posA.as<uint32_t>(), numSel.as<uint64_t>(), (int64_t)N,
                                   FirstSymbolIs{sym.as<uint8_t>(), 1}));
     CUB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b, keyA.as<uint64_t>(), keyB.as<uint64_t>(), posA.as<uint32_t>(),
                                             posB.as<uint32_t>(), (int64_t)maxBucket, 0, DEPTH * BITS));
-    CUB_TRY(cub::DeviceSelect::Flagged(nullptr, c, counting, flags.as<uint8_t>(), tieIdx.as<uint32_t>(),
-                                       numSel.as<uint64_t>(), (int64_t)maxBucket));
-    tempBytes = std::max(a, std::max(b, c));
-    CUB_TRY(temp.alloc(tempBytes));
+    CUB_TRY(ensureTemp(std::max(a, b)));
   }
-  std::vector<uint8_t> hostSym;  // fetched lazily, only if some suffixes still tie after DEPTH+1 symbols
+  {
+    const uint8_t sentinelFlags = 1;  // SA[0]: a group of its own
+    CUB_TRY(cudaMemcpy(flags.p, &sentinelFlags, 1, cudaMemcpyHostToDevice));
+  }
   uint64_t bucketStart = 1;
   for (int s = 1; s < NSYM; s++) {
     const uint64_t cnt = hist[s];
@@ -329,50 +372,101 @@ static int buildImpl(awfm_built_index *B, const uint8_t *dText) {
     tb = tempBytes;
     CUB_TRY(cub::DeviceRadixSort::SortPairs(temp.p, tb, keyA.as<uint64_t>(), keyB.as<uint64_t>(), posA.as<uint32_t>(),
                                             posB.as<uint32_t>(), (int64_t)cnt, 0, DEPTH * BITS));
-    tieFlags<<<gridOf(cnt), 256>>>(keyB.as<uint64_t>(), cnt, flags.as<uint8_t>());
-    tb = tempBytes;
-    CUB_TRY(cub::DeviceSelect::Flagged(temp.p, tb, counting, flags.as<uint8_t>(), tieIdx.as<uint32_t>(),
-                                       numSel.as<uint64_t>(), (int64_t)cnt));
-    uint64_t m = 0;
-    CUB_TRY(cudaMemcpy(&m, numSel.p, 8, cudaMemcpyDeviceToHost));
-    if (m > 0) {  // finish tied groups on the host by direct suffix comparison beyond the sorted prefix
-      B->tieSuffixes += m;
-      Buf tKeys, tPos;
-      CUB_TRY(tKeys.alloc(m * 8));
-      CUB_TRY(tPos.alloc(m * 4));
-      gatherTies<<<gridOf(m), 256>>>(tieIdx.as<uint32_t>(), m, keyB.as<uint64_t>(), posB.as<uint32_t>(),
-                                     tKeys.as<uint64_t>(), tPos.as<uint32_t>());
-      std::vector<uint64_t> hKeys(m);
-      std::vector<uint32_t> hPos(m), hIdx(m);
-      CUB_TRY(cudaMemcpy(hKeys.data(), tKeys.p, m * 8, cudaMemcpyDeviceToHost));
-      CUB_TRY(cudaMemcpy(hPos.data(), tPos.p, m * 4, cudaMemcpyDeviceToHost));
-      CUB_TRY(cudaMemcpy(hIdx.data(), tieIdx.p, m * 4, cudaMemcpyDeviceToHost));
-      if (hostSym.empty()) {
-        hostSym.resize(padded);
-        CUB_TRY(cudaMemcpy(hostSym.data(), sym.p, padded, cudaMemcpyDeviceToHost));
-      }
-      const uint8_t *hs = hostSym.data();
-      const uint64_t skip = DEPTH + 1;
-      auto less = [hs, skip, N](uint32_t a, uint32_t b) {
-        uint64_t i = (uint64_t)a + skip, j = (uint64_t)b + skip;
-        while (i < N && j < N && hs[i] == hs[j]) i++, j++;  // the sentinel (unique) always ends the comparison
-        return hs[i] < hs[j];
-      };
-      uint64_t r0 = 0;
-      while (r0 < m) {
-        uint64_t r1 = r0 + 1;
-        while (r1 < m && hIdx[r1] == hIdx[r1 - 1] + 1 && hKeys[r1] == hKeys[r0]) r1++;
-        std::sort(hPos.begin() + r0, hPos.begin() + r1, less);
-        r0 = r1;
-      }
-      CUB_TRY(cudaMemcpy(tPos.p, hPos.data(), m * 4, cudaMemcpyHostToDevice));
-      scatterTies<<<gridOf(m), 256>>>(tieIdx.as<uint32_t>(), m, tPos.as<uint32_t>(), posB.as<uint32_t>());
-    }
+    groupFlags<<<gridOf(cnt), 256>>>(keyB.as<uint64_t>(), cnt, flags.as<uint8_t>() + bucketStart);
     CUB_TRY(cudaMemcpyAsync(sa.as<uint32_t>() + bucketStart, posB.p, cnt * 4, cudaMemcpyDeviceToDevice));
     bucketStart += cnt;
   }
   CUB_TRY(cudaDeviceSynchronize());
-  posA.alloc(0), posB.alloc(0), keyA.alloc(0), keyB.alloc(0), flags.alloc(0), tieIdx.alloc(0);
+  posA.alloc(0), posB.alloc(0), keyA.alloc(0), keyB.alloc(0);
+
+  // 2b. groups that still tie after DEPTH+1 symbols: prefix doubling over the tied elements only
+  {
+    cub::TransformInputIterator<unsigned long long, IsTied, const uint8_t *> tiedCount(flags.as<uint8_t>(), IsTied());
+    size_t tb = 0;
+    CUB_TRY(cub::DeviceReduce::Sum(nullptr, tb, tiedCount, numSel.as<unsigned long long>(), (int64_t)N));
+    CUB_TRY(ensureTemp(tb));
+    tb = tempBytes;
+    CUB_TRY(cub::DeviceReduce::Sum(temp.p, tb, tiedCount, numSel.as<unsigned long long>(), (int64_t)N));
+    uint64_t m = 0;
+    CUB_TRY(cudaMemcpy(&m, numSel.p, 8, cudaMemcpyDeviceToHost));
+    B->tieSuffixes = m;
+    if (m > 0) {
+      cub::CountingInputIterator<uint32_t> counting(0);
+      // rank of every suffix in the (DEPTH+1)-order = SA position of the head of its group
+      Buf isa, rank;
+      CUB_TRY(isa.alloc(N * 4));
+      CUB_TRY(rank.alloc(N * 4));
+      {
+        cub::TransformInputIterator<uint32_t, HeadPosition, cub::CountingInputIterator<uint32_t>> heads(
+            counting, HeadPosition{flags.as<uint8_t>()});
+        tb = 0;
+        CUB_TRY(cub::DeviceScan::InclusiveScan(nullptr, tb, heads, rank.as<uint32_t>(), MaxU32(), (int64_t)N));
+        CUB_TRY(ensureTemp(tb));
+        tb = tempBytes;
+        CUB_TRY(cub::DeviceScan::InclusiveScan(temp.p, tb, heads, rank.as<uint32_t>(), MaxU32(), (int64_t)N));
+        scatterRanks<<<gridOf(N), 256>>>(sa.as<uint32_t>(), rank.as<uint32_t>(), N, isa.as<uint32_t>());
+        CUB_TRY(cudaGetLastError());
+      }
+      Buf tieIdx[2], keys[2], pos[2], still;
+      CUB_TRY(tieIdx[0].alloc(m * 4));
+      CUB_TRY(tieIdx[1].alloc(m * 4));
+      {
+        cub::TransformInputIterator<bool, IsTiedFlag, const uint8_t *> tiedFlag(flags.as<uint8_t>(), IsTiedFlag());
+        tb = 0;
+        CUB_TRY(cub::DeviceSelect::Flagged(nullptr, tb, counting, tiedFlag, tieIdx[0].as<uint32_t>(), numSel.as<uint64_t>(),
+                                           (int64_t)N));
+        CUB_TRY(ensureTemp(tb));
+        tb = tempBytes;
+        CUB_TRY(cub::DeviceSelect::Flagged(temp.p, tb, counting, tiedFlag, tieIdx[0].as<uint32_t>(), numSel.as<uint64_t>(),
+                                           (int64_t)N));
+      }
+      CUB_TRY(cudaDeviceSynchronize());
+      rank.alloc(0);
+      flags.alloc(0);
+      for (int i = 0; i < 2; i++) {
+        CUB_TRY(keys[i].alloc(m * 8));
+        CUB_TRY(pos[i].alloc(m * 4));
+      }
+      CUB_TRY(rank.alloc(m * 4));
+      CUB_TRY(still.alloc(m));
+      {
+        size_t a = 0, b = 0, c = 0;
+        CUB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, a, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(), pos[0].as<uint32_t>(),
+                                                pos[1].as<uint32_t>(), (int64_t)m, 0, 64));
+        cub::TransformInputIterator<uint32_t, DoublingHead, cub::CountingInputIterator<uint32_t>> heads(
+            counting, DoublingHead{keys[1].as<uint64_t>(), tieIdx[0].as<uint32_t>()});
+        CUB_TRY(cub::DeviceScan::InclusiveScan(nullptr, b, heads, rank.as<uint32_t>(), MaxU32(), (int64_t)m));
+        CUB_TRY(cub::DeviceSelect::Flagged(nullptr, c, tieIdx[0].as<uint32_t>(), still.as<uint8_t>(), tieIdx[1].as<uint32_t>(),
+                                           numSel.as<uint64_t>(), (int64_t)m));
+        CUB_TRY(ensureTemp(std::max(a, std::max(b, c))));
+      }
+      int cur = 0;
+      uint32_t rounds = 0;
+      for (uint64_t h = DEPTH + 1; m > 0; h *= 2, rounds++) {
+        if (h > N) return awfm_set_error(AWFM_GPU_ERR_CUDA, "suffix sort: ties left beyond the text length", nullptr);
+        uint32_t *idx = tieIdx[cur].as<uint32_t>();
+        doublingKeys<<<gridOf(m), 256>>>(idx, m, sa.as<uint32_t>(), isa.as<uint32_t>(), h, keys[0].as<uint64_t>(),
+                                         pos[0].as<uint32_t>());
+        tb = tempBytes;
+        CUB_TRY(cub::DeviceRadixSort::SortPairs(temp.p, tb, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(), pos[0].as<uint32_t>(),
+                                                pos[1].as<uint32_t>(), (int64_t)m, 0, 64));
+        cub::TransformInputIterator<uint32_t, DoublingHead, cub::CountingInputIterator<uint32_t>> heads(
+            counting, DoublingHead{keys[1].as<uint64_t>(), idx});
+        tb = tempBytes;
+        CUB_TRY(cub::DeviceScan::InclusiveScan(temp.p, tb, heads, rank.as<uint32_t>(), MaxU32(), (int64_t)m));
+        doublingScatter<<<gridOf(m), 256>>>(idx, m, keys[1].as<uint64_t>(), pos[1].as<uint32_t>(), rank.as<uint32_t>(),
+                                            sa.as<uint32_t>(), isa.as<uint32_t>(), still.as<uint8_t>());
+        tb = tempBytes;
+        CUB_TRY(cub::DeviceSelect::Flagged(temp.p, tb, idx, still.as<uint8_t>(), tieIdx[cur ^ 1].as<uint32_t>(),
+                                           numSel.as<uint64_t>(), (int64_t)m));
+        CUB_TRY(cudaMemcpy(&m, numSel.p, 8, cudaMemcpyDeviceToHost));
+        cur ^= 1;
+      }
+      B->tieRounds = rounds;
+    }
+  }
+  CUB_TRY(cudaDeviceSynchronize());
+  flags.alloc(0);
 
   // 3. BWT blocks + base occurrences
   const uint64_t numBlocks = B->numBlocks;
@@ -510,6 +604,8 @@ extern "C" int awfm_gpu_built_view(awfm_built_index *b, awfm_index_view *v, uint
   if (buildMs) *buildMs = b->buildMs;
   return AWFM_GPU_OK;
 }
+
+extern "C" uint32_t awfm_gpu_built_tie_rounds(const awfm_built_index *b) { return b ? b->tieRounds : 0; }
 
 // copies the arrays into caller-provided HOST buffers sized from the view (any pointer may be NULL to skip)
 extern "C" int awfm_gpu_built_download(awfm_built_index *b, void *blocks, uint64_t *prefixSums, void *seedTable, uint8_t *saBytes) {

@@ -999,7 +999,7 @@ def run_ours(args):
     build_s = time.time() - t0
     need_host = rank == 0 or "dropin" not in args.skip
     arrays = built.to_host() if need_host else None
-    tie_suffixes, build_ms = built.tie_suffixes, built.build_ms
+    tie_suffixes, tie_rounds, build_ms = built.tie_suffixes, built.tie_rounds, built.build_ms
     built.close()
     torch.cuda.empty_cache()
     if rank == 0:
@@ -1480,7 +1480,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "index": {"device_bytes": device_bytes, "build_s": round(build_s, 2), "build_gpu_ms": round(build_ms, 1),
-                  "tie_suffixes_resolved_on_host": tie_suffixes},
+                  "suffixes_tied_after_radix_pass": tie_suffixes, "prefix_doubling_rounds_on_device": tie_rounds},
         "gather": gather_mode,
     }
     if e2e is None and e2e_packed is not None:  # --skip dropin: the packed call is the only end-to-end number

@@ -300,7 +300,9 @@ int awfm_gpu_peer_copy_async(int device, void *dst, const void *src, uint64_t by
 
 /* ---- index construction on the device (replaces awFmCreateIndex, src/AwFmCreate.c:31-137,
  *      for texts with bwtLength < 2^32).  Output arrays are in the reference's own formats (raw 160/352-B blocks,
- *      prefix sums, seed table, bit-packed sampled SA) and stay on the device inside the handle. ---- */
+ *      prefix sums, seed table, bit-packed sampled SA) and stay on the device inside the handle.  The suffix order is
+ *      a radix sort on the first 22 (amino: 13) symbols followed by prefix doubling over the suffixes that still tie,
+ *      all on the device: repetitive texts cost O(log(longest repeat)) extra rounds. ---- */
 typedef struct awfm_built_index awfm_built_index;
 int awfm_gpu_build_index(awfm_built_index **built, int device, const uint8_t *dText /* DEVICE, ASCII */,
                          uint64_t textLength, uint8_t alphabet, uint8_t seedK, uint8_t saRatio);
@@ -308,6 +310,8 @@ int awfm_gpu_build_index_host(awfm_built_index **built, int device, const uint8_
                               uint64_t textLength, uint8_t alphabet, uint8_t seedK, uint8_t saRatio);
 /* `view` receives DEVICE pointers (feed it to awfm_gpu_ctx_create_from_device); valid until _destroy. */
 int awfm_gpu_built_view(awfm_built_index *built, awfm_index_view *view, uint64_t *tieSuffixes, double *buildMs);
+/* prefix-doubling rounds the suffix sort needed after its radix pass (0 = no suffixes tied) */
+uint32_t awfm_gpu_built_tie_rounds(const awfm_built_index *built);
 /* copies into caller-sized HOST buffers (sizes follow from the view); NULL pointers are skipped */
 int awfm_gpu_built_download(awfm_built_index *built, void *blocks, uint64_t *prefixSums, void *seedTable,
                             uint8_t *saBytes);

@@ -38,8 +38,38 @@ def test_tiny_texts(reference, tmp_path, n):
     reference.dealloc_index(ptr)
 
 
+def test_long_repeats_are_finished_by_prefix_doubling(reference, tmp_path):
+    """What real genomes hold and iid text does not: a tandem array (satellite DNA), a segment duplicated far away, a
+    homopolymer run and a 2-periodic run — suffixes that agree for up to 600 k symbols.  The device finishes them by
+    prefix doubling (log2 of the longest repeat rounds over the tied suffixes only); the result is byte-identical to
+    what the reference's libdivsufsort-based awFmCreateIndex builds."""
+    rng = np.random.default_rng(4)
+    unit = make_text(171, False, seed=9)
+    segment = make_text(300_000, False, seed=10)
+    text = np.concatenate([make_text(50_000, False, seed=11), np.tile(unit, 3500), make_text(70_000, False, seed=12),
+                           segment, np.full(40_000, ord("A"), np.uint8), make_text(20_000, False, seed=13), segment,
+                           np.frombuffer(b"AC" * 30_000, np.uint8), np.tile(unit, 200), make_text(10_000, False, seed=14)]).copy()
+    text[rng.integers(0, len(text), 40)] = ord("N")
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "long.awfmi"), abi.AwFmAlphabetDna, 6, 4)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetDna, 6, 4)
+    assert built.tie_suffixes > 900_000 and built.tie_rounds >= 12, (built.tie_suffixes, built.tie_rounds)
+    assert_same(built, reference.arrays(ptr), "long repeats")
+    built.close()
+    reference.dealloc_index(ptr)
+    # amino: a repeated domain and a low-complexity run
+    domain = make_text(400, True, seed=15)
+    atext = np.concatenate([make_text(20_000, True, seed=16), np.tile(domain, 150), np.full(5_000, ord("Q"), np.uint8),
+                            make_text(9_000, True, seed=17), np.tile(domain, 40)]).copy()
+    ptr = reference.create_index(atext.tobytes(), str(tmp_path / "along.awfmi"), abi.AwFmAlphabetAmino, 3, 3)
+    built = DeviceBuiltIndex.from_host_text(atext, abi.AwFmAlphabetAmino, 3, 3)
+    assert built.tie_suffixes > 60_000 and built.tie_rounds >= 8, (built.tie_suffixes, built.tie_rounds)
+    assert_same(built, reference.arrays(ptr), "amino repeats")
+    built.close()
+    reference.dealloc_index(ptr)
+
+
 def test_repetitive_text_goes_through_tie_resolution(reference, tmp_path):
-    """Long repeats defeat the 22-symbol radix pass; tied groups are finished by suffix comparison on the host."""
+    """Repeats defeat the 22-symbol radix pass; the tied groups are finished by prefix doubling on the device."""
     rng = np.random.default_rng(0)
     unit = make_text(300, False, seed=1)
     text = np.concatenate([unit] * 20 + [make_text(500, False, seed=2)] + [np.frombuffer(b"ACGT" * 200, np.uint8)])

@@ -68,6 +68,19 @@ def test_long_repeats_are_finished_by_prefix_doubling(reference, tmp_path):
     reference.dealloc_index(ptr)
 
 
+def test_duplicated_megabase_segments(reference, tmp_path):
+    """12 Mbp in which every suffix has three copies 3 Mbp apart (a segmental duplication at genome scale): all 12 M
+    suffixes tie after the radix pass and stay tied for ~17 doubling rounds."""
+    segment = synth.random_text(3_000_000)
+    text = np.concatenate([segment, segment, segment, segment])
+    ptr = reference.create_index(text.tobytes(), str(tmp_path / "dup.awfmi"), abi.AwFmAlphabetDna, 8, 16)
+    built = DeviceBuiltIndex.from_host_text(text, abi.AwFmAlphabetDna, 8, 16)
+    assert built.tie_suffixes > 11_900_000 and built.tie_rounds >= 17, (built.tie_suffixes, built.tie_rounds)
+    assert_same(built, reference.arrays(ptr), "duplicated segments")
+    built.close()
+    reference.dealloc_index(ptr)
+
+
 def test_repetitive_text_goes_through_tie_resolution(reference, tmp_path):
     """Repeats defeat the 22-symbol radix pass; the tied groups are finished by prefix doubling on the device."""
     rng = np.random.default_rng(0)

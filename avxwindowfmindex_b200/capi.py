@@ -9,7 +9,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libawfm_b200.so")
+# AWFM_B200_LIB: development only — a variant build of the same library (tools/build_variant.sh) for A/B probes
+LIB_PATH = os.environ.get("AWFM_B200_LIB") or os.path.join(_HERE, "csrc", "libawfm_b200.so")
 
 GPU_SYMBOLS = [
     "awfm_gpu_last_error", "awfm_gpu_device_count", "awfm_gpu_ctx_create", "awfm_gpu_ctx_create_from_device",

@@ -653,31 +653,34 @@ __global__ void __launch_bounds__(256)
   const uint64_t total = blockSum256(mine, warpSums);
   if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
 }
-// one CTA: exclusive scan of the tile sums in place (numTiles is small: n / 2048), grand total to tileSums[numTiles]
+// one CTA: exclusive scan of the tile sums in place (numTiles = n / 2048: 24 k for 50 M queries), grand total to
+// tileSums[numTiles].  Thread t owns the consecutive tiles [t*per, (t+1)*per): it sums them (independent loads, all in
+// flight together), the 256 partial sums are scanned once, and the thread walks its tiles again writing the exclusive
+// prefixes — two sweeps over an L2-resident array instead of numTiles/256 dependent rounds of load, scan and barrier
+// (which took 0.3 ms of a 0.5 ms scan at 50 M queries).
 static __global__ void __launch_bounds__(256) scanTileBases(uint64_t *__restrict__ tileSums, uint64_t numTiles, uint64_t base) {
   __shared__ uint64_t warpSums[8];
-  __shared__ uint64_t carry;
-  if (threadIdx.x == 0) carry = base;
-  __syncthreads();
-  for (uint64_t t0 = 0; t0 < numTiles; t0 += 256) {
-    const uint64_t t = t0 + threadIdx.x;
-    const uint64_t v = t < numTiles ? tileSums[t] : 0;
-    uint64_t incl = v;
+  const uint64_t per = (numTiles + 255) / 256;
+  const uint64_t t0 = min(numTiles, (uint64_t)threadIdx.x * per), t1 = min(numTiles, t0 + per);
+  uint64_t mine = 0;
+#pragma unroll 8
+  for (uint64_t t = t0; t < t1; t++) mine += tileSums[t];
+  uint64_t incl = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if ((threadIdx.x & 31u) >= (unsigned)d) incl += up;
-    }
-    if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint64_t before = carry;
-    for (unsigned w = 0; w < (threadIdx.x >> 5); w++) before += warpSums[w];
-    if (t < numTiles) tileSums[t] = before + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry = before + incl;
-    __syncthreads();
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if ((threadIdx.x & 31u) >= (unsigned)d) incl += up;
   }
-  if (threadIdx.x == 0) tileSums[numTiles] = carry;
+  if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint64_t run = base + incl - mine;
+  for (unsigned w = 0; w < (threadIdx.x >> 5); w++) run += warpSums[w];
+  for (uint64_t t = t0; t < t1; t++) {
+    const uint64_t v = tileSums[t];
+    tileSums[t] = run;
+    run += v;
+  }
+  if (threadIdx.x == 255) tileSums[numTiles] = run;  // (threads past the last tile carry the total through unchanged)
 }
 template <bool FROM_COUNTS>
 __global__ void __launch_bounds__(256)
@@ -687,12 +690,25 @@ __global__ void __launch_bounds__(256)
   const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // thread t owns the 8 consecutive queries q0 + 8t .. q0 + 8t + 7
+  static_assert(kScanTile / 256 == 8, "vector paths below: 8 queries per thread");
   uint64_t len[kScanTile / 256], mine = 0;
+  const uint64_t qFirst = q0 + (uint64_t)threadIdx.x * (kScanTile / 256);
+  // whole tile inside the batch and 16-byte aligned arrays (q0 is a multiple of 2048): 128-bit loads and stores
+  const bool vector = q0 + kScanTile <= n && (reinterpret_cast<uintptr_t>(ranges) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(hitOffsets) & 15u) == 0;
+  if (FROM_COUNTS && vector) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(ranges) + qFirst));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(ranges) + qFirst) + 1);
+    len[0] = a.x, len[1] = a.y, len[2] = a.z, len[3] = a.w, len[4] = b.x, len[5] = b.y, len[6] = b.z, len[7] = b.w;
 #pragma unroll
-  for (int j = 0; j < kScanTile / 256; j++) {
-    const uint64_t q = q0 + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
-    len[j] = q < n ? hitsOfQuery<FROM_COUNTS>(ranges, q) : 0;
-    mine += len[j];
+    for (int j = 0; j < 8; j++) mine += len[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < kScanTile / 256; j++) {
+      const uint64_t q = qFirst + j;
+      len[j] = q < n ? hitsOfQuery<FROM_COUNTS>(ranges, q) : 0;
+      mine += len[j];
+    }
   }
   uint64_t incl = mine;
 #pragma unroll
@@ -704,11 +720,19 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   uint64_t run = __ldg(tileBases + blockIdx.x) + incl - mine;
   for (unsigned w = 0; w < warp; w++) run += warpSums[w];
+  if (vector) {
 #pragma unroll
-  for (int j = 0; j < kScanTile / 256; j++) {
-    const uint64_t q = q0 + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
-    if (q < n) hitOffsets[q] = run;
-    run += len[j];
+    for (int j = 0; j < 8; j += 2) {
+      reinterpret_cast<ulonglong2 *>(hitOffsets + qFirst)[j >> 1] = make_ulonglong2(run, run + len[j]);
+      run += len[j] + len[j + 1];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kScanTile / 256; j++) {
+      const uint64_t q = qFirst + j;
+      if (q < n) hitOffsets[q] = run;
+      run += len[j];
+    }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) hitOffsets[n] = __ldg(tileBases + gridDim.x);
 }

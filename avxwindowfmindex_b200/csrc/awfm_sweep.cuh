@@ -466,6 +466,16 @@ __global__ void __launch_bounds__(256)
 // specialised for the four plain letters (same truth table as nucCodeCare: A = b2&b1, C = b2&b0, G = b1&b0,
 // T = ~b2&~b1&b0, src/AwFmOccurrence.c:18-35).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef AWFM_SWEEP_NEXT_PREFETCH
+#define AWFM_SWEEP_NEXT_PREFETCH 0  // 1: next tile's input towards L2, 2: towards L1
+#endif
+__device__ __forceinline__ void sweepPrefetchNext(const void *p) {
+#if AWFM_SWEEP_NEXT_PREFETCH == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 struct SweepSelector {
   uint32_t flipHi;               // T: match zeros in b2 and b1
   uint32_t any0, any1, any2;     // A ignores b0, C ignores b1, G ignores b2
@@ -485,26 +495,53 @@ __device__ __forceinline__ Pos sweepSuper(const DevIndex &ix, uint64_t row, uint
   if constexpr (sizeof(Pos) == 8) return __ldg(ix.superC + row * kSectorSuperStride + letter);
   else return __ldg(reinterpret_cast<const uint32_t *>(ix.superC) + (row * kSectorSuperStride + letter) * 2u);
 }
-template <typename Pos>  // `super` = sweepSuper(row of p)
-__device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t letter, const SweepSelector &s, Pos super) {
-  const uint4 *sec = ix.lines + (uint64_t)(p >> 6) * kSectorU4;
-  uint4 v0, v1;
+// One sector in registers; `when` == false: nothing is requested (a predicated-off LDG costs no L1 wavefront) and the
+// words are undefined — the caller substitutes another sector's.
+struct SweepSector {
+  uint64_t a, b, c, d;  // words 0-1, 2-3, 4-5 (code bits 0, 1, 2), 6-7 (counts)
+};
+__device__ __forceinline__ SweepSector sweepLoadSector(const uint4 *sec) {
+  SweepSector s;
 #ifdef AWFM_NO_LDG256
-  v0 = __ldg(sec), v1 = __ldg(sec + 1);
+  const uint4 v0 = __ldg(sec), v1 = __ldg(sec + 1);
+  s.a = v0.x | ((uint64_t)v0.y << 32), s.b = v0.z | ((uint64_t)v0.w << 32);
+  s.c = v1.x | ((uint64_t)v1.y << 32), s.d = v1.z | ((uint64_t)v1.w << 32);
 #else
-  {  // the whole 32-B sector in ONE request (LDG.E.256, sm_100): the passes are bound by the L1/LSU pipe, not by DRAM
-    uint64_t a, b, c, d;
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(sec));
-    v0 = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
-    v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
-  }
+  // the whole 32-B sector in ONE request (LDG.E.256, sm_100): the passes are bound by the L1/LSU pipe, not by DRAM
+  asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.a), "=l"(s.b), "=l"(s.c), "=l"(s.d) : "l"(sec));
 #endif
+  return s;
+}
+// the sector at `sec` if `when`, else a copy of `other`: the request is PREDICATED (a predicated-off LDG costs no L1
+// wavefront and nothing is branched around, so it is in flight together with the request for `other`)
+__device__ __forceinline__ SweepSector sweepLoadSectorOr(const uint4 *sec, bool when, const SweepSector &other) {
+  SweepSector s;
+  asm("{\n\t.reg .pred p;\n\t.reg .b64 t0, t1, t2, t3;\n\t"
+      "setp.ne.u32 p, %9, 0;\n\t"
+      "mov.b64 t0, 0;\n\tmov.b64 t1, 0;\n\tmov.b64 t2, 0;\n\tmov.b64 t3, 0;\n\t"  // (undefined registers get a stack home)
+      "@p ld.global.nc.v4.u64 {t0,t1,t2,t3}, [%8];\n\t"
+      "selp.b64 %0, t0, %4, p;\n\t"
+      "selp.b64 %1, t1, %5, p;\n\t"
+      "selp.b64 %2, t2, %6, p;\n\t"
+      "selp.b64 %3, t3, %7, p;\n\t}"
+      : "=l"(s.a), "=l"(s.b), "=l"(s.c), "=l"(s.d)
+      : "l"(other.a), "l"(other.b), "l"(other.c), "l"(other.d), "l"(sec), "r"((uint32_t)when));
+  return s;
+}
+template <typename Pos>  // `super` = sweepSuper(row of p)
+__device__ __forceinline__ Pos sweepRankIn(const SweepSector &v, Pos p, uint32_t letter, const SweepSelector &s, Pos super) {
+  const uint32_t b0lo = (uint32_t)v.a, b0hi = (uint32_t)(v.a >> 32), b1lo = (uint32_t)v.b, b1hi = (uint32_t)(v.b >> 32);
+  const uint32_t b2lo = (uint32_t)v.c, b2hi = (uint32_t)(v.c >> 32);
   const int local = (int)((uint32_t)p & 63u) + 1;             // positions 0..local-1 of the sector count
   const uint32_t maskLo = lowBits(local), maskHi = lowBits(local - 32);
-  const uint32_t lo = ((v0.z ^ s.flipHi) | s.any1) & ((v1.x ^ s.flipHi) | s.any2) & (v0.x | s.any0) & maskLo;
-  const uint32_t hi = ((v0.w ^ s.flipHi) | s.any1) & ((v1.y ^ s.flipHi) | s.any2) & (v0.y | s.any0) & maskHi;
-  const uint32_t rel = (((letter & 2u) ? v1.w : v1.z) >> ((letter & 1u) * 16u)) & 0xFFFFu;
+  const uint32_t lo = ((b1lo ^ s.flipHi) | s.any1) & ((b2lo ^ s.flipHi) | s.any2) & (b0lo | s.any0) & maskLo;
+  const uint32_t hi = ((b1hi ^ s.flipHi) | s.any1) & ((b2hi ^ s.flipHi) | s.any2) & (b0hi | s.any0) & maskHi;
+  const uint32_t rel = (uint32_t)(v.d >> (letter * 16u)) & 0xFFFFu;
   return super + rel + __popc(lo) + __popc(hi);
+}
+template <typename Pos>
+__device__ __forceinline__ Pos sweepRank(const DevIndex &ix, Pos p, uint32_t letter, const SweepSelector &s, Pos super) {
+  return sweepRankIn<Pos>(sweepLoadSector(ix.lines + (uint64_t)(p >> 6) * kSectorU4), p, letter, s, super);
 }
 
 // Amino: one thread reads the code bits and the letter's count of one 128-B quarter-line (awfm_device.cuh): uint4 0/1 =
@@ -618,6 +655,24 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
   // some CTAs of this grid start late, and with static striding their tiles would simply run after everyone else's.
   // The ticket of the next tile is drawn while this one is worked on; the barrier that publishes it doubles as the
   // "previous tile's append buffers consumed" barrier.
+  // where record i of the input generation lives (16-byte records)
+  [[maybe_unused]] auto recordPtr = [&](uint32_t i) -> const uint4 * {
+    if constexpr (AMINO) {
+      uint32_t b = 0;  // bucket of record i: binary search over the padded prefix counts
+#pragma unroll
+      for (uint32_t step = 16; step > 0; step >>= 1)
+        if (i >= inPrefixSh[b + step]) b += step;
+      const uint32_t r = i - inPrefixSh[b];
+      return in.arr[b >> 1] + ((b & 1u) ? inLast - r : r);
+    } else {
+      // buckets 0/2 grow up in arrays 0/1, buckets 1/3 grow down from the end
+      const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;
+      const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
+      const bool odd = ge1 != ge2 || ge3;  // bucket 1 or 3
+      const uint32_t r = i - first;
+      return (ge2 ? in1 : in0) + (odd ? inLast - r : r);
+    }
+  };
   __shared__ uint32_t tileTicket[2];
   uint32_t nextTile = 0;  // thread 0
   if (threadIdx.x == 0) nextTile = atomicAdd(out.count + 31, 1u);
@@ -803,8 +858,20 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
 #else
           const Pos superB = rowB == rowA ? superA : sweepSuper<Pos>(ix, rowB, letter);
 #endif
+#ifndef AWFM_SWEEP_SHARED_SECTOR
           nsp = sweepRank<Pos>(ix, pa, letter, sel, superA);
           nep = sweepRank<Pos>(ix, pb, letter, sel, superB) - 1u;
+#else
+          // After the first steps sp-1 and ep nearly always lie in the same 64-position sector; here it is requested
+          // once (the second request predicated off, nothing branched around).  Measured: NO gain — 0.933 / 0.937 /
+          // 0.867 ms against 0.911 / 0.914 / 0.849 for passes 2-4 of 100 M 20-mers — the passes are not bound by the
+          // wavefronts of the sector requests; kept for the record, off.
+          const bool apart = (pb >> 6) != (pa >> 6);
+          const SweepSector secA = sweepLoadSector(ix.lines + (uint64_t)(pa >> 6) * kSectorU4);
+          const SweepSector secB = sweepLoadSectorOr(ix.lines + (uint64_t)(pb >> 6) * kSectorU4, apart, secA);
+          nsp = sweepRankIn<Pos>(secA, pa, letter, sel, superA);
+          nep = sweepRankIn<Pos>(secB, pb, letter, sel, superB) - 1u;
+#endif
         }
         sp[it] = nsp;
         ep[it] = nep;
@@ -850,7 +917,29 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
         if (lane < 4) warpCount[it][warp][lane] = __popc(live & ((lane & 1u) ? bit0 : ~bit0) & ((lane & 2u) ? bit1 : ~bit1));
       }
     }
+#if AWFM_SWEEP_NEXT_PREFETCH
+    if (threadIdx.x == 0) tileTicket[(round + 1u) & 1u] = nextTile;  // (drawn at the top of this round: long since back)
+#endif
     __syncthreads();
+#if AWFM_SWEEP_NEXT_PREFETCH
+    // The next tile's records (pairs) are pulled towards the SM while this tile waits for its room in the buckets and
+    // writes its records out: one DRAM round trip less on the next tile's critical path.
+    if constexpr (!REC12) {
+      const uint32_t nextBase = tileTicket[(round + 1u) & 1u] * kSweepTile;
+      if ((uint64_t)tileTicket[(round + 1u) & 1u] * kSweepTile < total) {
+#pragma unroll
+        for (int it = 0; it < kSweepItems; it++) {
+          const uint32_t i = min(nextBase + it * kSweepThreads + threadIdx.x, total - 1u);
+          if (FIRST) {
+            sweepPrefetchNext(vals + i);
+            if ((threadIdx.x & 1u) == 0) sweepPrefetchNext(keys + i);
+          } else {
+            sweepPrefetchNext(recordPtr(i));
+          }
+        }
+      }
+    }
+#endif
     if (threadIdx.x < NB) {
       uint32_t run = 0;
 #pragma unroll

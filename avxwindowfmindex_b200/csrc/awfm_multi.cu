@@ -6,9 +6,14 @@
 // straight into the caller's host arrays — no device-to-device exchange exists on this path.  One host thread per GPU
 // drives that GPU's pipeline; with one GPU the calling thread does it itself.
 //
-// Per GPU, a shard is worked through in chunks on three slots (stream + buffers): while chunk i is searched, chunk i+1
-// is on its way in and the counts of chunk i-1 on their way out.  The searches of successive chunks serialise on the
-// device (the sweep path's scratch is one per lane), the copies overlap them.
+// Per GPU, a shard is worked through in chunks on four slots (stream + buffers): while chunk i is searched, chunk i+1
+// is on its way in and the counts of chunk i-1 on their way out.  Every H2D goes through the device's one copy-in
+// stream, in chunk order (copies queued on several streams are interleaved by the copy engine: with six slots and a
+// copy per slot stream the call took 16.3-18.8 ms instead of 13.7).  The searches of successive chunks serialise on the
+// device (the sweep path's scratch is one per lane), the copies overlap them.  Chunks are 3 * 2^23 queries: the sweep
+// streams the index once per LF step whatever the batch, 0.7 ms per chunk at 3.1 Gbp, so the link (11 M 2-bit 20-mers
+// per ms) and the search (2.3 ms per 25 M chunk) run at the same pace; measured 13.7 ms per 100 M against 14.2 with
+// 2^24-query chunks, the same with 3, 4 or 6 slots.
 //
 // There is no CPU fallback: every entry point fails when CUDA is unavailable.
 #include <string.h>
@@ -33,7 +38,7 @@ struct PendingCopy {  // a pageable destination: the D2H went to page-locked sta
 
 struct PackSlot {  // one in-flight chunk (count) or walk window (locate) of a device's pipeline
   cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr, arrived = nullptr;  // arrived: the chunk's H2D (on the device's copy-in stream) is complete
   GrowBuf dQueries, dOffsets, dCounts, dPos, dSeq, dLoc;
   GrowBuf hIn, hOffsets, hOut;
   LocateScratch sc;
@@ -45,8 +50,14 @@ struct PackSlot {  // one in-flight chunk (count) or walk window (locate) of a d
 struct GroupDevice {
   awfm_gpu_ctx *ctx = nullptr;
   bool owned = false, ready = false;
-  static constexpr int kSlots = 3;
+#ifndef AWFM_GROUP_SLOTS
+#define AWFM_GROUP_SLOTS 4
+#endif
+  // one more slot than stages (H2D, search, D2H): a chunk's H2D can be queued while the counts of the chunk three
+  // before it are still on their way out
+  static constexpr int kSlots = AWFM_GROUP_SLOTS;
   PackSlot slots[kSlots];
+  cudaStream_t copyIn = nullptr;  // every H2D of the pipeline, in chunk order: chunk i is complete before chunk i+1 starts
   GrowBuf dRanges, dHit, dCounts;  // locate: the shard's ranges, counts and hit offsets stay on the device between the two phases
   uint64_t *hTotal = nullptr;  // page-locked
   cudaEvent_t rebased = nullptr;  // locate phase B: the shard's hit offsets carry their global base
@@ -60,7 +71,7 @@ struct GroupDevice {
 
 struct awfm_gpu_group {
   std::vector<std::unique_ptr<GroupDevice>> dev;
-  int64_t chunkQueries = 1ll << 24, minShard = 1ll << 16, windowHits = 1ll << 22;
+  int64_t chunkQueries = 3ll << 23, minShard = 1ll << 16, windowHits = 1ll << 22;
   std::mutex mu;  // one packed-batch call at a time per group
 };
 
@@ -72,8 +83,10 @@ int prepareDevice(GroupDevice &D) {
   for (auto &s : D.slots) {
     if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (!s.arrived) CU(cudaEventCreateWithFlags(&s.arrived, cudaEventDisableTiming));
     if (!s.sc.dWorkCounter) CU(cudaMalloc(&s.sc.dWorkCounter, 64));
   }
+  if (!D.copyIn) CU(cudaStreamCreateWithFlags(&D.copyIn, cudaStreamNonBlocking));
   if (!D.hTotal) CU(cudaHostAlloc(&D.hTotal, 64, cudaHostAllocPortable));
   if (!D.rebased) CU(cudaEventCreateWithFlags(&D.rebased, cudaEventDisableTiming));
   D.ready = true;
@@ -89,11 +102,18 @@ void releaseDevice(GroupDevice &D) {
       cudaStreamDestroy(s.stream);
     }
     if (s.done) cudaEventDestroy(s.done);
+    if (s.arrived) cudaEventDestroy(s.arrived);
+    s.arrived = nullptr;
     for (GrowBuf *b : {&s.dQueries, &s.dOffsets, &s.dCounts, &s.dPos, &s.dSeq, &s.dLoc, &s.hIn, &s.hOffsets, &s.hOut}) b->release();
     cudaFree(s.sc.scanTemp);
     cudaFree(s.sc.dWorkCounter);
     s.sc = LocateScratch();
     s.stream = nullptr, s.done = nullptr;
+  }
+  if (D.copyIn) {
+    cudaStreamSynchronize(D.copyIn);
+    cudaStreamDestroy(D.copyIn);
+    D.copyIn = nullptr;
   }
   D.dRanges.release();
   D.dHit.release();
@@ -144,8 +164,11 @@ int copyOut(PackSlot &s, GrowBuf &stage, size_t stageOffset, void *dst, bool dst
   return AWFM_GPU_OK;
 }
 
-// H2D of queries [q0, q0+m) into the slot, and the batch descriptor the kernels take
-int shipChunk(const Job &job, PackSlot &s, uint64_t q0, uint64_t m, PackedBatch *batch, uint64_t *h2dBytes) {
+// H2D of queries [q0, q0+m) into the slot, and the batch descriptor the kernels take.  The copy is queued on the
+// device's ONE copy-in stream (copies queued on several streams are interleaved by the copy engine, so every chunk
+// would arrive late); the slot's stream — search and D2H — waits for it.  The caller has made sure the slot's previous
+// chunk is finished (its buffers are rewritten here).
+int shipChunk(const Job &job, cudaStream_t copyIn, PackSlot &s, uint64_t q0, uint64_t m, PackedBatch *batch, uint64_t *h2dBytes) {
   const bool variable = job.offsets != nullptr;
   const uint64_t b0 = variable ? job.offsets[q0] : q0 * job.queryBytes;
   const uint64_t nbytes = variable ? job.offsets[q0 + m] - b0 : m * job.queryBytes;
@@ -159,7 +182,7 @@ int shipChunk(const Job &job, PackSlot &s, uint64_t q0, uint64_t m, PackedBatch 
     memcpy(s.hIn.p, src, nbytes);
     src = (const uint8_t *)s.hIn.p;
   }
-  if (nbytes) CU(cudaMemcpyAsync((uint8_t *)s.dQueries.p + pad, src, nbytes, cudaMemcpyHostToDevice, s.stream));
+  if (nbytes) CU(cudaMemcpyAsync((uint8_t *)s.dQueries.p + pad, src, nbytes, cudaMemcpyHostToDevice, copyIn));
   *h2dBytes += nbytes;
   batch->format = job.format;
   batch->length = job.fixedLen;
@@ -174,11 +197,13 @@ int shipChunk(const Job &job, PackSlot &s, uint64_t q0, uint64_t m, PackedBatch 
       memcpy(s.hOffsets.p, osrc, (m + 1) * 8);
       osrc = (const uint64_t *)s.hOffsets.p;
     }
-    CU(cudaMemcpyAsync(s.dOffsets.p, osrc, (m + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.dOffsets.p, osrc, (m + 1) * 8, cudaMemcpyHostToDevice, copyIn));
     *h2dBytes += (m + 1) * 8;
     batch->offsets = (const uint64_t *)s.dOffsets.p;
     batch->data = (const uint8_t *)s.dQueries.p + pad - b0;  // only ever dereferenced at + offsets[q] >= b0
   }
+  CU(cudaEventRecord(s.arrived, copyIn));
+  CU(cudaStreamWaitEvent(s.stream, s.arrived, 0));
   return AWFM_GPU_OK;
 }
 
@@ -237,7 +262,7 @@ int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, u
       fprintf(stderr, "[awfm_gpu] packed count dev %d chunk %zu (%llu queries): waited for its slot %.3f -> %.3f ms\n",
               c->device, k, (unsigned long long)m, tw, ms());
     PackedBatch b;
-    if ((rc = shipChunk(job, s, q0, m, &b, &h2d))) break;
+    if ((rc = shipChunk(job, D.copyIn, s, q0, m, &b, &h2d))) break;
     if ((rc = s.dCounts.ensure(m * 4))) break;
     if ((rc = awfm_count_device_impl(c, L, b, (uint32_t *)s.dCounts.p, nullptr, s.stream))) break;
     if (!job.countsPinned && (rc = s.hOut.ensure(m * 4))) break;
@@ -257,6 +282,7 @@ int countShard(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_t qa, u
     if (r) cudaStreamSynchronize(s.stream), s.busy = false, s.pending.clear();
     if (verbose) fprintf(stderr, "[awfm_gpu] packed count dev %d: a slot drained at %.3f ms\n", c->device, ms());
   }
+  if (rc != AWFM_GPU_OK) cudaStreamSynchronize(D.copyIn);  // (a copy queued for a chunk that was never searched)
   L.stats.h2dBytes = h2d;
   L.stats.d2hBytes = d2h;
   addStats(D.stats, L.stats);
@@ -284,7 +310,7 @@ int locateShardRanges(awfm_gpu_group *g, GroupDevice &D, const Job &job, uint64_
     const uint64_t q0 = starts[k], m = starts[k + 1] - q0;
     if (k >= GroupDevice::kSlots) CU(cudaStreamSynchronize(s.stream));  // the slot's input buffer is about to be rewritten
     PackedBatch b;
-    if (int r = shipChunk(job, s, q0, m, &b, &h2d)) return r;
+    if (int r = shipChunk(job, D.copyIn, s, q0, m, &b, &h2d)) return r;
     b.rangesOfHitsOnly = true;  // the hit offsets are scanned from the counts; the walk reads the ranges of hits only
     if (int r = awfm_count_device_impl(c, L, b, (uint32_t *)D.dCounts.p + (q0 - qa), (awfm_range *)D.dRanges.p + (q0 - qa), s.stream))
       return r;

@@ -469,6 +469,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
   else if (k == "sweep_record12" && (value == 0 || value == 1)) c->sweepRecord12 = (int)value;
+  else if (k == "sweep_compact_pairs" && (value == 0 || value == 1)) c->sweepCompactPairs = (int)value;
   else if (k == "sweep_variable" && (value == 0 || value == 1)) c->sweepVariable = (int)value;
   else if (k == "sweep_wide" && (value == 0 || value == 1)) c->sweepWide = (int)value;
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
@@ -737,27 +738,37 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   uint32_t *countB = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.sortCtrl) + sizeof(SortCtrl));
   uint32_t *cursorB = countB + (1u << (2 * kSortMaxDigitBits));
   if (ownSort) CU(cudaMemsetAsync(w.sortCtrl, 0, sizeof(SortCtrl) + (dB ? sizeof(uint32_t) << (dA + dB) : 0), st));
+  // Compact pairs between the pack kernel and the second bucket pass (awfm_sort.cuh): one 8-byte word per pair when key,
+  // payload and query id fit it once the first digit has left the key.
+  SortCompact compact{};
+  compact.keyBits = (uint32_t)endBit, compact.lowBits = (uint32_t)endBit - dA;
+  compact.restBits = variable ? SweepAlphabet<AMINO>::kLetterBits * kVarMaxRest + 1u : SweepAlphabet<AMINO>::kLetterBits * steps;
+  compact.idBits = 1;
+  while (compact.idBits < 32 && n > (1ull << compact.idBits) - 1ull) compact.idBits++;  // all ones = irregular query
+  const bool compactPairs = ownSort && dB > 0 && c->sweepCompactPairs && compact.keyBits + compact.restBits <= 63 &&
+                            compact.lowBits + compact.restBits + compact.idBits <= 64 && n <= (1ull << compact.idBits) - 1ull;
+  const uint32_t compactShift = compactPairs ? compact.keyBits : 0u;
   {
     const uint64_t tiles = (n + 255) / 256;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->numSMs * 8);
     if (variable) {
-      sweepPackVar<AMINO><<<grid, 256, 0, st>>>(dLetters, dOffsets, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA);
+      sweepPackVar<AMINO><<<grid, 256, 0, st>>>(dLetters, dOffsets, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift);
     } else if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
       const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
-      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA);
+      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA, compactShift);
     } else if (AMINO && len % 4 == 0 && len <= 12) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
-        case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
-        case 2: sweepPackWordsAmino<2><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
-        default: sweepPackWordsAmino<3><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); break;
+        case 1: sweepPackWordsAmino<1><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift); break;
+        case 2: sweepPackWordsAmino<2><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift); break;
+        default: sweepPackWordsAmino<3><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift); break;
       }
     } else if (!AMINO && len % 4 == 0) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
 #define AWFM_PACK_CASE(W)                                                                                         \
   case W:                                                                                                         \
-    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA); \
+    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift); \
     break;
         AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
         AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
@@ -766,7 +777,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       }
     } else {
       const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
-      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA);
+      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift);
     }
     CU(cudaGetLastError());
   }
@@ -782,20 +793,34 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     if (int r = gridFor(c, sortPass<false>, kSortThreads, &grid, kSortSmemBytes)) return r;
     grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSortTile - 1) / kSortTile);
     sortBases<0><<<1, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
-    sortPass<false><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[0], w.vals[0], w.keys[1], w.vals[1], (uint32_t)n, sortCtrl,
-                                                               cursorB, dA, dB, shiftA);
-    cur = 1;
-    sortLaunches = 2;
-    if (dB) {
+    if (compactPairs) {  // (dB > 0) pack words in vals[0] -> pass A words in vals[1] -> (key, payload | id) pairs in keys[0] / vals[0]
       int countGrid = 0;
-      if (int r = gridFor(c, sortDigitCounts, kSortThreads, &countGrid)) return r;
+      if (int r = gridFor(c, sortDigitCounts<true>, kSortThreads, &countGrid)) return r;
       countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + kSortTile - 1) / kSortTile + (1u << dA));
-      sortDigitCounts<<<countGrid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
+      sortPassCompact<false><<<grid, kSortThreads, kSortCompactSmemBytes, st>>>(w.vals[0], w.vals[1], nullptr, nullptr, (uint32_t)n,
+                                                                               sortCtrl, cursorB, dA, dB, shiftA, compact);
+      sortDigitCounts<true><<<countGrid, kSortThreads, 0, st>>>(w.vals[1], sortCtrl, countB, dA, dB, shiftB);
       sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
-      sortPass<true><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[1], w.vals[1], w.keys[0], w.vals[0], (uint32_t)n, sortCtrl,
-                                                                cursorB, dA, dB, shiftB);
+      sortPassCompact<true><<<grid, kSortThreads, kSortCompactSmemBytes, st>>>(w.vals[1], nullptr, w.keys[0], w.vals[0], (uint32_t)n,
+                                                                              sortCtrl, cursorB, dA, dB, shiftB, compact);
       cur = 0;
       sortLaunches = 5;
+    } else {
+      sortPass<false><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[0], w.vals[0], w.keys[1], w.vals[1], (uint32_t)n, sortCtrl,
+                                                                 cursorB, dA, dB, shiftA);
+      cur = 1;
+      sortLaunches = 2;
+      if (dB) {
+        int countGrid = 0;
+        if (int r = gridFor(c, sortDigitCounts<false>, kSortThreads, &countGrid)) return r;
+        countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + kSortTile - 1) / kSortTile + (1u << dA));
+        sortDigitCounts<false><<<countGrid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
+        sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+        sortPass<true><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[1], w.vals[1], w.keys[0], w.vals[0], (uint32_t)n, sortCtrl,
+                                                                  cursorB, dA, dB, shiftB);
+        cur = 0;
+        sortLaunches = 5;
+      }
     }
     CU(cudaGetLastError());
   } else if (endBit > beginBit) {

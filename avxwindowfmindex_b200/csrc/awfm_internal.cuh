@@ -133,6 +133,7 @@ struct awfm_gpu_ctx {
   int sweepRecord12 = 0;  // 12-byte live records when the batch allows it (nucleotide, <= 8 letters left of the seed)
   int sweepWide = 0;      // 1: the 64-bit-position passes even on an index below 2^32 positions (cross-check)
   int sweepVariable = 1;  // variable-length batches may take the sweep (marker-bit payloads, sweepPackVar)
+  int sweepCompactPairs = 1;  // 8-byte pairs through the bucket passes when key, payload and id fit (awfm_sort.cuh)
   int sweepOwnSort = 1;  // 1 = the hand-written stable radix passes (awfm_sort.cuh), 0 = CUB (cross-check)
   static constexpr int kLanes = 3;
   Lane lanes[kLanes];

@@ -112,9 +112,25 @@ __device__ __forceinline__ void sortTileOfBucket(const SortCtrl *__restrict__ ct
   count = min((uint32_t)kSortTile, end - first);
 }
 
-// histogram of digit B inside the bucket regions (keys only: 4 B per pair)
-static __global__ void __launch_bounds__(kSortThreads)
-    sortDigitCounts(const uint32_t *__restrict__ keys, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB,
+// Compact pairs (8 bytes instead of 4 + 8 between the pack kernel and the second bucket pass).  The pack kernel writes
+// pair i at index i, so the query id is implicit there; pass A turns the pack word into a word that carries the id but
+// no longer the digit it has just bucketed by (implied by the bucket the word lies in); pass B, whose tiles never
+// straddle two buckets, restores the full key and writes the (key, payload | id) pairs the first sweep pass reads.
+//   pack word:   key in bits [0, keyBits), payload in [keyBits, keyBits + restBits), bit 63 = irregular query
+//   pass A word: key bits below digit A in [0, lowBits), payload in [lowBits, lowBits + restBits), id above them
+//                (idBits wide; all ones = irregular query)
+// Usable when keyBits + restBits <= 63 and lowBits + restBits + idBits <= 64 (100 M 20-mers on a k = 12 table:
+// 16 + 16 + 27 = 59).  A pass then moves one 64-bit word per pair through registers, shared memory and the LSU instead
+// of a 32-bit and a 64-bit one: the passes are bound by exactly that pipe (profiles/r02_ncu_sweep_kernels.json).
+struct SortCompact {
+  uint32_t keyBits, lowBits, restBits, idBits;
+};
+constexpr uint32_t kSortNoId = 0xFFFFFFFFu;  // (= kSweepNoId)
+
+// histogram of digit B inside the bucket regions (keys only: 4 B per pair; COMPACT: the low half of pass A's words)
+template <bool COMPACT>
+__global__ void __launch_bounds__(kSortThreads)
+    sortDigitCounts(const void *__restrict__ keysOrWords, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB,
                     uint32_t dA, uint32_t dB, uint32_t shiftB) {
   __shared__ uint32_t bins[kSortBins];
   __shared__ uint32_t tileShared;
@@ -133,7 +149,9 @@ static __global__ void __launch_bounds__(kSortThreads)
 #pragma unroll
     for (int it = 0; it < kSortItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
-      key[it] = __ldg(keys + first + min(i, count - 1u));
+      const uint32_t src = first + min(i, count - 1u);
+      if (COMPACT) key[it] = __ldg(reinterpret_cast<const uint2 *>(keysOrWords) + src).x;
+      else key[it] = __ldg(reinterpret_cast<const uint32_t *>(keysOrWords) + src);
     }
 #pragma unroll
     for (int it = 0; it < kSortItems; it++) {
@@ -230,6 +248,105 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
   }
 }
 
+// The same bucket pass on compact pairs.  SECOND = false: pack words in (id = index), pass A words out; digit A leaves
+// the word before it is staged, so the tile keeps one byte per staged pair to know the bucket it is written to.
+// SECOND = true: pass A words in, (key, payload | id) pairs out for the first sweep pass.  `shift` = position of the
+// digit inside the low 32 bits of the input word (the key occupies the word's low bits in both formats).
+template <bool SECOND>
+__global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
+    sortPassCompact(const uint64_t *__restrict__ wordsIn, uint64_t *__restrict__ wordsOut, uint32_t *__restrict__ keysOut,
+                    uint64_t *__restrict__ valsOut, uint32_t numPairs, SortCtrl *__restrict__ ctrl,
+                    uint32_t *__restrict__ cursorB, uint32_t dA, uint32_t dB, uint32_t shift, const SortCompact f) {
+  extern __shared__ __align__(16) uint8_t sortSmem[];
+  uint64_t *sWord = reinterpret_cast<uint64_t *>(sortSmem);       // kSortTile
+  uint8_t *sDigit = sortSmem + 8 * (size_t)kSortTile;             // kSortTile (pass A only)
+  __shared__ uint32_t bins[kSortBins], localBase[kSortBins], globalDelta[kSortBins];
+  __shared__ uint32_t warpSums[kSortThreads / 32];
+  __shared__ uint32_t tileShared;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t digitBits = SECOND ? dB : dA, mask = (1u << digitBits) - 1u;
+  const uint32_t numBuckets = 1u << dA;
+  const uint32_t totalTiles = SECOND ? ctrl->tilesBefore[numBuckets] : (numPairs + kSortTile - 1) / kSortTile;
+  const uint64_t lowMask = (1ull << f.lowBits) - 1ull, restMask = (1ull << f.restBits) - 1ull;
+  const uint32_t idShift = f.lowBits + f.restBits;  // <= 63
+  const uint64_t idMask = (1ull << f.idBits) - 1ull;  // idBits <= 32
+  for (;;) {
+    __syncthreads();  // previous tile's staging consumed
+    if (threadIdx.x == 0) tileShared = atomicAdd(&ctrl->ticket[SECOND ? 2 : 0], 1u);
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = tileShared;
+    if (tile >= totalTiles) break;
+    uint32_t a = 0, first, count;
+    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
+    else first = tile * kSortTile, count = min((uint32_t)kSortTile, numPairs - first);
+    uint64_t word[kSortItems];
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      word[it] = __ldg(wordsIn + first + min(i, count - 1u));
+    }
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) rank[it] = atomicAdd(&bins[((uint32_t)word[it] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    {  // exclusive scan of the tile's bin counts; room behind the global cursors
+      const uint32_t c = bins[threadIdx.x];
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (unsigned)d) incl += up;
+      }
+      if (lane == 31u) warpSums[warp] = incl;
+      __syncthreads();
+      uint32_t before = 0;
+#pragma unroll
+      for (unsigned w = 0; w < kSortThreads / 32; w++) before += w < warp ? warpSums[w] : 0u;
+      const uint32_t local = before + incl - c;
+      localBase[threadIdx.x] = local;
+      uint32_t *cursor = SECOND ? cursorB + (a << dB) + threadIdx.x : ctrl->cursorA + threadIdx.x;
+      globalDelta[threadIdx.x] = (c ? atomicAdd(cursor, c) : 0u) - local;  // staged pair i of bucket d goes to globalDelta[d] + i
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) {
+        uint64_t w = word[it];
+        const uint32_t d = ((uint32_t)w >> shift) & mask;
+        const uint32_t dst = localBase[d] + rank[it];
+        if (!SECOND) {  // pack word -> pass A word: digit A leaves, the id becomes explicit
+          const uint64_t id = (w >> 63) ? idMask : (uint64_t)(first + i);
+          w = (w & lowMask) | (((w >> f.keyBits) & restMask) << f.lowBits) | (id << idShift);
+          sDigit[dst] = (uint8_t)d;
+        }
+        sWord[dst] = w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+      const uint32_t i = it * kSortThreads + threadIdx.x;
+      if (i < count) {
+        const uint64_t w = sWord[i];
+        if (!SECOND) {
+          wordsOut[globalDelta[sDigit[i]] + i] = w;
+        } else {
+          const uint32_t dst = globalDelta[((uint32_t)w >> shift) & mask] + i;
+          const uint32_t id = (uint32_t)((w >> idShift) & idMask);
+          keysOut[dst] = (a << f.lowBits) | (uint32_t)(w & lowMask);
+          valsOut[dst] = (((w >> f.lowBits) & restMask) << 32) | (id == (uint32_t)idMask ? kSortNoId : id);
+        }
+      }
+    }
+  }
+}
+
 constexpr size_t kSortSmemBytes = 12 * (size_t)kSortTile;
+constexpr size_t kSortCompactSmemBytes = 9 * (size_t)kSortTile;
 
 }  // namespace awfm

@@ -102,6 +102,17 @@ struct PackHistogram {
     }
   }
 };
+// One packed query leaves the pack kernel either as a (key, payload | id) pair or — compactShift != 0, the bucket
+// passes on compact pairs (awfm_sort.cuh) — as ONE word at index q: key | payload << compactShift, bit 63 = irregular.
+__device__ __forceinline__ void sweepStorePair(uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint64_t q, uint32_t key,
+                                               uint32_t payload, bool irregular, uint32_t compactShift) {
+  if (compactShift) {
+    vals[q] = (uint64_t)key | ((uint64_t)payload << compactShift) | ((uint64_t)irregular << 63);
+  } else {
+    keys[q] = key;
+    vals[q] = ((uint64_t)payload << 32) | (irregular ? kSweepNoId : (uint32_t)q);
+  }
+}
 __device__ __forceinline__ uint32_t packFourLetters(uint32_t w, uint32_t &bad) {
   const uint32_t code = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
   const uint32_t b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u, both = b0 & b1;
@@ -115,7 +126,8 @@ template <int WORDS>  // words per query (len / 4), fully unrolled
 __global__ void __launch_bounds__(256)
     sweepPackWords(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
                    uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-                   uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+                   uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
+                   uint32_t compactShift) {
   __shared__ uint32_t histShared[kSortBins];
   PackHistogram hist;
   hist.begin(histShared, sortCtrl);
@@ -130,13 +142,8 @@ __global__ void __launch_bounds__(256)
     uint32_t bad = 0;
 #pragma unroll
     for (int i = 0; i < WORDS; i++) Q = (Q << 8) | packFourLetters(w[i], bad);
-    uint32_t id = (uint32_t)q;
-    if (bad) {
-      irregularIds[atomicAdd(irregularCount, 1u)] = id;
-      id = kSweepNoId;
-    }
-    keys[q] = (uint32_t)(Q & keyMask);
-    vals[q] = ((Q >> (2 * k)) << 32) | id;
+    if (bad) irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)q;
+    sweepStorePair(keys, vals, q, (uint32_t)(Q & keyMask), (uint32_t)(Q >> (2 * k)), bad != 0, compactShift);
     hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
   }
   hist.flush(sortCtrl);
@@ -149,7 +156,8 @@ template <int WORDS>
 __global__ void __launch_bounds__(256)
     sweepPackWordsAmino(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
                         uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-                        uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+                        uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
+                        uint32_t compactShift) {
   __shared__ uint32_t histShared[kSortBins];
   PackHistogram hist;
   hist.begin(histShared, sortCtrl);
@@ -170,13 +178,8 @@ __global__ void __launch_bounds__(256)
       if (i >= rest) key = key * 20u + v;              // leftmost of the last k letters most significant
       else packed |= v << (5u * (rest - 1u - i));      // letter prepended at step j+1 is s[rest-1-j]
     }
-    uint32_t id = (uint32_t)q;
-    if (bad) {
-      irregularIds[atomicAdd(irregularCount, 1u)] = id;
-      id = kSweepNoId;
-    }
-    keys[q] = key;
-    vals[q] = ((uint64_t)packed << 32) | id;
+    if (bad) irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)q;
+    sweepStorePair(keys, vals, q, key, packed, bad != 0, compactShift);
     hist.add(sortCtrl, key, shiftA);
   }
   hist.flush(sortCtrl);
@@ -189,7 +192,8 @@ template <bool AMINO>  // amino: key = mixed-radix seed index (radix 20), 5 bits
 __global__ void __launch_bounds__(256)
     sweepPack(const uint8_t *__restrict__ letters, uint64_t numQueries, uint32_t len, uint32_t k,
               uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-              uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+              uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
+              uint32_t compactShift) {
   constexpr uint32_t CARD = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   extern __shared__ __align__(16) uint8_t sLetters[];  // 256 * len bytes, rounded up to 16
   __shared__ uint32_t histShared[kSortBins];
@@ -230,13 +234,8 @@ __global__ void __launch_bounds__(256)
         bad |= l >= CARD;
         packed |= (l < CARD ? l : 0u) << (LB * j);
       }
-      uint32_t id = (uint32_t)(q0 + threadIdx.x);
-      if (bad) {
-        irregularIds[atomicAdd(irregularCount, 1u)] = id;
-        id = kSweepNoId;
-      }
-      keys[q0 + threadIdx.x] = key;
-      vals[q0 + threadIdx.x] = ((uint64_t)packed << 32) | id;
+      if (bad) irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)(q0 + threadIdx.x);
+      sweepStorePair(keys, vals, q0 + threadIdx.x, key, packed, bad != 0, compactShift);
       hist.add(sortCtrl, key, shiftA);
     }
   }
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(256)
 static __global__ void __launch_bounds__(256)
     sweepPackBits(const uint8_t *__restrict__ packed, uint64_t numQueries, uint32_t len, uint32_t k,
                   uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, SortCtrl *__restrict__ sortCtrl,
-                  uint32_t shiftA) {
+                  uint32_t shiftA, uint32_t compactShift) {
   extern __shared__ __align__(16) uint8_t sPacked[];  // 256 * B bytes, rounded up to 16
   __shared__ uint32_t histShared[kSortBins];
   PackHistogram hist;
@@ -289,8 +288,7 @@ static __global__ void __launch_bounds__(256)
       uint64_t r = __brevll(raw);  // letter j: bits (2j, 2j+1) -> (63-2j, 62-2j)
       r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);  // ... -> (62-2j, 63-2j)
       const uint64_t Q = r >> (64u - 2u * len);  // first letter most significant, 2 bits per letter
-      keys[q0 + threadIdx.x] = (uint32_t)(Q & keyMask);
-      vals[q0 + threadIdx.x] = ((Q >> (2 * k)) << 32) | (uint32_t)(q0 + threadIdx.x);
+      sweepStorePair(keys, vals, q0 + threadIdx.x, (uint32_t)(Q & keyMask), (uint32_t)(Q >> (2 * k)), false, compactShift);
       hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
     }
   }
@@ -363,7 +361,8 @@ template <bool AMINO>
 __global__ void __launch_bounds__(256)
     sweepPackVar(const uint8_t *__restrict__ letters, const uint64_t *__restrict__ offsets, uint64_t numQueries, uint32_t k,
                  uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
-                 uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA) {
+                 uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
+                 uint32_t compactShift) {
   constexpr uint32_t kMaxRest = AMINO ? kSweepVarMaxRestAmino : kSweepVarMaxRestNuc;
   __shared__ uint32_t histShared[kSortBins];
   __shared__ uint64_t sOff[257];
@@ -442,15 +441,12 @@ __global__ void __launch_bounds__(256)
           sweepPackVarDirect<AMINO>(letters, totalBytes, o, len, k, keyMask, key, payload, bad);
         }
       }
-      uint32_t id = (uint32_t)q;
       if (bad) {
-        irregularIds[atomicAdd(irregularCount, 1u)] = id;
-        id = kSweepNoId;
+        irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)q;
         key = 0;
         payload = 1u;
       }
-      keys[q] = key;
-      vals[q] = ((uint64_t)payload << 32) | id;
+      sweepStorePair(keys, vals, q, key, payload, bad != 0, compactShift);
       hist.add(sortCtrl, key, shiftA);
     }
   }

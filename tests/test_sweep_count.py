@@ -297,6 +297,49 @@ def test_own_bucket_passes_and_cub_order_alike(small_indexes, name):
     gpu.close()
 
 
+@pytest.mark.parametrize("name", ["nuc_r8", "nuc_r16", "amino_r8"])
+def test_compact_pairs_through_the_bucket_passes(small_indexes, name):
+    """csrc/awfm_sort.cuh, compact pairs: one 8-byte word per pair between the pack kernel and the second bucket pass
+    (query id implicit in the pack kernel's output, explicit once the first digit has left the key).  Two-digit
+    orderings (sweep_local_bits = 0 leaves every key bit to the bucket passes) with the compact words on and off, for
+    fixed-length ASCII and 2-bit batches, variable-length batches, batches with irregular letters, batches smaller and
+    larger than one sort tile: counts and ranges equal to the oracle's."""
+    from avxwindowfmindex_b200 import GpuGroup, pack_queries_bits
+    from avxwindowfmindex_b200.search import QUERY_2BIT
+    b = small_indexes[name]
+    k = b.arrays.seed_k
+    room = 6 if b.amino else 15
+    oracle = harness.Oracle(b.arrays)
+    gpu = GpuIndex(b.arrays)
+    group = GpuGroup(indexes=[gpu])
+    for compact in (1, 0):
+        for local in (0, 2):
+            gpu.set_tuning(sweep_min_queries=1, sweep_own_sort=1, sweep_sort_bits=32, sweep_local_bits=local,
+                           sweep_compact_pairs=compact, sweep_profile=1)
+            for length, num in ((k + 1, 3), (k + 3, 3071), (k + 2, 3073), (k + 4, 50000), (k, 9000), (k + room // 2, 7001)):
+                letters = fixed_batch(b, length, num, seed=num + 3 * length)
+                o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
+                counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
+                assert gpu.sweep_stage_ms(), "the batch did not take the sweep path"
+                assert np.array_equal(counts, o_counts), (name, length, num, compact, local)
+                assert np.array_equal(ranges, o_ranges), (name, length, num, compact, local)
+                if not b.amino:
+                    clean = fixed_batch(b, length, num, seed=num + 5 * length, irregular=False) & 0xDF  # upper case
+                    clean[~np.isin(clean, np.frombuffer(b"ACGT", dtype=np.uint8))] = ord("A")  # (the text holds N's)
+                    c_counts, _, _ = oracle.count(clean, fixed_len=length)
+                    packed = pack_queries_bits(clean, length)
+                    assert np.array_equal(group.count(packed, QUERY_2BIT, fixed_len=length), c_counts), (name, length, num, compact, local, "2bit")
+            for num, lo, hi, seed in ((9000, 0, k + room + 3, 11), (20000, k, k + 4, 12), (2, k + 1, k + 2, 13)):
+                letters, offsets = variable_batch(b, num, seed=seed * 17 + num, lo=lo, hi=hi)
+                o_counts, o_ranges, _ = oracle.count(letters, offsets)
+                counts, ranges = gpu.count(letters, offsets, want_ranges=True)
+                assert len(gpu.sweep_stage_ms()) == 3 + room, "the batch did not take the sweep path"
+                assert np.array_equal(counts, o_counts), (name, num, lo, hi, compact, local)
+                assert np.array_equal(ranges, o_ranges), (name, num, lo, hi, compact, local)
+    group.close()
+    gpu.close()
+
+
 def test_twelve_byte_records_and_the_wide_range_escape(reference, tmp_path):
     """Nucleotide batches with at most 8 letters left of the seed travel as 12-byte records with a 16-bit range width;
     a query whose SEED range is wider than 65534 positions leaves the sweep for the generic per-query search.  With a

@@ -84,6 +84,14 @@ def main():
               "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
               "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref)),
               "device_bytes": gpu.device_bytes()})
+    for compact in (1, 0):  # 8-byte words through the bucket passes (csrc/awfm_sort.cuh) vs 4 + 8 bytes
+        gpu.set_tuning(sweep_sort_bits=32, sweep_items=4, sweep_local_bits=-1, sweep_own_sort=1, sweep_compact_pairs=compact)
+        d_counts.fill_(-1)
+        ms = timed(n, d_counts)
+        emit({"variant": "compact_pairs", "on": compact, "queries": n, "ms": ms, "Gq_per_s": n / ms / 1e6,
+              "stage_ms": [round(x, 3) for x in gpu.sweep_stage_ms()],
+              "equal_to_tile": None if args.no_tile else bool(torch.equal(d_counts, d_ref))})
+    gpu.set_tuning(sweep_compact_pairs=1)
     if args.wide:
         gpu.set_tuning(sweep_sort_bits=32, sweep_items=4, sweep_local_bits=-1, sweep_own_sort=1, sweep_wide=1)
         d_counts.fill_(-1)

@@ -790,17 +790,26 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       CU(cudaFuncSetAttribute(sortPass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
       CU(cudaFuncSetAttribute(sortPass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
     }
-    if (int r = gridFor(c, sortPass<false>, kSortThreads, &grid, kSortSmemBytes)) return r;
-    grid = (int)std::min<uint64_t>((uint64_t)grid, (n + kSortTile - 1) / kSortTile);
-    sortBases<0><<<1, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+    if (kSortCompactSmemBytes + 6 * 1024 > 48 * 1024) {
+      CU(cudaFuncSetAttribute(sortPassCompact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortCompactSmemBytes));
+      CU(cudaFuncSetAttribute(sortPassCompact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortCompactSmemBytes));
+    }
+    const uint32_t tilePairs = compactPairs ? (uint32_t)kSortCompactTile : (uint32_t)kSortTile;
+    if (compactPairs) {
+      if (int r = gridFor(c, sortPassCompact<false>, kSortThreads, &grid, kSortCompactSmemBytes)) return r;
+    } else if (int r = gridFor(c, sortPass<false>, kSortThreads, &grid, kSortSmemBytes)) {
+      return r;
+    }
+    grid = (int)std::min<uint64_t>((uint64_t)grid, (n + tilePairs - 1) / tilePairs);
+    sortBases<0><<<1, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB, tilePairs);
     if (compactPairs) {  // (dB > 0) pack words in vals[0] -> pass A words in vals[1] -> (key, payload | id) pairs in keys[0] / vals[0]
       int countGrid = 0;
-      if (int r = gridFor(c, sortDigitCounts<true>, kSortThreads, &countGrid)) return r;
-      countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + kSortTile - 1) / kSortTile + (1u << dA));
+      if (int r = gridFor(c, sortDigitCounts<true, kSortCompactItems>, kSortThreads, &countGrid)) return r;
+      countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + tilePairs - 1) / tilePairs + (1u << dA));
       sortPassCompact<false><<<grid, kSortThreads, kSortCompactSmemBytes, st>>>(w.vals[0], w.vals[1], nullptr, nullptr, (uint32_t)n,
                                                                                sortCtrl, cursorB, dA, dB, shiftA, compact);
-      sortDigitCounts<true><<<countGrid, kSortThreads, 0, st>>>(w.vals[1], sortCtrl, countB, dA, dB, shiftB);
-      sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+      sortDigitCounts<true, kSortCompactItems><<<countGrid, kSortThreads, 0, st>>>(w.vals[1], sortCtrl, countB, dA, dB, shiftB);
+      sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB, tilePairs);
       sortPassCompact<true><<<grid, kSortThreads, kSortCompactSmemBytes, st>>>(w.vals[1], nullptr, w.keys[0], w.vals[0], (uint32_t)n,
                                                                               sortCtrl, cursorB, dA, dB, shiftB, compact);
       cur = 0;
@@ -812,10 +821,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       sortLaunches = 2;
       if (dB) {
         int countGrid = 0;
-        if (int r = gridFor(c, sortDigitCounts<false>, kSortThreads, &countGrid)) return r;
-        countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + kSortTile - 1) / kSortTile + (1u << dA));
-        sortDigitCounts<false><<<countGrid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
-        sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB);
+        if (int r = gridFor(c, sortDigitCounts<false, kSortItems>, kSortThreads, &countGrid)) return r;
+        countGrid = (int)std::min<uint64_t>((uint64_t)countGrid, (n + tilePairs - 1) / tilePairs + (1u << dA));
+        sortDigitCounts<false, kSortItems><<<countGrid, kSortThreads, 0, st>>>(w.keys[1], sortCtrl, countB, dA, dB, shiftB);
+        sortBases<1><<<1u << dA, kSortThreads, 0, st>>>(sortCtrl, countB, cursorB, dA, dB, tilePairs);
         sortPass<true><<<grid, kSortThreads, kSortSmemBytes, st>>>(w.keys[1], w.vals[1], w.keys[0], w.vals[0], (uint32_t)n, sortCtrl,
                                                                   cursorB, dA, dB, shiftB);
         cur = 0;

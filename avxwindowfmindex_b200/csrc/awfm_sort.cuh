@@ -48,7 +48,7 @@ struct SortCtrl {
 template <int LEVEL>  // 0: bucket bases from countA; 1: group bases from countB (grid = 2^dA CTAs)
 __global__ void __launch_bounds__(kSortThreads)
     sortBases(SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB, uint32_t *__restrict__ cursorB, uint32_t dA,
-              uint32_t dB) {
+              uint32_t dB, uint32_t tilePairs /* pairs per tile of pass B */) {
   __shared__ uint32_t warpSums[kSortThreads / 32];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   auto blockExclusive = [&](uint32_t v, uint32_t &total) {  // exclusive scan over the CTA's 256 threads
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kSortThreads)
     const uint32_t c = threadIdx.x < bins ? ctrl->countA[threadIdx.x] : 0u;
     uint32_t total, tilesTotal;
     const uint32_t base = blockExclusive(c, total);
-    const uint32_t tiles = (c + kSortTile - 1) / kSortTile;
+    const uint32_t tiles = (c + tilePairs - 1) / tilePairs;
     const uint32_t tb = blockExclusive(tiles, tilesTotal);
     if (threadIdx.x < bins) {
       ctrl->baseA[threadIdx.x] = base;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kSortThreads)
 
 // pass B's tile t -> (bucket a, first pair, number of pairs); tiles never straddle two buckets
 __device__ __forceinline__ void sortTileOfBucket(const SortCtrl *__restrict__ ctrl, uint32_t numBuckets, uint32_t tile,
-                                                 uint32_t &a, uint32_t &first, uint32_t &count) {
+                                                 uint32_t tilePairs, uint32_t &a, uint32_t &first, uint32_t &count) {
   uint32_t lo = 0, hi = numBuckets;  // last a with tilesBefore[a] <= tile
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
@@ -108,8 +108,8 @@ __device__ __forceinline__ void sortTileOfBucket(const SortCtrl *__restrict__ ct
   a = lo;
   const uint32_t j = tile - ctrl->tilesBefore[a];
   const uint32_t begin = ctrl->baseA[a], end = ctrl->baseA[a + 1];
-  first = begin + j * kSortTile;
-  count = min((uint32_t)kSortTile, end - first);
+  first = begin + j * tilePairs;
+  count = min(tilePairs, end - first);
 }
 
 // Compact pairs (8 bytes instead of 4 + 8 between the pack kernel and the second bucket pass).  The pack kernel writes
@@ -128,7 +128,7 @@ struct SortCompact {
 constexpr uint32_t kSortNoId = 0xFFFFFFFFu;  // (= kSweepNoId)
 
 // histogram of digit B inside the bucket regions (keys only: 4 B per pair; COMPACT: the low half of pass A's words)
-template <bool COMPACT>
+template <bool COMPACT, int ITEMS>  // ITEMS * kSortThreads = pairs per tile of pass B
 __global__ void __launch_bounds__(kSortThreads)
     sortDigitCounts(const void *__restrict__ keysOrWords, SortCtrl *__restrict__ ctrl, uint32_t *__restrict__ countB,
                     uint32_t dA, uint32_t dB, uint32_t shiftB) {
@@ -144,17 +144,17 @@ __global__ void __launch_bounds__(kSortThreads)
     const uint32_t tile = tileShared;
     if (tile >= totalTiles) break;
     uint32_t a, first, count;
-    sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
-    uint32_t key[kSortItems];  // every load is issued before the first shared atomic waits on one
+    sortTileOfBucket(ctrl, numBuckets, tile, ITEMS * kSortThreads, a, first, count);
+    uint32_t key[ITEMS];  // every load is issued before the first shared atomic waits on one
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < ITEMS; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       const uint32_t src = first + min(i, count - 1u);
       if (COMPACT) key[it] = __ldg(reinterpret_cast<const uint2 *>(keysOrWords) + src).x;
       else key[it] = __ldg(reinterpret_cast<const uint32_t *>(keysOrWords) + src);
     }
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < ITEMS; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       if (i < count) atomicAdd(&bins[(key[it] >> shiftB) & maskB], 1u);
     }
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
     const uint32_t tile = tileShared;
     if (tile >= totalTiles) break;
     uint32_t a = 0, first, count;
-    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
+    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, kSortTile, a, first, count);
     else first = tile * kSortTile, count = min((uint32_t)kSortTile, numPairs - first);
     uint32_t key[kSortItems], rank[kSortItems];
     uint64_t val[kSortItems];
@@ -252,21 +252,29 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
 // the word before it is staged, so the tile keeps one byte per staged pair to know the bucket it is written to.
 // SECOND = true: pass A words in, (key, payload | id) pairs out for the first sweep pass.  `shift` = position of the
 // digit inside the low 32 bits of the input word (the key occupies the word's low bits in both formats).
+#ifndef AWFM_SORT_COMPACT_ITEMS
+#define AWFM_SORT_COMPACT_ITEMS 16  // (a word per pair leaves registers for more pairs per thread: 1.15 -> 1.01 ms per 100 M)
+#endif
+#ifndef AWFM_SORT_COMPACT_MIN_CTAS
+#define AWFM_SORT_COMPACT_MIN_CTAS 4
+#endif
+constexpr int kSortCompactItems = AWFM_SORT_COMPACT_ITEMS;
+constexpr int kSortCompactTile = kSortThreads * kSortCompactItems;
 template <bool SECOND>
-__global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
+__global__ void __launch_bounds__(kSortThreads, AWFM_SORT_COMPACT_MIN_CTAS)
     sortPassCompact(const uint64_t *__restrict__ wordsIn, uint64_t *__restrict__ wordsOut, uint32_t *__restrict__ keysOut,
                     uint64_t *__restrict__ valsOut, uint32_t numPairs, SortCtrl *__restrict__ ctrl,
                     uint32_t *__restrict__ cursorB, uint32_t dA, uint32_t dB, uint32_t shift, const SortCompact f) {
   extern __shared__ __align__(16) uint8_t sortSmem[];
-  uint64_t *sWord = reinterpret_cast<uint64_t *>(sortSmem);       // kSortTile
-  uint8_t *sDigit = sortSmem + 8 * (size_t)kSortTile;             // kSortTile (pass A only)
+  uint64_t *sWord = reinterpret_cast<uint64_t *>(sortSmem);       // kSortCompactTile
+  uint8_t *sDigit = sortSmem + 8 * (size_t)kSortCompactTile;             // kSortCompactTile (pass A only)
   __shared__ uint32_t bins[kSortBins], localBase[kSortBins], globalDelta[kSortBins];
   __shared__ uint32_t warpSums[kSortThreads / 32];
   __shared__ uint32_t tileShared;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t digitBits = SECOND ? dB : dA, mask = (1u << digitBits) - 1u;
   const uint32_t numBuckets = 1u << dA;
-  const uint32_t totalTiles = SECOND ? ctrl->tilesBefore[numBuckets] : (numPairs + kSortTile - 1) / kSortTile;
+  const uint32_t totalTiles = SECOND ? ctrl->tilesBefore[numBuckets] : (numPairs + kSortCompactTile - 1) / kSortCompactTile;
   const uint64_t lowMask = (1ull << f.lowBits) - 1ull, restMask = (1ull << f.restBits) - 1ull;
   const uint32_t idShift = f.lowBits + f.restBits;  // <= 63
   const uint64_t idMask = (1ull << f.idBits) - 1ull;  // idBits <= 32
@@ -278,17 +286,17 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
     const uint32_t tile = tileShared;
     if (tile >= totalTiles) break;
     uint32_t a = 0, first, count;
-    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, a, first, count);
-    else first = tile * kSortTile, count = min((uint32_t)kSortTile, numPairs - first);
-    uint64_t word[kSortItems];
-    uint32_t rank[kSortItems];
+    if (SECOND) sortTileOfBucket(ctrl, numBuckets, tile, kSortCompactTile, a, first, count);
+    else first = tile * kSortCompactTile, count = min((uint32_t)kSortCompactTile, numPairs - first);
+    uint64_t word[kSortCompactItems];
+    uint32_t rank[kSortCompactItems];
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < kSortCompactItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       word[it] = __ldg(wordsIn + first + min(i, count - 1u));
     }
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < kSortCompactItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       if (i < count) rank[it] = atomicAdd(&bins[((uint32_t)word[it] >> shift) & mask], 1u);
     }
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < kSortCompactItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       if (i < count) {
         uint64_t w = word[it];
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {
+    for (int it = 0; it < kSortCompactItems; it++) {
       const uint32_t i = it * kSortThreads + threadIdx.x;
       if (i < count) {
         const uint64_t w = sWord[i];
@@ -347,6 +355,6 @@ __global__ void __launch_bounds__(kSortThreads, AWFM_SORT_MIN_CTAS)
 }
 
 constexpr size_t kSortSmemBytes = 12 * (size_t)kSortTile;
-constexpr size_t kSortCompactSmemBytes = 9 * (size_t)kSortTile;
+constexpr size_t kSortCompactSmemBytes = 9 * (size_t)kSortCompactTile;
 
 }  // namespace awfm

@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256)
 // tileSums[numTiles].  Thread t owns the consecutive tiles [t*per, (t+1)*per): it sums them (independent loads, all in
 // flight together), the 256 partial sums are scanned once, and the thread walks its tiles again writing the exclusive
 // prefixes — two sweeps over an L2-resident array instead of numTiles/256 dependent rounds of load, scan and barrier
-// (which took 0.3 ms of a 0.5 ms scan at 50 M queries).
+// (50 M queries: the whole scan 0.53 -> 0.44 ms from ranges, together with the 128-bit requests of scanTileOffsets).
 static __global__ void __launch_bounds__(256) scanTileBases(uint64_t *__restrict__ tileSums, uint64_t numTiles, uint64_t base) {
   __shared__ uint64_t warpSums[8];
   const uint64_t per = (numTiles + 255) / 256;

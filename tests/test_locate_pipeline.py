@@ -203,3 +203,48 @@ def test_count_pipeline_rounds_and_driver_thread(small_indexes, reference, name)
                     assert np.array_equal(sl.counts(), r_counts), (name, label, chunk, threads)
                 sl.close()
     lib.awFmGpuReleaseIndex(ip)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2047, 2048, 2049, 524_288, 524_289, 1_300_003])
+def test_hit_offset_scan_against_numpy(small_indexes, n):
+    """scanTileSums / scanTileBases / scanTileOffsets (csrc/awfm_kernels.cuh): exclusive scan of the u32-truncated range
+    lengths (src/AwFmParallelSearch.c:328,367).  Sizes around one tile (2048 queries), around 256 tiles (where a thread of
+    the base kernel starts owning more than one tile) and far beyond; empty ranges, ranges longer than 2^32 (truncated),
+    ranges at the top of the 64-bit position space; from ranges (awfm_gpu_scan_ranges_device) and, through a search, from
+    counts (awfm_gpu_locate_prepare_device)."""
+    import torch
+    from avxwindowfmindex_b200 import GpuIndex
+    b = small_indexes["nuc_r8"]
+    gpu = GpuIndex(b.arrays)
+    rng = np.random.default_rng(n + 5)
+    sp = rng.integers(1, 1 << 40, n, dtype=np.uint64)
+    length = rng.integers(0, 9, n, dtype=np.uint64)               # 0 = empty range
+    length[rng.random(n) < 0.01] = np.uint64((1 << 32) + 7)        # u32 truncation: counts as 7
+    ep = sp + length - np.uint64(1)                                # empty: ep = sp - 1
+    if n:
+        sp[-1], ep[-1] = np.uint64(0xFFFFFFFFFFFFFFF0), np.uint64(0xFFFFFFFFFFFFFFF4)
+        length[-1] = 5
+    want = np.zeros(n + 1, dtype=np.uint64)
+    want[1:] = np.cumsum(length & np.uint64(0xFFFFFFFF))
+    ranges = np.stack([sp, ep], axis=1).astype(np.uint64) if n else np.zeros((0, 2), np.uint64)
+    d_ranges = torch.zeros((max(n, 1), 2), dtype=torch.int64, device="cuda")
+    d_ranges[:n] = torch.from_numpy(ranges.view(np.int64))
+    d_hit = torch.full((n + 1,), -1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    gpu.scan_ranges_device(d_ranges.data_ptr(), n, d_hit.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_hit.cpu().numpy().view(np.uint64), want), n
+    if n >= 2048:  # from counts: a real search over sampled 8-mers, offsets against the cumulative counts
+        L = 8
+        starts = rng.integers(0, len(b.text) - L, n)
+        letters = b.text[starts[:, None] + np.arange(L)[None, :]].reshape(-1).copy()
+        d_letters = torch.from_numpy(letters).cuda()
+        d_counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_r = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+        gpu.locate_prepare_device(d_letters.data_ptr(), 0, L, n, d_counts.data_ptr(), d_r.data_ptr(), d_hit.data_ptr(), st)
+        torch.cuda.synchronize()
+        counts = d_counts.cpu().numpy().view(np.uint32).astype(np.uint64)
+        want = np.zeros(n + 1, dtype=np.uint64)
+        want[1:] = np.cumsum(counts)
+        assert np.array_equal(d_hit.cpu().numpy().view(np.uint64), want), n
+    gpu.close()

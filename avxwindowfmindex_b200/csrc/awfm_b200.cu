@@ -632,8 +632,8 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
     const uint32_t k = sweepSeedK(c, len);
     if (c->ix.amino) {  // 5 bits per remaining letter in a 32-bit payload, 20^k seed entries in a 32-bit key
       if (k == 0 || k > 7 || len < k || len - k > 6 || len > 64) return false;
-    } else if (k == 0 || k > 16 || len < k || len - k > 16) {
-      return false;
+    } else if (k == 0 || k > 16 || len < k || len - k > kSweepMaxRestNuc || len > 32) {
+      return false;  // (17..24 letters left of the seed: sweepRefill; the pack kernels hold a query in 64 bits)
     }
   }
   if (c->sweepMinQueries > 0) return n >= (uint64_t)c->sweepMinQueries;
@@ -663,7 +663,7 @@ static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
   w.bytes = 0;
   w.cap = 0;
   const uint64_t cap = (n + (n >> 4) + 1024 + 15) & ~15ull;  // multiple of 16 records: every carved buffer 64-B aligned
-  const uint64_t bytes = cap * (2 * 4 + 2 * 8 + 2 * (uint64_t)arrays * 16 + 4);
+  const uint64_t bytes = cap * (2 * 4 + 2 * 8 + 2 * (uint64_t)arrays * 16 + 4 + 4);
   if (cudaMalloc(&w.arena, bytes) != cudaSuccess) {
     cudaGetLastError();
     w.arena = nullptr;
@@ -674,7 +674,8 @@ static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {
     for (int a = 0; a < arrays; a++) w.recs[g][a] = reinterpret_cast<uint4 *>(p), p += cap * 16;
   for (int i = 0; i < 2; i++) w.vals[i] = reinterpret_cast<uint64_t *>(p), p += cap * 8;
   for (int i = 0; i < 2; i++) w.keys[i] = reinterpret_cast<uint32_t *>(p), p += cap * 4;
-  w.irregularIds = reinterpret_cast<uint32_t *>(p);
+  w.irregularIds = reinterpret_cast<uint32_t *>(p), p += cap * 4;
+  w.more = reinterpret_cast<uint32_t *>(p);
   w.cap = cap;
   w.arrays = arrays;
   w.bytes = bytes;
@@ -745,7 +746,9 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   compact.restBits = variable ? SweepAlphabet<AMINO>::kLetterBits * kVarMaxRest + 1u : SweepAlphabet<AMINO>::kLetterBits * steps;
   compact.idBits = 1;
   while (compact.idBits < 32 && n > (1ull << compact.idBits) - 1ull) compact.idBits++;  // all ones = irregular query
-  const bool compactPairs = ownSort && dB > 0 && c->sweepCompactPairs && compact.keyBits + compact.restBits <= 63 &&
+  // more than 16 letters left of the seed (nucleotide, fixed length): letters 17.. wait in w.more for sweepRefill
+  uint32_t *more = (!AMINO && !variable && steps > 16) ? w.more : nullptr;
+  const bool compactPairs = ownSort && dB > 0 && !more && c->sweepCompactPairs && compact.keyBits + compact.restBits <= 63 &&
                             compact.lowBits + compact.restBits + compact.idBits <= 64 && n <= (1ull << compact.idBits) - 1ull;
   const uint32_t compactShift = compactPairs ? compact.keyBits : 0u;
   {
@@ -755,7 +758,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       sweepPackVar<AMINO><<<grid, 256, 0, st>>>(dLetters, dOffsets, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift);
     } else if (format == AWFM_QUERY_2BIT) {  // nucleotide only (sweepEligible): the packed bytes straight into (key, payload)
       const size_t smem = ((size_t)256 * ((len + 3) / 4) + 15) & ~(size_t)15;
-      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA, compactShift);
+      sweepPackBits<<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], sortCtrl, shiftA, compactShift, more);
     } else if (AMINO && len % 4 == 0 && len <= 12) {
       const uint32_t *words = reinterpret_cast<const uint32_t *>(dLetters);
       switch (len / 4) {
@@ -768,7 +771,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       switch (len / 4) {
 #define AWFM_PACK_CASE(W)                                                                                         \
   case W:                                                                                                         \
-    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift); \
+    sweepPackWords<W><<<grid, 256, 0, st>>>(words, n, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift, more); \
     break;
         AWFM_PACK_CASE(1) AWFM_PACK_CASE(2) AWFM_PACK_CASE(3) AWFM_PACK_CASE(4) AWFM_PACK_CASE(5) AWFM_PACK_CASE(6)
         AWFM_PACK_CASE(7) AWFM_PACK_CASE(8)
@@ -777,7 +780,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       }
     } else {
       const size_t smem = ((size_t)256 * len + 15) & ~(size_t)15;
-      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift);
+      sweepPack<AMINO><<<grid, 256, smem, st>>>(dLetters, n, len, k, w.keys[0], w.vals[0], w.irregularIds, irregularCount, sortCtrl, shiftA, compactShift, more);
     }
     CU(cudaGetLastError());
   }
@@ -861,6 +864,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   // 12-byte records (nucleotide, at most 8 letters left of the seed table's k-mer): see sweepStep
   const bool wide = !AMINO && (c->ix.bwtLength >= 0xFFFFFFF0ull || c->sweepWide);
   const bool rec12 = !AMINO && !variable && !wide && steps <= 8 && c->sweepRecord12;
+  uint32_t refills = 0;
   auto launchPass = [&](auto first, auto items, auto small, auto var, auto big, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
@@ -907,6 +911,11 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   mark();
   for (uint32_t pass = 1; pass < steps; pass++) {
     if (int r = launchPassItems(std::false_type(), pass)) return r;
+    if (more && pass == 15 && steps > 16) {  // generation 15 has prepended its 16 letters: the next ones from w.more
+      sweepRefill<<<(int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8), 256, 0, st>>>(gen(pass & 1, pass), more);
+      CU(cudaGetLastError());
+      refills++;
+    }
     mark();
   }
   if (format == AWFM_QUERY_ASCII) {
@@ -922,7 +931,7 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   CU(cudaEventRecord(w.done, st));
   w.stagesRecorded = stage;
   w.lastSteps = steps, w.lastBuckets = AMINO ? 20 : 4, w.lastQueries = n;
-  L.stats.launches += 2 + ((format == AWFM_QUERY_ASCII || rec12 || wide) ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches;
+  L.stats.launches += 2 + ((format == AWFM_QUERY_ASCII || rec12 || wide) ? 1 : 0) + (steps > 1 ? steps - 1 : 0) + sortLaunches + refills;
   return AWFM_GPU_OK;
 }
 

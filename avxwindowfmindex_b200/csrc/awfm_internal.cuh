@@ -57,6 +57,7 @@ struct SweepScratch {  // buffers of the sweep count path (awfm_sweep.cuh), grow
   int arrays = 0;                          // arrays per generation the arena was carved for
   uint32_t *ctrl = nullptr;                // [kSweepMaxPasses][stride] bucket counters, then the irregular-query counter
   uint32_t *irregularIds = nullptr;
+  uint32_t *more = nullptr;                // [cap] letters 17.. left of the seed k-mer (sweepRefill)
   void *sortCtrl = nullptr;                // awfm_sort.cuh: SortCtrl + group counts + group cursors
   void *sortTemp = nullptr;                // CUB's temporary storage (seed tables deeper than 2^24 entries)
   size_t sortTempBytes = 0;

@@ -37,7 +37,7 @@
 //
 // Exactness: same seed entries, same ranks (sectorRank), same stop rule; only the processing order differs, and the
 // result of a query does not depend on it.  Not covered here (the caller falls back to the tile kernels): fixed-length
-// batches with len - k > 16 (amino: 6), k > 16 (amino: 7), amino indexes beyond 2^32 positions, nucleotide ones beyond
+// batches with len - k > 24 or len > 32 (amino: len - k > 6), k > 16 (amino: 7), amino indexes beyond 2^32 positions, nucleotide ones beyond
 // 2^40; inside a variable-length batch, queries shorter than k or with more than 15 (amino: 6) letters left of the seed
 // are answered by sweepIrregular within the same call.
 #pragma once
@@ -53,7 +53,8 @@ namespace awfm {
 #endif
 constexpr int kSweepThreads = AWFM_SWEEP_THREADS;  // 256 or 512 (measured: profiles/r01_sweep_probe.jsonl)
 constexpr uint32_t kSweepNoId = 0xFFFFFFFFu;
-constexpr int kSweepMaxPasses = 18;
+constexpr int kSweepMaxPasses = 26;
+constexpr uint32_t kSweepMaxRestNuc = 24;   // fixed-length nucleotide batches: letters left of the seed k-mer (16 in the record + a refill)
 
 // One generation of live records: bucket b (= letter prepended last) lives in arr[b >> 1]; even buckets grow up
 // from slot 0, odd ones down from slot cap-1, so two buckets of unknown sizes share cap slots (total <= cap).
@@ -104,13 +105,17 @@ struct PackHistogram {
 };
 // One packed query leaves the pack kernel either as a (key, payload | id) pair or — compactShift != 0, the bucket
 // passes on compact pairs (awfm_sort.cuh) — as ONE word at index q: key | payload << compactShift, bit 63 = irregular.
+// Nucleotide batches with 17..24 letters left of the seed k-mer (32-mers on a k = 12 table): the pair holds the first 16
+// of them, letters 17.. go to more[q], from where sweepRefill hands them to the record once the 16 have been prepended.
 __device__ __forceinline__ void sweepStorePair(uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint64_t q, uint32_t key,
-                                               uint32_t payload, bool irregular, uint32_t compactShift) {
+                                               uint64_t payload, bool irregular, uint32_t compactShift,
+                                               uint32_t *__restrict__ more = nullptr) {
   if (compactShift) {
-    vals[q] = (uint64_t)key | ((uint64_t)payload << compactShift) | ((uint64_t)irregular << 63);
+    vals[q] = (uint64_t)key | (payload << compactShift) | ((uint64_t)irregular << 63);
   } else {
     keys[q] = key;
-    vals[q] = ((uint64_t)payload << 32) | (irregular ? kSweepNoId : (uint32_t)q);
+    vals[q] = (payload << 32) | (irregular ? kSweepNoId : (uint32_t)q);
+    if (more) more[q] = (uint32_t)(payload >> 32);
   }
 }
 __device__ __forceinline__ uint32_t packFourLetters(uint32_t w, uint32_t &bad) {
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(256)
     sweepPackWords(const uint32_t *__restrict__ words, uint64_t numQueries, uint32_t k, uint32_t *__restrict__ keys,
                    uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
                    uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
-                   uint32_t compactShift) {
+                   uint32_t compactShift, uint32_t *__restrict__ more /* or nullptr: at most 16 letters left of the seed */) {
   __shared__ uint32_t histShared[kSortBins];
   PackHistogram hist;
   hist.begin(histShared, sortCtrl);
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < WORDS; i++) Q = (Q << 8) | packFourLetters(w[i], bad);
     if (bad) irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)q;
-    sweepStorePair(keys, vals, q, (uint32_t)(Q & keyMask), (uint32_t)(Q >> (2 * k)), bad != 0, compactShift);
+    sweepStorePair(keys, vals, q, (uint32_t)(Q & keyMask), Q >> (2 * k), bad != 0, compactShift, more);
     hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
   }
   hist.flush(sortCtrl);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(256)
     sweepPack(const uint8_t *__restrict__ letters, uint64_t numQueries, uint32_t len, uint32_t k,
               uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, uint32_t *__restrict__ irregularIds,
               uint32_t *__restrict__ irregularCount, SortCtrl *__restrict__ sortCtrl, uint32_t shiftA,
-              uint32_t compactShift) {
+              uint32_t compactShift, uint32_t *__restrict__ more) {
   constexpr uint32_t CARD = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
   extern __shared__ __align__(16) uint8_t sLetters[];  // 256 * len bytes, rounded up to 16
   __shared__ uint32_t histShared[kSortBins];
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (threadIdx.x < nq) {
       const uint8_t *s = sLetters + threadIdx.x * len;
-      uint32_t key = 0, packed = 0, bad = 0;
+      uint32_t key = 0, bad = 0;
+      uint64_t packed = 0;
       for (uint32_t i = 0; i < k; i++) {  // leftmost of the last k letters most significant
         const uint32_t l = letterIndex<AMINO>(s[rest + i]);
         bad |= l >= CARD;
@@ -232,10 +238,10 @@ __global__ void __launch_bounds__(256)
       for (uint32_t j = 0; j < rest; j++) {  // letter prepended at step j+1 is s[rest-1-j]: low bits first
         const uint32_t l = letterIndex<AMINO>(s[rest - 1 - j]);
         bad |= l >= CARD;
-        packed |= (l < CARD ? l : 0u) << (LB * j);
+        packed |= (uint64_t)(l < CARD ? l : 0u) << (LB * j);
       }
       if (bad) irregularIds[atomicAdd(irregularCount, 1u)] = (uint32_t)(q0 + threadIdx.x);
-      sweepStorePair(keys, vals, q0 + threadIdx.x, key, packed, bad != 0, compactShift);
+      sweepStorePair(keys, vals, q0 + threadIdx.x, key, packed, bad != 0, compactShift, more);
       hist.add(sortCtrl, key, shiftA);
     }
   }
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(256)
 static __global__ void __launch_bounds__(256)
     sweepPackBits(const uint8_t *__restrict__ packed, uint64_t numQueries, uint32_t len, uint32_t k,
                   uint32_t *__restrict__ keys, uint64_t *__restrict__ vals, SortCtrl *__restrict__ sortCtrl,
-                  uint32_t shiftA, uint32_t compactShift) {
+                  uint32_t shiftA, uint32_t compactShift, uint32_t *__restrict__ more) {
   extern __shared__ __align__(16) uint8_t sPacked[];  // 256 * B bytes, rounded up to 16
   __shared__ uint32_t histShared[kSortBins];
   PackHistogram hist;
@@ -288,7 +294,7 @@ static __global__ void __launch_bounds__(256)
       uint64_t r = __brevll(raw);  // letter j: bits (2j, 2j+1) -> (63-2j, 62-2j)
       r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);  // ... -> (62-2j, 63-2j)
       const uint64_t Q = r >> (64u - 2u * len);  // first letter most significant, 2 bits per letter
-      sweepStorePair(keys, vals, q0 + threadIdx.x, (uint32_t)(Q & keyMask), (uint32_t)(Q >> (2 * k)), false, compactShift);
+      sweepStorePair(keys, vals, q0 + threadIdx.x, (uint32_t)(Q & keyMask), Q >> (2 * k), false, compactShift, more);
       hist.add(sortCtrl, (uint32_t)(Q & keyMask), shiftA);
     }
   }
@@ -966,6 +972,23 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
         }
       }
     }
+  }
+}
+
+// sweepRefill (fixed-length nucleotide batches with more than 16 letters left of the seed k-mer): the records of
+// generation `gen` have prepended the 16 letters they carried; each takes the query's next letters from more[id]
+// (written by the pack kernel) into its letters word.  16-byte records, plain or WIDE: id = word 2, letters = word 3.
+static __global__ void __launch_bounds__(256) sweepRefill(const __grid_constant__ SweepRecs gen, const uint32_t *__restrict__ more) {
+  const uint32_t c0 = gen.count[0], c1 = gen.count[1], c2 = gen.count[2], c3 = gen.count[3];
+  const uint32_t before1 = c0, before2 = c0 + c1, before3 = before2 + c2, total = before3 + c3;
+  const uint32_t last = (uint32_t)gen.cap - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;  // buckets 0/2 grow up, 1/3 down (sweepStep)
+    const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
+    const bool odd = ge1 != ge2 || ge3;
+    const uint32_t r = i - first;
+    uint32_t *rec = reinterpret_cast<uint32_t *>(gen.arr[ge2 ? 1 : 0] + (odd ? last - r : r));
+    rec[3] = __ldg(more + rec[2]);
   }
 }
 

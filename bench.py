@@ -820,6 +820,18 @@ def leg_cfg5(env):
     env.barrier()
     ms = env.max_over_ranks(ev0.elapsed_time(ev1) / steps)
     ms_count = env.event_ms(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream), reps=3)
+    # which path the count took (automatic choice; 32-mers on a k = 12 table: 20 letters left of the seed, sweepRefill)
+    # and the tile kernel on the same batch beside it
+    gpu.set_tuning(sweep_profile=1)
+    gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream)
+    torch.cuda.synchronize()
+    count_stages = gpu.sweep_stage_ms()
+    gpu.set_tuning(sweep_profile=0, sweep_min_queries=-1)
+    d_ranges_tile = torch.zeros_like(d_ranges)
+    ms_count_tile = env.event_ms(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges_tile.data_ptr(), stream), reps=3)
+    tile_same = bool(torch.equal(d_ranges_tile, d_ranges))
+    del d_ranges_tile
+    gpu.set_tuning(sweep_min_queries=0)
     ms_walk = env.event_ms(lambda: gpu.locate_device(d_ranges.data_ptr(), d_hit.data_ptr(), n, 0, hits, d_pos.data_ptr(), stream), reps=3)
     ms_map = env.event_ms(lambda: gpu.map_positions_device(d_pos.data_ptr(), hits, d_seq.data_ptr(), d_loc.data_ptr(), stream), reps=3)
     # by-construction check of EVERY query of this rank: the (contig, offset) it was cut from is among its hits
@@ -843,6 +855,9 @@ def leg_cfg5(env):
            "n_gpus": world, "queries_per_gpu": n, "hits_total": all_hits, "ms_per_step": ms, "steps": steps,
            "locate_queries_per_s": world * n / ms * 1e3, "located_and_mapped_hits_per_s": all_hits / ms * 1e3,
            "kernel_ms_rank0": {"count_with_ranges": ms_count, "expand+walk": ms_walk, "contig_map": ms_map},
+           "count_path": "sweep (20 passes, letters 17-20 through sweepRefill)" if count_stages else "tile kernel",
+           "count_stages_ms": [round(x, 3) for x in count_stages], "count_tile_kernel_ms": ms_count_tile,
+           "count_ranges_equal_to_tile_kernel_all_queries": tile_same,
            "every_query_found_at_its_origin": ok_all, "index_build_gpu_ms": build_ms, "scaling": "weak",
            "gather": ("copy-engine peer writes of (position, contig, offset) rows into rank 0's buffer, inside the timed step"
                       if gather is not None else None), "gathered_rows_check": gathered_ok}

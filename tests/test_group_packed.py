@@ -53,7 +53,7 @@ def test_group_count_every_format(small_indexes, name, sweep):
     # small chunks and shards so that the pipeline has several chunks per device and both devices get a shard
     group.set_tuning(packed_chunk_queries=1024, packed_min_shard=512, sweep_min_queries=1 if sweep else -1)
     bits_fmt = QUERY_5BIT if b.amino else QUERY_2BIT
-    for length in (k, k + 1, k + 4, (k + 6) if b.amino else 20, 31):
+    for length in (k, k + 1, k + 4, (k + 6) if b.amino else 20, 31) + (() if b.amino else (28, 29, 32)):
         letters = fixed_queries(b, length, 5000 + length, seed=length)
         o_counts, _, _ = oracle.count(letters, fixed_len=length)
         counts = group.count(letters, QUERY_ASCII, fixed_len=length)

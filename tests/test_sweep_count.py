@@ -92,7 +92,8 @@ def test_sweep_matches_oracle(small_indexes, name):
     k = b.arrays.seed_k
     oracle = harness.Oracle(b.arrays)
     gpu = GpuIndex(b.arrays)
-    for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 5, 255), (k + 8, 5000), (k + 16, 1031), (k + 3, 20000)):
+    for length, num in ((k, 700), (k + 1, 513), (k + 2, 1), (k + 5, 255), (k + 8, 5000), (k + 16, 1031), (k + 3, 20000),
+                        (k + 17, 900), (k + 20, 3001), (k + 24, 1500)):  # 17..24 letters left of the seed: sweepRefill
         letters = fixed_batch(b, length, num, seed=length * 31 + num)
         o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
         for bits, local, items in ((32, 8, 4), (16, 0, 2), (0, 8, 1), (3, 5, 8), (32, 0, 4)):
@@ -208,9 +209,12 @@ def test_sweep_falls_back_outside_its_domain(small_indexes):
     oracle = harness.Oracle(b.arrays)
     gpu = GpuIndex(b.arrays)
     gpu.set_tuning(sweep_min_queries=1)
-    letters = fixed_batch(b, k + 17, 300, seed=5)
-    o_counts, o_ranges, _ = oracle.count(letters, fixed_len=k + 17)
-    assert np.array_equal(gpu.count(letters, fixed_len=k + 17), o_counts)
+    for length in (k + 25, 33, 40):  # more than 24 letters left of the seed / more than 32 letters in all
+        letters = fixed_batch(b, length, 300, seed=5)
+        o_counts, o_ranges, _ = oracle.count(letters, fixed_len=length)
+        gpu.set_tuning(sweep_profile=1)
+        assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
+        assert not gpu.sweep_stage_ms(), "a batch outside the sweep's domain took it"
     letters = fixed_batch(b, k + 4, 300, seed=6)
     o_counts, o_ranges, _ = oracle.count(letters, fixed_len=k + 4)
     counts, ranges = gpu.count(letters, fixed_len=k + 4, want_ranges=True)

@@ -405,6 +405,7 @@ static void freeSlot(PipeSlot &s) {
   if (s.hLetters) cudaFreeHost(s.hLetters);
   if (s.hOffsets) cudaFreeHost(s.hOffsets);
   if (s.hCounts) cudaFreeHost(s.hCounts);
+  free(s.hOld);
   cudaFree(s.dLetters);
   cudaFree(s.dOffsets);
   cudaFree(s.dCounts);
@@ -475,7 +476,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_local_bits" && value >= -1 && value <= 8) c->sweepLocalBits = (int)value;
   else if (k == "sweep_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepItems = (int)value;
   else if (k == "sweep_first_items" && (value == 1 || value == 2 || value == 4 || value == 8)) c->sweepFirstItems = (int)value;
-  else if (k == "chunk_queries" && value >= 64 && value <= (1ll << 30)) c->chunkQueries = value;
+  else if (k == "chunk_queries" && (value == 0 || (value >= 64 && value <= (1ll << 30)))) c->chunkQueries = value;
   else if (k == "locate_chunk_queries" && value >= 64 && value <= (1ll << 30)) c->locateChunkQueries = value;
   else if (k == "locate_inline_hits" && value >= 0 && value <= (1ll << 32)) c->locateInlineHits = value;
   else if (k == "locate_window_hits" && value >= 1 && value <= (1ll << 32)) c->locateWindowHits = value;
@@ -1471,8 +1472,10 @@ static int ensureSlot(PipeSlot &s, uint64_t queries, uint64_t letterBytes, bool 
     cudaFree(s.dOffsets);
     cudaFree(s.dCounts);
     cudaFree(s.dRanges);
-    s.hOffsets = nullptr, s.hCounts = nullptr, s.dOffsets = nullptr, s.dCounts = nullptr, s.dRanges = nullptr;
+    free(s.hOld);
+    s.hOffsets = nullptr, s.hCounts = nullptr, s.dOffsets = nullptr, s.dCounts = nullptr, s.dRanges = nullptr, s.hOld = nullptr;
     s.queryCap = 0;
+    if (!(s.hOld = static_cast<uint32_t *>(malloc(queries * 4)))) return awfm_fail(AWFM_GPU_ERR_ALLOC, "host memory for a pipeline slot");
     CU(cudaHostAlloc(&s.hOffsets, (queries + 1) * 8, cudaHostAllocPortable));
     CU(cudaHostAlloc(&s.hCounts, queries * 4, cudaHostAllocPortable));
     CU(cudaMalloc(&s.dOffsets, (queries + 1) * 8));
@@ -1545,6 +1548,7 @@ struct TeamPack {
   uint64_t n = 0, len0 = 0;
   bool optimistic = false, direct = false, fallback = false, wantRanges = false;
   uint8_t *staging = nullptr;
+  uint32_t *old = nullptr;  // count engine: every entry's current `count` is noted while its line is being read anyway
   const uint8_t *base = nullptr;
   int uniformAll = 1, contiguousAll = 1;
   std::vector<uint64_t> partSum;
@@ -1566,6 +1570,7 @@ static void teamPackPrepare(TeamPack &tp, PipeSlot &s, const awfm_kmer_search_da
   // later only grow the (portable, page-locked) host staging
   tp.rc = ensureSlot(s, n, (!tp.optimistic || tp.direct) ? 16 : n * tp.len0 + 16, wantRanges);
   tp.staging = s.hLetters;
+  tp.old = wantRanges ? nullptr : s.hOld;
   tp.uniformAll = tp.contiguousAll = 1;
   tp.fallback = !tp.optimistic;
 }
@@ -1576,19 +1581,29 @@ static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
   const uint64_t n = tp.n, len0 = tp.len0;
   const bool worker = t >= 0;  // t < 0: a thread that only keeps the team's barriers (the count engine's driver)
   const uint64_t a = worker ? n * t / T : 0, b = worker ? n * (t + 1) / T : 0;
+  uint32_t *old = tp.rc == AWFM_GPU_OK ? tp.old : nullptr;
   if (n && tp.rc == AWFM_GPU_OK && tp.optimistic) {
     bool uni = true, con = true;
     if (tp.direct) {
       const uint8_t *base = tp.base;
-      for (uint64_t i = a; i < b; i++) {
-        uni &= d0[i].kmerLength == len0;
-        con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+      if (old) {
+        for (uint64_t i = a; i < b; i++) {
+          uni &= d0[i].kmerLength == len0;
+          con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+          old[i] = d0[i].count;
+        }
+      } else {
+        for (uint64_t i = a; i < b; i++) {
+          uni &= d0[i].kmerLength == len0;
+          con &= (const uint8_t *)d0[i].kmerString == base + i * len0;
+        }
       }
     } else {
       uint8_t *staging = tp.staging;
       for (uint64_t i = a; i < b && uni; i++) {
         uni = d0[i].kmerLength == len0;
         if (uni) copyLetters(staging + i * len0, (const uint8_t *)d0[i].kmerString, len0);
+        if (old) old[i] = d0[i].count;
       }
     }
     if (!uni) {
@@ -1619,7 +1634,10 @@ static void teamPack(TeamPack &tp, PipeSlot &s, int t, int T) {
 #pragma omp barrier
     } else if (!tp.optimistic || !tp.uniformAll) {
       uint64_t sum = 0;
-      for (uint64_t i = a; i < b; i++) sum += d0[i].kmerLength;
+      for (uint64_t i = a; i < b; i++) {
+        sum += d0[i].kmerLength;
+        if (old) old[i] = d0[i].count;
+      }
       if (worker) tp.partSum[t + 1] = sum;
 #pragma omp barrier
 #pragma omp master

@@ -74,6 +74,7 @@ struct PipeSlot {  // one in-flight chunk of the search-list engine
   uint64_t lettersCap = 0, dLettersCap = 0;
   uint64_t *hOffsets = nullptr, *dOffsets = nullptr;
   uint32_t *hCounts = nullptr, *dCounts = nullptr;
+  uint32_t *hOld = nullptr;  // count engine: the counts the chunk's entries held when they were packed (pageable)
   uint4 *dRanges = nullptr;
   uint64_t queryCap = 0;
   cudaStream_t stream = nullptr;
@@ -124,7 +125,7 @@ struct awfm_gpu_ctx {
   bool hasSa = false;
   // tuning
   int countLpq = 2, locateLpq = 2, countVariant = 1, locateVariant = 1, ctaThreads = 256, blocksPerSm = 0 /* 0 = occupancy */;
-  int64_t chunkQueries = 1 << 16;
+  int64_t chunkQueries = 0;  // list count engine: queries per chunk; 0 = automatic (awfm_list_engine.inc)
   int64_t locateChunkQueries = 1 << 18;
   int64_t locateInlineHits = 1 << 22;  // a chunk with more hits than this is finished through windows of ...
   int64_t locateWindowHits = 1 << 26;  // ... this many flat hit indices

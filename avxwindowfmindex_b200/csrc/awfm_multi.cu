@@ -628,7 +628,8 @@ static int groupList(awfm_gpu_group *g, awfm_kmer_search_data *data, uint64_t n,
   if (!g || g->dev.empty()) return awfm_fail(AWFM_GPU_ERR_ARG, "null argument");
   std::vector<awfm_gpu_ctx *> ctxs;
   // a list too short to give every device a chunk uses fewer devices
-  const uint64_t chunk = (uint64_t)(locate ? g->dev[0]->ctx->locateChunkQueries : g->dev[0]->ctx->chunkQueries);
+  const int64_t countChunk = g->dev[0]->ctx->chunkQueries > 0 ? g->dev[0]->ctx->chunkQueries : (1ll << 16);  // 0 = automatic, at least 2^16
+  const uint64_t chunk = (uint64_t)(locate ? g->dev[0]->ctx->locateChunkQueries : countChunk);
   const uint64_t chunks = std::max<uint64_t>(1, (n + chunk - 1) / chunk);
   for (size_t d = 0; d < g->dev.size() && d < chunks; d++) ctxs.push_back(g->dev[d]->ctx);
   const int rc = awfm_search_list_run(ctxs.data(), (int)ctxs.size(), data, n, numThreads, locate);

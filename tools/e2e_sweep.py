@@ -20,13 +20,19 @@ del d_q
 sl = KmerSearchList(lib, n)
 os.environ["AWFM_GPU_VERBOSE"] = "1"
 threads = os.cpu_count()
-for src_name, src in (("pinned", pinned.numpy()), ("pageable", pageable)):
+chunks = [int(x) for x in os.environ.get("CHUNKS", "32768,65536,131072,262144,1048576").split(",")]
+sources = (("pinned", pinned.numpy()), ("pageable", pageable)) if not os.environ.get("PINNED_ONLY") else (("pinned", pinned.numpy()),)
+for src_name, src in sources:
     sl.fill(src, fixed_len=L)
-    for chunk in (1 << 16, 1 << 18, 1 << 19, 1 << 20, 1 << 21):
+    counts = sl.entries()["count"]
+    for chunk in chunks:
         os.environ["AWFM_GPU_CHUNK_QUERIES"] = str(chunk)
         lib.awFmGpuReleaseIndex(ip)
         lib.awFmParallelSearchCount(ip, sl.ptr, threads)
-        best = 1e9
-        for _ in range(3):
-            t0 = time.perf_counter(); lib.awFmParallelSearchCount(ip, sl.ptr, threads); best = min(best, time.perf_counter() - t0)
-        print(f"RESULT {src_name} chunk={chunk} best={best*1e3:.1f} ms -> {n/best/1e6:.0f} Mq/s", flush=True)
+        # fresh: count == 0 everywhere before the call (awFmCreateKmerSearchList's state); stale: every count has to be rewritten
+        for state, value in (("fresh", 0), ("stale", 0xFFFFFFFF)):
+            best = 1e9
+            for _ in range(3):
+                counts[:n] = value
+                t0 = time.perf_counter(); lib.awFmParallelSearchCount(ip, sl.ptr, threads); best = min(best, time.perf_counter() - t0)
+            print(f"RESULT {src_name} chunk={chunk} list={state} best={best*1e3:.1f} ms -> {n/best/1e6:.0f} Mq/s", flush=True)

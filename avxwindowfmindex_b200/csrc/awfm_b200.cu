@@ -936,8 +936,8 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   return AWFM_GPU_OK;
 }
 
-// Batches larger than "sweep_max_batch" queries go through the scratch in slices (92 B of scratch per query of a
-// slice for nucleotide indexes, 348 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
+// Batches larger than "sweep_max_batch" queries go through the scratch in slices (96 B of scratch per query of a
+// slice for nucleotide indexes, 352 B for amino ones: two generations of 2 | 10 record arrays + the sort buffers).
 static int sweepCount(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, const uint64_t *dOffsets, uint32_t format,
                       uint32_t len, uint64_t n, uint32_t *dCounts, uint4 *dRanges, bool hitsOnly, cudaStream_t st) {
   const bool amino = c->ix.amino != 0;

@@ -125,7 +125,8 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * "count_variant" (0 group-per-query from global memory, 1 CTA tiles staged in shared memory), "locate_variant"
  * (0 group-per-hit, 1 group-per-hit with refill), "blocks_per_sm" (0 = occupancy query), "use_deep_seed_table" (0/1:
  * A/B switch for a table already derived with awfm_gpu_ctx_extend_seed_table); of the search-list engine:
- * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate), "locate_inline_hits" (a
+ * "chunk_queries" / "locate_chunk_queries" (queries per pipeline chunk of count / locate; chunk_queries 0 = automatic,
+ * a power of two between 2^16 and 2^19 that leaves every device about 48 chunks), "locate_inline_hits" (a
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
  * Sweep count path (csrc/awfm_sweep.cuh; large batches of either alphabet, fixed or variable length, counts and ranges):
  * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per two 128-B lines of the index) queries and no
@@ -133,7 +134,7 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * index the radix sort orders, default 32 = all but the low "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 =
  * automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items" /
  * "sweep_first_items" (records per thread and tile of the later passes / of the first pass: 1, 2, 4, 8; default 4),
- * "sweep_max_batch" (queries per slice of the scratch — 92 B per query, 348 B for amino indexes —, default 2^27; when
+ * "sweep_max_batch" (queries per slice of the scratch — 96 B per query, 352 B for amino indexes —, default 2^27; when
  * even that does not fit the call is answered by the tile kernel), "sweep_profile" (0/1: record an event after every
  * stage of the next calls), "sweep_own_sort" (1, the default: the hand-written bucket passes of csrc/awfm_sort.cuh order
  * the pairs whenever at most 16 key bits have to be ordered globally; 0: CUB's radix sort, kept as cross-check and for

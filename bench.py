@@ -988,7 +988,8 @@ def leg_fanout(env, arrays, h_bits_rank0, want_counts_rank0):
             devices = lib.awFmGpuNumDevices(ip)
             ts = wall_times(lambda: lib.awFmParallelSearchCount(ip, sl.ptr, env.cores), reps=a.e2e_steps, warm=1)
             ok = bool(np.array_equal(sl.counts()[:1_000_000], want_counts_rank0[:1_000_000]))
-            out["dropin_all_gpus"] = {"call": "awFmParallelSearchCount with AWFM_GPU_DEVICES=all", "devices": int(devices),
+            out["dropin_all_gpus"] = {"call": "awFmParallelSearchCount with AWFM_GPU_DEVICES=all (query strings back to back in PAGEABLE memory: "
+                                              "the engine copies them to page-locked staging)", "devices": int(devices),
                                       "queries": nl, "ms_per_call": 1e3 * min(ts), "queries_per_s": nl / min(ts),
                                       "host_threads": env.cores, "bit_exact_sample": ok}
             sl.close()

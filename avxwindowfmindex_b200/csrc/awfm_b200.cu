@@ -470,6 +470,7 @@ extern "C" int awfm_gpu_ctx_set_tuning(awfm_gpu_ctx *c, const char *key, int64_t
   else if (k == "sweep_profile" && (value == 0 || value == 1)) c->sweepProfile = (int)value;
   else if (k == "sweep_own_sort" && (value == 0 || value == 1)) c->sweepOwnSort = (int)value;
   else if (k == "sweep_record12" && (value == 0 || value == 1)) c->sweepRecord12 = (int)value;
+  else if (k == "sweep_ordered_emit" && (value == 0 || value == 1)) c->sweepOrderedEmit = (int)value;
   else if (k == "sweep_compact_pairs" && (value == 0 || value == 1)) c->sweepCompactPairs = (int)value;
   else if (k == "sweep_variable" && (value == 0 || value == 1)) c->sweepVariable = (int)value;
   else if (k == "sweep_wide" && (value == 0 || value == 1)) c->sweepWide = (int)value;
@@ -866,13 +867,18 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   const bool wide = !AMINO && (c->ix.bwtLength >= 0xFFFFFFF0ull || c->sweepWide);
   const bool rec12 = !AMINO && !variable && !wide && steps <= 8 && c->sweepRecord12;
   uint32_t refills = 0;
-  auto launchPass = [&](auto first, auto items, auto small, auto var, auto big, uint32_t pass) -> int {
+  // Ordered emit (sweepStep<EMIT>, sweepEmit): range output of a fixed-length nucleotide batch small enough for a quarter
+  // of its counts and ranges (20 B per query) to stay in L2 while it is written.
+  const bool emit = !AMINO && !variable && !rec12 && dRanges && steps >= 1 && c->sweepOrderedEmit && n >= 4 && n <= (1ull << 24);
+  const uint32_t emitDiv = (uint32_t)((n + 3) / 4);
+  auto launchPass = [&](auto first, auto items, auto small, auto var, auto big, auto ordered, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
     constexpr bool VARLEN = decltype(var)::value;
     constexpr bool WIDE = decltype(big)::value && !AMINO;
     constexpr bool REC12 = decltype(small)::value && !AMINO && !VARLEN && !WIDE;
-    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12, VARLEN, WIDE>;
+    constexpr bool EMIT = decltype(ordered)::value && !AMINO && !VARLEN && !REC12;
+    auto kf = sweepStep<FIRST, ITEMS, AMINO, REC12, VARLEN, WIDE, EMIT>;
     int grid = 0;
     if (int r = gridFor(c, kf, kSweepThreads, &grid)) return r;
     const uint64_t tile = (uint64_t)kSweepThreads * ITEMS;
@@ -880,25 +886,30 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
     if (FIRST)
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, w.keys[cur], w.vals[cur], n, deep, gen(1, kSweepMaxPasses - 1), gen(0, 0),
                                          steps, localBits | (localShift << 8), dCounts, dRanges, w.irregularIds, irregularCount,
-                                         hitsOnly);
+                                         hitsOnly, emitDiv);
     else  // pass p does LF step p+1 of the queries still alive
       kf<<<grid, kSweepThreads, 0, st>>>(c->ix, nullptr, nullptr, 0, deep, gen((pass - 1) & 1, pass - 1),
                                          gen(pass & 1, pass), steps - pass, 0u, dCounts, dRanges, w.irregularIds, irregularCount,
-                                         hitsOnly);
+                                         hitsOnly, emitDiv);
     CU(cudaGetLastError());
     return AWFM_GPU_OK;
   };
   auto launchPassRec = [&](auto first, auto items, uint32_t pass) -> int {
-    return rec12 ? launchPass(first, items, std::true_type(), std::false_type(), std::false_type(), pass)
-                 : launchPass(first, items, std::false_type(), std::false_type(), std::false_type(), pass);
+    if (emit && pass + 1 == steps)  // the last pass hands its survivors to sweepEmit
+      return launchPass(first, items, std::false_type(), std::false_type(), std::false_type(), std::true_type(), pass);
+    return rec12 ? launchPass(first, items, std::true_type(), std::false_type(), std::false_type(), std::false_type(), pass)
+                 : launchPass(first, items, std::false_type(), std::false_type(), std::false_type(), std::false_type(), pass);
   };
   auto launchPassItems = [&](auto first, uint32_t pass) -> int {
     // variable lengths / 64-bit positions: one instantiation per pass kind, 4 records per thread
     constexpr auto four = std::integral_constant<int, 4>();
-    if (wide)
-      return variable ? launchPass(first, four, std::false_type(), std::true_type(), std::true_type(), pass)
-                      : launchPass(first, four, std::false_type(), std::false_type(), std::true_type(), pass);
-    if (variable) return launchPass(first, four, std::false_type(), std::true_type(), std::false_type(), pass);
+    if (wide) {
+      if (variable) return launchPass(first, four, std::false_type(), std::true_type(), std::true_type(), std::false_type(), pass);
+      if (emit && pass + 1 == steps)
+        return launchPass(first, four, std::false_type(), std::false_type(), std::true_type(), std::true_type(), pass);
+      return launchPass(first, four, std::false_type(), std::false_type(), std::true_type(), std::false_type(), pass);
+    }
+    if (variable) return launchPass(first, four, std::false_type(), std::true_type(), std::false_type(), std::false_type(), pass);
     switch (decltype(first)::value ? c->sweepFirstItems : c->sweepItems) {
       case 1: return launchPassRec(first, std::integral_constant<int, 1>(), pass);
       case 2: return launchPassRec(first, std::integral_constant<int, 2>(), pass);
@@ -908,10 +919,21 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
       default: return launchPassRec(first, std::integral_constant<int, 4>(), pass);
     }
   };
+  auto emitSurvivors = [&](uint32_t pass) -> int {  // after the last pass (pass + 1 == steps)
+    if (!emit || pass + 1 != steps) return AWFM_GPU_OK;
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8);
+    if (wide) sweepEmit<true><<<grid, 256, 0, st>>>(gen(pass & 1, pass), dCounts, dRanges);
+    else sweepEmit<false><<<grid, 256, 0, st>>>(gen(pass & 1, pass), dCounts, dRanges);
+    CU(cudaGetLastError());
+    refills++;
+    return AWFM_GPU_OK;
+  };
   if (int r = launchPassItems(std::true_type(), 0)) return r;
+  if (int r = emitSurvivors(0)) return r;
   mark();
   for (uint32_t pass = 1; pass < steps; pass++) {
     if (int r = launchPassItems(std::false_type(), pass)) return r;
+    if (int r = emitSurvivors(pass)) return r;
     if (more && pass == 15 && steps > 16) {  // generation 15 has prepended its 16 letters: the next ones from w.more
       sweepRefill<<<(int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8), 256, 0, st>>>(gen(pass & 1, pass), more);
       CU(cudaGetLastError());

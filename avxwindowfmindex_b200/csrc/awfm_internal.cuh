@@ -132,6 +132,7 @@ struct awfm_gpu_ctx {
   int64_t sweepMinQueries = 0;  // 0 = automatic (see sweepEligible); 1 = whenever the batch qualifies; < 0 = never
   int64_t sweepMaxBatch = 1ll << 27;
   int sweepSortBits = 32, sweepLocalBits = -1 /* automatic */, sweepProfile = 0, sweepItems = 4, sweepFirstItems = 4;
+  int sweepOrderedEmit = 1;  // range output of batches of up to 2^24 queries: survivors leave through sweepEmit (awfm_sweep.cuh)
   int sweepRecord12 = 0;  // 12-byte live records when the batch allows it (nucleotide, <= 8 letters left of the seed)
   int sweepWide = 0;      // 1: the 64-bit-position passes even on an index below 2^32 positions (cross-check)
   int sweepVariable = 1;  // variable-length batches may take the sweep (marker-bit payloads, sweepPackVar)

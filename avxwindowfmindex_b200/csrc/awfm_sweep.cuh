@@ -599,14 +599,23 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // WIDE (nucleotide indexes of 2^32 .. 2^40 positions): 64-bit positions in registers; a record is still 16 bytes —
 // {sp bits 0-31, sp bits 32-39 | range width << 8, id, letters} — because a range only narrows from step to step: a
 // query whose SEED range is wider than 2^24 - 2 leaves for the irregular list once, in the first pass.
-template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false, bool WIDE = false>
+// EMIT (the LAST pass of a fixed-length nucleotide batch with range output and many survivors — locate workloads): a
+// query that has prepended all its letters does not store its count and range at [id] from here — ids are in no order
+// by now, so that is two scattered partial-sector stores per query, each a read-modify-write in DRAM (cfg 5, 10 M
+// 32-mers all found: 0.70 ms for the last pass against 0.145 for any other) — but is appended once more, to the
+// bucket of the QUARTER of the id space its id lies in (id / emitDiv).  sweepEmit then writes the buckets out in order:
+// one quarter's slice of counts and ranges (20 B per query) stays in L2 until its sectors are complete.
+template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false, bool WIDE = false,
+          bool EMIT = false>
 __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
     sweepStep(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ keys, const uint64_t *__restrict__ vals,
               uint64_t numPairs, bool deep, const __grid_constant__ SweepRecs in, const __grid_constant__ SweepRecs out,
               uint32_t steps, uint32_t localBits, uint32_t *__restrict__ counts,
               uint4 *__restrict__ ranges /* or nullptr: every query's final (sp, ep) as the reference leaves it */,
               uint32_t *__restrict__ irregularIds, uint32_t *__restrict__ irregularCount,
-              bool rangesOfHitsOnly /* ranges only of queries whose final range is non-empty (locate) */) {
+              bool rangesOfHitsOnly /* ranges only of queries whose final range is non-empty (locate) */,
+              uint32_t emitDiv /* EMIT: query ids per output bucket */) {
+  static_assert(!(EMIT && (AMINO || REC12 || VARLEN)), "ordered emit: fixed-length nucleotide batches, 16-byte records");
   static_assert(!(REC12 && AMINO), "12-byte records are a nucleotide format");
   static_assert(!(REC12 && VARLEN), "12-byte records hold 16 bits of letters, no room for the marker bit");
   static_assert(!(WIDE && (AMINO || REC12)), "64-bit positions: nucleotide, 16-byte records");
@@ -888,14 +897,18 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
       }
       bucket[it] = NB;  // no output
       if (valid) {
-        const bool last = VARLEN ? (steps <= 1 || rest[it] == 1u) : steps <= 1;
-        if (last && ranges) ranges[id[it]] = make_uint4((uint32_t)sp[it], (uint32_t)((uint64_t)sp[it] >> 32), (uint32_t)ep[it],
-                                                        (uint32_t)((uint64_t)ep[it] >> 32));
-        if (last) counts[id[it]] = (uint32_t)(ep[it] - sp[it] + 1u);
-        else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
+        if constexpr (EMIT) {  // (launched for the last pass only) count and range leave through sweepEmit
+          bucket[it] = min(id[it] / emitDiv, NB - 1u);
+        } else {
+          const bool last = VARLEN ? (steps <= 1 || rest[it] == 1u) : steps <= 1;
+          if (last && ranges) ranges[id[it]] = make_uint4((uint32_t)sp[it], (uint32_t)((uint64_t)sp[it] >> 32), (uint32_t)ep[it],
+                                                          (uint32_t)((uint64_t)ep[it] >> 32));
+          if (last) counts[id[it]] = (uint32_t)(ep[it] - sp[it] + 1u);
+          else bucket[it] = letter;  // grouped by the letter just prepended: sp' = C[c] + Occ(c, sp-1) keeps the order
+        }
       }
     }
-    if (steps <= 1) continue;  // last pass: nothing to append (uniform for the whole grid)
+    if (!EMIT && steps <= 1) continue;  // last pass: nothing to append (uniform for the whole grid)
     // ---- stable (inside the tile) append to the output buckets ----
     uint32_t rank[kSweepItems];  // (warpCount / bucketBase of the previous tile were consumed before this tile's ticket barrier)
 #pragma unroll
@@ -989,6 +1002,30 @@ static __global__ void __launch_bounds__(256) sweepRefill(const __grid_constant_
     const uint32_t r = i - first;
     uint32_t *rec = reinterpret_cast<uint32_t *>(gen.arr[ge2 ? 1 : 0] + (odd ? last - r : r));
     rec[3] = __ldg(more + rec[2]);
+  }
+}
+
+// sweepEmit: the survivors of an EMIT last pass, bucketed by the quarter of the id space, leave for counts[id] and
+// ranges[id].  The grid walks the buckets in order (a window of gridDim.x * 256 consecutive records at any moment), so
+// the stores of one moment fall into one quarter of the two output arrays.
+template <bool WIDE>
+static __global__ void __launch_bounds__(256) sweepEmit(const __grid_constant__ SweepRecs gen, uint32_t *__restrict__ counts,
+                                                        uint4 *__restrict__ ranges) {
+  const uint32_t c0 = gen.count[0], c1 = gen.count[1], c2 = gen.count[2], c3 = gen.count[3];
+  const uint32_t before1 = c0, before2 = c0 + c1, before3 = before2 + c2, total = before3 + c3;
+  const uint32_t last = (uint32_t)gen.cap - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;  // buckets 0/2 grow up, 1/3 down (sweepStep)
+    const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
+    const bool odd = ge1 != ge2 || ge3;
+    const uint32_t r = i - first;
+    const uint4 rec = __ldg(gen.arr[ge2 ? 1 : 0] + (odd ? last - r : r));
+    uint64_t sp, width;
+    if constexpr (WIDE) sp = (uint64_t)rec.x | ((uint64_t)(rec.y & 0xFFu) << 32), width = rec.y >> 8;
+    else sp = rec.x, width = rec.y;
+    const uint64_t ep = WIDE ? sp + width : (uint64_t)(uint32_t)(rec.x + rec.y);
+    counts[rec.z] = (uint32_t)width + 1u;
+    ranges[rec.z] = make_uint4((uint32_t)sp, (uint32_t)(sp >> 32), (uint32_t)ep, (uint32_t)(ep >> 32));
   }
 }
 

@@ -828,7 +828,9 @@ def leg_cfg5(env):
     gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream)
     torch.cuda.synchronize()
     count_stages = gpu.sweep_stage_ms()
-    gpu.set_tuning(sweep_profile=0, sweep_min_queries=-1)
+    gpu.set_tuning(sweep_profile=0, sweep_ordered_emit=0)  # survivors' counts and ranges scattered straight from the last pass
+    ms_count_scatter = env.event_ms(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges.data_ptr(), stream), reps=3)
+    gpu.set_tuning(sweep_ordered_emit=1, sweep_min_queries=-1)
     d_ranges_tile = torch.zeros_like(d_ranges)
     ms_count_tile = env.event_ms(lambda: gpu.count_device(d_q.data_ptr(), None, L, n, d_counts.data_ptr(), d_ranges_tile.data_ptr(), stream), reps=3)
     tile_same = bool(torch.equal(d_ranges_tile, d_ranges))
@@ -857,8 +859,9 @@ def leg_cfg5(env):
            "n_gpus": world, "queries_per_gpu": n, "hits_total": all_hits, "ms_per_step": ms, "steps": steps,
            "locate_queries_per_s": world * n / ms * 1e3, "located_and_mapped_hits_per_s": all_hits / ms * 1e3,
            "kernel_ms_rank0": {"count_with_ranges": ms_count, "expand+walk": ms_walk, "contig_map": ms_map},
-           "count_path": "sweep (20 passes, letters 17-20 through sweepRefill)" if count_stages else "tile kernel",
+           "count_path": "sweep (20 passes, letters 17-20 through sweepRefill, survivors through sweepEmit)" if count_stages else "tile kernel",
            "count_stages_ms": [round(x, 3) for x in count_stages], "count_tile_kernel_ms": ms_count_tile,
+           "count_without_ordered_emit_ms": ms_count_scatter,
            "count_ranges_equal_to_tile_kernel_all_queries": tile_same,
            "every_query_found_at_its_origin": ok_all, "index_build_gpu_ms": build_ms, "scaling": "weak",
            "gather": ("copy-engine peer writes of (position, contig, offset) rows into rank 0's buffer, inside the timed step"

@@ -104,11 +104,14 @@ def test_sweep_matches_oracle(small_indexes, name):
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
         # range output: every query's final (sp, ep) as the reference leaves it, incl. the pair a dying search stops at;
         # with 32-bit positions and with the 64-bit-position passes an index beyond 2^32 positions takes
-        for wide in (0, 1):
-            gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=4, sweep_profile=1, sweep_wide=wide)
+        # (sweep_ordered_emit: the last pass's survivors leave through sweepEmit, bucketed by id quarter, or straight from the pass)
+        for wide, emit, items in ((0, 1, 4), (0, 0, 4), (1, 1, 4), (1, 0, 4), (0, 1, 1), (0, 1, 8)):
+            gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=items, sweep_first_items=items, sweep_profile=1,
+                           sweep_wide=wide, sweep_ordered_emit=emit)
             counts, ranges = gpu.count(letters, fixed_len=length, want_ranges=True)
             assert gpu.sweep_stage_ms(), "range output did not take the sweep path"
-            assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num, wide)
+            assert np.array_equal(counts, o_counts) and np.array_equal(ranges, o_ranges), (name, length, num, wide, emit, items)
+        gpu.set_tuning(sweep_items=4, sweep_first_items=4, sweep_wide=0, sweep_ordered_emit=1)
         gpu.set_tuning(sweep_min_queries=-1)
         assert np.array_equal(gpu.count(letters, fixed_len=length), o_counts)
     gpu.close()

@@ -867,10 +867,10 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   const bool wide = !AMINO && (c->ix.bwtLength >= 0xFFFFFFF0ull || c->sweepWide);
   const bool rec12 = !AMINO && !variable && !wide && steps <= 8 && c->sweepRecord12;
   uint32_t refills = 0;
-  // Ordered emit (sweepStep<EMIT>, sweepEmit): range output of a fixed-length nucleotide batch small enough for a quarter
-  // of its counts and ranges (20 B per query) to stay in L2 while it is written.
-  const bool emit = !AMINO && !variable && !rec12 && dRanges && steps >= 1 && c->sweepOrderedEmit && n >= 4 && n <= (1ull << 24);
-  const uint32_t emitDiv = (uint32_t)((n + 3) / 4);
+  // Ordered emit (sweepStep<EMIT>, sweepEmit): range output of a fixed-length nucleotide batch small enough for a
+  // sixteenth of its counts and ranges (20 B per query) to stay in L2 while it is written.
+  const bool emit = !AMINO && !variable && !rec12 && dRanges && steps >= 1 && c->sweepOrderedEmit && n <= (1ull << 24);
+  const uint32_t emitDiv = (uint32_t)((n + kSweepEmitBuckets - 1) / kSweepEmitBuckets);  // (16 * emitDiv <= n + 15 <= w.cap)
   auto launchPass = [&](auto first, auto items, auto small, auto var, auto big, auto ordered, uint32_t pass) -> int {
     constexpr bool FIRST = decltype(first)::value;
     constexpr int ITEMS = decltype(items)::value;
@@ -922,8 +922,8 @@ static int sweepCountBatch(awfm_gpu_ctx *c, Lane &L, const uint8_t *dLetters, co
   auto emitSurvivors = [&](uint32_t pass) -> int {  // after the last pass (pass + 1 == steps)
     if (!emit || pass + 1 != steps) return AWFM_GPU_OK;
     const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->numSMs * 8);
-    if (wide) sweepEmit<true><<<grid, 256, 0, st>>>(gen(pass & 1, pass), dCounts, dRanges);
-    else sweepEmit<false><<<grid, 256, 0, st>>>(gen(pass & 1, pass), dCounts, dRanges);
+    if (wide) sweepEmit<true><<<grid, 256, 0, st>>>(gen(pass & 1, pass), emitDiv, dCounts, dRanges);
+    else sweepEmit<false><<<grid, 256, 0, st>>>(gen(pass & 1, pass), emitDiv, dCounts, dRanges);
     CU(cudaGetLastError());
     refills++;
     return AWFM_GPU_OK;

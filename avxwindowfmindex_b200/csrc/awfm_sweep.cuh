@@ -599,12 +599,14 @@ __device__ __forceinline__ uint32_t aminoSweepRank(const DevIndex &ix, uint32_t 
 // WIDE (nucleotide indexes of 2^32 .. 2^40 positions): 64-bit positions in registers; a record is still 16 bytes —
 // {sp bits 0-31, sp bits 32-39 | range width << 8, id, letters} — because a range only narrows from step to step: a
 // query whose SEED range is wider than 2^24 - 2 leaves for the irregular list once, in the first pass.
+constexpr uint32_t kSweepEmitBits = 4, kSweepEmitBuckets = 1u << kSweepEmitBits;
 // EMIT (the LAST pass of a fixed-length nucleotide batch with range output and many survivors — locate workloads): a
 // query that has prepended all its letters does not store its count and range at [id] from here — ids are in no order
 // by now, so that is two scattered partial-sector stores per query, each a read-modify-write in DRAM (cfg 5, 10 M
 // 32-mers all found: 0.70 ms for the last pass against 0.145 for any other) — but is appended once more, to the
-// bucket of the QUARTER of the id space its id lies in (id / emitDiv).  sweepEmit then writes the buckets out in order:
-// one quarter's slice of counts and ranges (20 B per query) stays in L2 until its sectors are complete.
+// bucket of the SIXTEENTH of the id space its id lies in (id / emitDiv; a slice of n/16 ids holds at most that many
+// records, so the slices lie flat in the output generation's first array).  sweepEmit then writes the slices out in
+// order: one slice of counts and ranges (20 B per query) stays in L2 until its sectors are complete.
 template <bool FIRST, int kSweepItems, bool AMINO = false, bool REC12 = false, bool VARLEN = false, bool WIDE = false,
           bool EMIT = false>
 __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThreads == 256 && kSweepItems <= 4) ? 4 : 0)
@@ -622,10 +624,12 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
   using Pos = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
   constexpr uint32_t kSweepTile = kSweepThreads * kSweepItems;
   constexpr uint32_t NB = SweepAlphabet<AMINO>::kCard, LB = SweepAlphabet<AMINO>::kLetterBits;
+  // output buckets: one per letter; EMIT: kSweepEmitBuckets slices of the id space, laid out flat (see sweepEmit)
+  constexpr uint32_t NBO = EMIT ? kSweepEmitBuckets : NB, LBO = EMIT ? kSweepEmitBits : LB;
   constexpr uint32_t kLetterMask = (1u << LB) - 1u;
   constexpr uint32_t kLineU4 = AMINO ? kAminoLineU4 : kSectorU4;
-  __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][NB];
-  __shared__ uint32_t bucketBase[NB];
+  __shared__ uint32_t warpCount[kSweepItems][kSweepThreads / 32][NBO];
+  __shared__ uint32_t bucketBase[NBO];
   __shared__ uint32_t inPrefixSh[AMINO ? 33 : 1];  // amino: records before bucket b, padded with the total
   __shared__ uint16_t codeCareSh[AMINO ? 32 : 1];  // amino: kAminoCodeCare, lanes index it with different letters
   // first pass only: tile-local counting sort on the key bits the global radix sort left unordered
@@ -895,10 +899,10 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
           }
         }
       }
-      bucket[it] = NB;  // no output
+      bucket[it] = NBO;  // no output
       if (valid) {
         if constexpr (EMIT) {  // (launched for the last pass only) count and range leave through sweepEmit
-          bucket[it] = min(id[it] / emitDiv, NB - 1u);
+          bucket[it] = min(id[it] / emitDiv, NBO - 1u);
         } else {
           const bool last = VARLEN ? (steps <= 1 || rest[it] == 1u) : steps <= 1;
           if (last && ranges) ranges[id[it]] = make_uint4((uint32_t)sp[it], (uint32_t)((uint64_t)sp[it] >> 32), (uint32_t)ep[it],
@@ -913,17 +917,17 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
     uint32_t rank[kSweepItems];  // (warpCount / bucketBase of the previous tile were consumed before this tile's ticket barrier)
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
-      if constexpr (AMINO) {
+      if constexpr (AMINO || EMIT) {
         const uint32_t b = bucket[it];
-        unsigned mine = __ballot_sync(0xFFFFFFFFu, b < NB), forLane = mine;  // lanes in my bucket / in bucket `lane`
+        unsigned mine = __ballot_sync(0xFFFFFFFFu, b < NBO), forLane = mine;  // lanes in my bucket / in bucket `lane`
 #pragma unroll
-        for (uint32_t bit = 0; bit < LB; bit++) {
+        for (uint32_t bit = 0; bit < LBO; bit++) {
           const unsigned m = __ballot_sync(0xFFFFFFFFu, (b >> bit) & 1u);
           mine &= ((b >> bit) & 1u) ? m : ~m;
           forLane &= ((lane >> bit) & 1u) ? m : ~m;
         }
         rank[it] = __popc(mine & lanesBelow);
-        if (lane < NB) warpCount[it][warp][lane] = __popc(forLane);
+        if (lane < NBO) warpCount[it][warp][lane] = __popc(forLane);
       } else {
         const unsigned live = __ballot_sync(0xFFFFFFFFu, bucket[it] < 4u);
         const unsigned bit0 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 1u), bit1 = __ballot_sync(0xFFFFFFFFu, bucket[it] & 2u);
@@ -955,7 +959,7 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
       }
     }
 #endif
-    if (threadIdx.x < NB) {
+    if (threadIdx.x < NBO) {
       uint32_t run = 0;
 #pragma unroll
       for (int it = 0; it < kSweepItems; it++)
@@ -971,10 +975,11 @@ __global__ void __launch_bounds__(kSweepThreads, (!AMINO && !WIDE && kSweepThrea
 #pragma unroll
     for (int it = 0; it < kSweepItems; it++) {
       const uint32_t b = bucket[it];
-      if (b < NB) {
+      if (b < NBO) {
         const uint32_t r = bucketBase[b] + warpCount[it][warp][b] + rank[it];
-        uint4 *dst = AMINO ? out.arr[b >> 1] : ((b & 2u) ? out1 : out0);
-        const uint32_t slot = (b & 1u) ? outLast - r : r;
+        // (EMIT: slice b holds ids [b * emitDiv, (b + 1) * emitDiv), so at most emitDiv records: slices lie flat in array 0)
+        uint4 *dst = EMIT ? out0 : AMINO ? out.arr[b >> 1] : ((b & 2u) ? out1 : out0);
+        const uint32_t slot = EMIT ? b * emitDiv + r : (b & 1u) ? outLast - r : r;
         if constexpr (REC12) {
           reinterpret_cast<uint2 *>(dst)[slot] = make_uint2((uint32_t)sp[it], id[it]);
           reinterpret_cast<uint32_t *>(reinterpret_cast<uint2 *>(dst) + out.cap)[slot] = (uint32_t)(ep[it] - sp[it]) | (rest[it] << 16);
@@ -1005,21 +1010,21 @@ static __global__ void __launch_bounds__(256) sweepRefill(const __grid_constant_
   }
 }
 
-// sweepEmit: the survivors of an EMIT last pass, bucketed by the quarter of the id space, leave for counts[id] and
-// ranges[id].  The grid walks the buckets in order (a window of gridDim.x * 256 consecutive records at any moment), so
-// the stores of one moment fall into one quarter of the two output arrays.
+// sweepEmit: the survivors of an EMIT last pass, in kSweepEmitBuckets slices of the id space (slice b: gen.count[b]
+// records from slot b * emitDiv of array 0), leave for counts[id] and ranges[id].  The grid walks the slices in order (a
+// window of gridDim.x * 256 consecutive slots at any moment), so the stores of one moment fall into one slice of the two
+// output arrays.
 template <bool WIDE>
-static __global__ void __launch_bounds__(256) sweepEmit(const __grid_constant__ SweepRecs gen, uint32_t *__restrict__ counts,
-                                                        uint4 *__restrict__ ranges) {
-  const uint32_t c0 = gen.count[0], c1 = gen.count[1], c2 = gen.count[2], c3 = gen.count[3];
-  const uint32_t before1 = c0, before2 = c0 + c1, before3 = before2 + c2, total = before3 + c3;
-  const uint32_t last = (uint32_t)gen.cap - 1u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const bool ge1 = i >= before1, ge2 = i >= before2, ge3 = i >= before3;  // buckets 0/2 grow up, 1/3 down (sweepStep)
-    const uint32_t first = ge3 ? before3 : ge2 ? before2 : ge1 ? before1 : 0u;
-    const bool odd = ge1 != ge2 || ge3;
-    const uint32_t r = i - first;
-    const uint4 rec = __ldg(gen.arr[ge2 ? 1 : 0] + (odd ? last - r : r));
+static __global__ void __launch_bounds__(256) sweepEmit(const __grid_constant__ SweepRecs gen, uint32_t emitDiv,
+                                                        uint32_t *__restrict__ counts, uint4 *__restrict__ ranges) {
+  __shared__ uint32_t sliceCount[kSweepEmitBuckets];
+  if (threadIdx.x < kSweepEmitBuckets) sliceCount[threadIdx.x] = gen.count[threadIdx.x];
+  __syncthreads();
+  const uint32_t slots = kSweepEmitBuckets * emitDiv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += gridDim.x * blockDim.x) {
+    const uint32_t b = i / emitDiv;
+    if (i - b * emitDiv >= sliceCount[b]) continue;
+    const uint4 rec = __ldg(gen.arr[0] + i);
     uint64_t sp, width;
     if constexpr (WIDE) sp = (uint64_t)rec.x | ((uint64_t)(rec.y & 0xFFu) << 32), width = rec.y >> 8;
     else sp = rec.x, width = rec.y;

@@ -141,8 +141,8 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * deeper seed tables), "sweep_compact_pairs" (1, the default: between the pack kernel and the second bucket pass a pair
  * travels as ONE 8-byte word — key, remaining letters and, once the first digit has left the key, the query id —
  * whenever those fit 64 bits, instead of a 4-byte key and an 8-byte payload; 0: always 4 + 8 bytes), "sweep_ordered_emit"
- * (1, the default: with range output and at most 2^24 queries the last pass hands its survivors, bucketed by the quarter
- * of the id space, to a kernel that writes counts and ranges quarter by quarter; 0: scattered straight from the pass),
+ * (1, the default: with range output and at most 2^24 queries the last pass hands its survivors, bucketed by the sixteenth
+ * of the id space, to a kernel that writes counts and ranges slice by slice; 0: scattered straight from the pass),
  * "sweep_record12" (1: live records of nucleotide batches with at most 8 letters left of the seed
  * travel as 12 bytes — 16-bit range width, 16 bits of letters — and queries whose seed range is wider than 65534 take
  * the generic per-query search; 0, the default: 16-byte records — the passes are latency-bound, not byte-bound, and the

@@ -104,7 +104,7 @@ def test_sweep_matches_oracle(small_indexes, name):
             assert len(gpu.sweep_stage_ms()) == 3 + max(length - k, 1), "the batch did not take the sweep path"
         # range output: every query's final (sp, ep) as the reference leaves it, incl. the pair a dying search stops at;
         # with 32-bit positions and with the 64-bit-position passes an index beyond 2^32 positions takes
-        # (sweep_ordered_emit: the last pass's survivors leave through sweepEmit, bucketed by id quarter, or straight from the pass)
+        # (sweep_ordered_emit: the last pass's survivors leave through sweepEmit, bucketed by slices of the id space, or straight from the pass)
         for wide, emit, items in ((0, 1, 4), (0, 0, 4), (1, 1, 4), (1, 0, 4), (0, 1, 1), (0, 1, 8)):
             gpu.set_tuning(sweep_sort_bits=32, sweep_local_bits=-1, sweep_items=items, sweep_first_items=items, sweep_profile=1,
                            sweep_wide=wide, sweep_ordered_emit=emit)

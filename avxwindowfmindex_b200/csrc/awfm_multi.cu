@@ -71,7 +71,7 @@ struct GroupDevice {
 
 struct awfm_gpu_group {
   std::vector<std::unique_ptr<GroupDevice>> dev;
-  int64_t chunkQueries = 3ll << 23, minShard = 1ll << 16, windowHits = 1ll << 22;
+  int64_t chunkQueries = 3ll << 23, minShard = 1ll << 16, windowHits = 1ll << 21;
   std::mutex mu;  // one packed-batch call at a time per group
 };
 

@@ -885,6 +885,12 @@ def leg_cfg5(env):
                              "ms_per_step": 1e3 * t_step, "located_and_mapped_hits_per_s": all_hits / t_step,
                              "queries_per_s": world * n / t_step, "h2d_bytes_per_step": int(pin.array.nbytes),
                              "d2h_bytes_per_step": (n + 1) * 8 + 24 * hits, "bit_exact_vs_device_path": same}
+        if world == 1:  # hits per walk window of the pipeline (default 2^22): smaller windows shorten fill and drain
+            sweep = {}
+            for wh in (1 << 20, 1 << 21, 1 << 22):
+                group.set_tuning(packed_window_hits=wh)
+                sweep[str(wh)] = 1e3 * min(wall_times(call, reps=3, warm=1))
+            out["e2e_packed"]["ms_by_window_hits"] = sweep
         for p in (pin, ph, pp, ps, pl):
             p.close()
         group.close()
@@ -1295,7 +1301,7 @@ def run_ours(args):
         def reset_counts(v=0):
             ent_counts[:ne] = v
 
-        times = wall_times(lambda: lib.awFmParallelSearchCount(ip, sl.ptr, threads), reps=args.e2e_steps, warm=0, before=reset_counts)
+        times = wall_times(lambda: lib.awFmParallelSearchCount(ip, sl.ptr, threads), reps=max(args.e2e_steps, 5), warm=0, before=reset_counts)
         assert lib.awFmGpuLastCountStatus() == abi.AwFmSuccess
         times_poisoned = wall_times(lambda: lib.awFmParallelSearchCount(ip, sl.ptr, threads), reps=2, warm=0,
                                     before=lambda: reset_counts(0xFFFFFFFF))
@@ -1306,7 +1312,8 @@ def run_ours(args):
         e2e = {"value": world * ne / t_step, "unit": UNIT, "h2d_bytes_per_step": ne * L, "d2h_bytes_per_step": ne * 4,
                "call": "awFmParallelSearchCount(index, searchList, numThreads) drop-in, host AwFmKmerSearchList "
                        "(32-B entries pointing at query strings laid back to back in page-locked memory)",
-               "host_threads": threads, "ms_per_step": 1e3 * t_step, "search_list_setup_s": round(list_s, 2),
+               "host_threads": threads, "ms_per_step": 1e3 * t_step, "ms_each_call_this_rank": [round(1e3 * t, 2) for t in times],
+               "search_list_setup_s": round(list_s, 2),
                "queries_per_gpu": ne,
                "list_state": "count == 0 in every entry before each timed call (a fresh list); entries whose count is already "
                              "right are not rewritten",

@@ -255,7 +255,7 @@ awfm_gpu_ctx *awfm_gpu_group_context(awfm_gpu_group *group, int i);
 int awfm_gpu_group_set_sequences(awfm_gpu_group *group, const void *metadata, uint64_t numSequences);
 /* keys: "packed_chunk_queries" (queries per pipeline chunk of awfm_gpu_group_count/_locate, multiple of 256; default
  * 3 * 2^23), "packed_min_shard" (a device is only given a shard of at least this many queries; default 2^16),
- * "packed_window_hits" (hits per walk window of awfm_gpu_group_locate; default 2^22); any other key is forwarded to
+ * "packed_window_hits" (hits per walk window of awfm_gpu_group_locate; default 2^21); any other key is forwarded to
  * every context (awfm_gpu_ctx_set_tuning). */
 int awfm_gpu_group_set_tuning(awfm_gpu_group *group, const char *key, int64_t value);
 int awfm_gpu_group_get_stats(awfm_gpu_group *group, awfm_gpu_stats *out); /* summed over the devices, last call */

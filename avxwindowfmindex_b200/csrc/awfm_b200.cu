@@ -644,8 +644,14 @@ static bool sweepEligible(const awfm_gpu_ctx *c, const uint8_t *dLetters, const 
   // sweep: 12 M).
   // (with range output every query also pays a scattered 16-B store: the break-even stays where round 1 measured it;
   // with a derived deep seed table the tile kernel has fewer steps left to pay for: twice the batch)
+  // (range output that leaves through the ordered emit — fixed-length nucleotide batches of up to 2^24 queries — costs
+  // less than the scattered stores did: locate's front end for 10 M 16-mers at 3.1 Gbp 1.34 ms through the sweep, 1.41
+  // through the tile kernel; threshold at three quarters of the old one)
   const bool deepActive = !dOffsets && c->ix.deepSeedK && len >= c->ix.deepSeedK;
-  return n >= std::max<uint64_t>(1ull << 22, c->ix.bwtLength >> (c->ix.amino ? 6 : dRanges ? 8 : 9)) << (deepActive ? 1 : 0);
+  const bool emits = dRanges && !c->ix.amino && !dOffsets && c->sweepOrderedEmit && n <= (1ull << 24);
+  const uint64_t perLine = emits ? (c->ix.bwtLength >> 9) + (c->ix.bwtLength >> 10)
+                                 : c->ix.bwtLength >> (c->ix.amino ? 6 : dRanges ? 8 : 9);
+  return n >= std::max<uint64_t>(1ull << 22, perLine) << (deepActive ? 1 : 0);
 }
 
 static int ensureSweep(awfm_gpu_ctx *c, Lane &L, uint64_t n, int arrays) {

@@ -572,8 +572,16 @@ def locate_leg(env, gpu, arrays, d_lq, nl, Ll, label, reference_sample=1_000_000
     # leaves it), for the record
     ms_count = env.event_ms(lambda: gpu.count_device(d_lq.data_ptr(), None, Ll, nl, d_lc.data_ptr(), d_lr.data_ptr(), stream), reps=3)
     ms_scan = env.event_ms(lambda: gpu.scan_ranges_device(d_lr.data_ptr(), nl, d_lh.data_ptr(), stream), reps=3)
+    # the front end through the sweep whatever the batch size (the automatic choice for this batch is in stages_ms)
+    auto = 0 if env.args.count_path == "auto" else (1 if env.args.count_path == "sweep" else -1)
+    gpu.set_tuning(sweep_min_queries=1)
+    ms_prepare_sweep = env.event_ms(prepare, reps=3)
+    gpu.set_tuning(sweep_min_queries=-1)
+    ms_prepare_tile = env.event_ms(prepare, reps=3)
+    gpu.set_tuning(sweep_min_queries=auto)
     prepare()
-    loc = {"workload": label, "queries": nl, "hits": hits, "locate_ms": ms_all, "located_hits_per_s": hits / ms_all * 1e3,
+    loc = {"workload": label, "queries": nl, "hits": hits, "locate_ms": ms_all,
+           "prepare_ms_by_count_path": {"sweep": ms_prepare_sweep, "tile_kernel": ms_prepare_tile}, "located_hits_per_s": hits / ms_all * 1e3,
            "locate_queries_per_s": nl / ms_all * 1e3,
            "stages_ms": {"search+ranges_of_hits+scan (awfm_gpu_locate_prepare_device)": ms_prepare, "expand+walk": ms_walk},
            "separate_calls_ms": {"count_with_all_ranges": ms_count, "scan_of_ranges": ms_scan},

@@ -129,8 +129,8 @@ int awfm_gpu_ctx_get_stats(const awfm_gpu_ctx *ctx, awfm_gpu_stats *out);
  * a power of two between 2^16 and 2^19 that leaves every device about 48 chunks), "locate_inline_hits" (a
  * chunk with more hits is finished through windows), "locate_window_hits" (hits per such window).
  * Sweep count path (csrc/awfm_sweep.cuh; large batches of either alphabet, fixed or variable length, counts and ranges):
- * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per two 128-B lines of the index) queries and no
- * derived deep seed table; n > 0 = batches of at least n queries; -1 = never), "sweep_sort_bits" (top bits of the seed
+ * "sweep_min_queries" (0 = automatic: batches of at least max(2^22, one query per two 128-B lines of the index) queries — with range
+ * output one per line, three per four lines when the ranges leave through the ordered emit — and no derived deep seed table; n > 0 = batches of at least n queries; -1 = never), "sweep_sort_bits" (top bits of the seed
  * index the radix sort orders, default 32 = all but the low "sweep_local_bits"), "sweep_local_bits" (0..8, or -1 =
  * automatic, the default: low bits ordered inside each tile of the first pass instead), "sweep_items" /
  * "sweep_first_items" (records per thread and tile of the later passes / of the first pass: 1, 2, 4, 8; default 4),
